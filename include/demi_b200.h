@@ -1,0 +1,203 @@
+/*
+ * demi_b200.h — C ABI of the B200 schedule-space exploration engine.
+ *
+ * This is the drop-in boundary for the hot path of NetSys/demi (DEMi).  The
+ * reference has no FFI: the path sits behind two Scala traits,
+ *   trait Scheduler   (src/main/scala/verification/schedulers/Scheduler.scala:13-104)
+ *   trait TestOracle  (src/main/scala/verification/minification/TestOracle.scala:30-55)
+ * and the scheduler-specific driver entry points
+ *   RandomScheduler.explore/test        (schedulers/RandomScheduler.scala:226-272, :597-612)
+ *   STSScheduler.test                   (schedulers/STSScheduler.scala:199-310)
+ *   DDMin.minimize                      (minification/DeltaDebugging.scala:27-62)
+ *   DPORwHeuristics.test                (schedulers/DPORwHeuristics.scala:1193-1242)
+ * Each entry point below names the reference method it replaces.  A JVM host
+ * binds these through a ~150-line JNI shim (jni/DemiNative.c).
+ *
+ * Conventions (all entry points):
+ *   - return int32 status: 0 = DEMI_OK, <0 = error; text via demi_last_error().
+ *   - plain pointers + sizes, little-endian PODs, no C++/torch types.
+ *   - blocking, single caller per handle (matches TestOracle.test / explore()).
+ *   - host buffers are caller-owned and only borrowed for the call; the
+ *     library owns all device memory.  "_dev" variants take device pointers
+ *     and a CUDA stream and do not synchronise.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns DEMI_ERR_NO_DEVICE.
+ */
+#ifndef DEMI_B200_H
+#define DEMI_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+#define DEMI_OK                 0
+#define DEMI_ERR_INVALID       -1   /* IllegalArgumentException analogue        */
+#define DEMI_ERR_STATE         -2   /* IllegalStateException analogue (e.g. no model / no invariant) */
+#define DEMI_ERR_NO_DEVICE     -3   /* no CUDA device / extension cannot run     */
+#define DEMI_ERR_CUDA          -4   /* CUDA runtime error (text in last_error)   */
+#define DEMI_ERR_CAPACITY      -5   /* an on-chip structure overflowed           */
+#define DEMI_ERR_REPLAY        -6   /* ReplayException analogue (strict replay diverged) */
+
+/* ------------------------------------------------------------ data model   */
+
+/* Actor index of the "deadLetters" pseudo-sender (externals and timers,
+ * RandomScheduler.scala:288-290) and of the "Timer" alias recorded on
+ * MsgSend events (RandomScheduler.scala:319). */
+#define DEMI_DEADLETTERS 0xFFu
+#define DEMI_TIMER_SND   0xFEu
+#define DEMI_MAX_ACTORS  32
+
+/* One message: (sender, receiver, fingerprint).  The fingerprint of the
+ * reference (MessageFingerprints.scala:9-124) is (type,p0,p1) here, so
+ * fingerprint equality is integer equality. 12 bytes. */
+typedef struct demi_msg {
+  uint8_t  src;     /* actor index or DEMI_DEADLETTERS                       */
+  uint8_t  dst;     /* actor index                                           */
+  uint8_t  type;    /* model-defined message type                            */
+  uint8_t  flags;   /* DEMI_MF_*                                             */
+  uint32_t p0, p1;  /* model-defined payload                                 */
+} demi_msg;
+#define DEMI_MF_EXTERNAL 0x1u  /* enqueued via Send external (ExternalEventInjector.scala:258-268) */
+#define DEMI_MF_TIMER    0x2u  /* enqueued via handle_timer (ExternalEventInjector.scala:282-297) */
+
+/* External events (ExternalEvents.scala:62-91).  CodeBlock / WaitCondition /
+ * HardKill carry JVM closures or live ActorCells and are out of scope. */
+enum {
+  DEMI_EXT_START = 1,            /* Start(name)            a = actor          */
+  DEMI_EXT_KILL = 2,             /* Kill(name) = isolate   a = actor          */
+  DEMI_EXT_SEND = 3,             /* Send(name, msg)        a = dst, type/p0/p1*/
+  DEMI_EXT_WAIT_QUIESCENCE = 4,  /* WaitQuiescence()                          */
+  DEMI_EXT_PARTITION = 5,        /* Partition(a,b)                            */
+  DEMI_EXT_UNPARTITION = 6       /* UnPartition(a,b)                          */
+};
+typedef struct demi_ext_event {
+  uint8_t  kind, a, b, type;
+  uint32_t p0, p1;
+  uint32_t id;      /* stable id == UniqueExternalEvent._id (ExternalEvents.scala:14-31) */
+} demi_ext_event;   /* 16 bytes */
+
+/* Recorded execution event == one element of EventTrace.events
+ * (EventTrace.scala:20, :96-110; AuxilaryTypes.scala:34-73). 16 bytes. */
+enum {
+  DEMI_EV_MSG_SEND = 1,          /* UniqueMsgSend(MsgSend(snd,rcv,msg), uniq)  */
+  DEMI_EV_MSG_EVENT = 2,         /* UniqueMsgEvent(MsgEvent(snd,rcv,msg), uniq)*/
+  DEMI_EV_SPAWN = 3,             /* SpawnEvent (from Start)                    */
+  DEMI_EV_KILL = 4,              /* KillEvent                                  */
+  DEMI_EV_PARTITION = 5,         /* PartitionEvent                             */
+  DEMI_EV_UNPARTITION = 6,       /* UnPartitionEvent                           */
+  DEMI_EV_BEGIN_WAIT_QUIESCENCE = 7,
+  DEMI_EV_QUIESCENCE = 8
+};
+typedef struct demi_event {
+  uint8_t  kind, src, dst, type;
+  uint32_t p0, p1;
+  uint16_t uniq;    /* Uniq id: ties a MsgSend to its MsgEvent (per-execution, from 1) */
+  uint16_t node;    /* Unique id in the DepTracker tree (per-execution, root = 0)      */
+} demi_event;
+
+/* Built-in actor models ("compiled, data-only" stand-ins for the application's
+ * receive()).  */
+enum {
+  DEMI_MODEL_PINGPONG3 = 1,
+  DEMI_MODEL_RAFT5 = 2,
+  DEMI_MODEL_BCAST32 = 3
+};
+
+/* Engine-wide configuration == SchedulerConfig (SchedulerConfig.scala:9-37)
+ * restricted to the fields that are meaningful without a JVM. */
+typedef struct demi_config {
+  int32_t  device;            /* CUDA device ordinal                           */
+  int32_t  model;             /* DEMI_MODEL_*                                   */
+  uint32_t model_flags;       /* model-defined (raft5: seeded-bug bits)        */
+  uint32_t blocked_mask;      /* Instrumenter.blockedActors as a bitmask       */
+  int32_t  ignore_timers;     /* SchedulerConfig.ignoreTimers                  */
+  int32_t  reserved[3];
+} demi_config;
+
+/* Per-prefix result of one RandomScheduler execution. 32 bytes. */
+typedef struct demi_fuzz_result {
+  uint32_t violation;     /* ViolationFingerprint code, 0 = none              */
+  uint32_t steps;         /* messagesScheduledSoFar at the end                */
+  uint64_t state_hash;    /* hash of all actor states at the end              */
+  uint64_t trace_hash;    /* order-sensitive hash of the whole EventTrace + dep tree */
+  uint16_t n_nodes;       /* DepTracker nodes allocated (incl. root)          */
+  uint16_t n_events;      /* EventTrace length                                */
+  uint16_t max_pending;   /* high-water mark of the pending set               */
+  uint16_t status;        /* 0 ok, else DEMI_PS_*                             */
+} demi_fuzz_result;
+#define DEMI_PS_OK              0
+#define DEMI_PS_PENDING_OVF     1
+#define DEMI_PS_QUEUE_OVF       2
+#define DEMI_PS_NODE_OVF        3
+#define DEMI_PS_EVENT_OVF       4
+
+typedef struct demi_fuzz_params {
+  int64_t  seed_base;          /* prefix i runs FullyRandom(seed = seed_base + i) (RandomScheduler.scala:635-639) */
+  uint64_t n_prefixes;
+  int32_t  max_messages;       /* RandomScheduler.setMaxMessages (RandomScheduler.scala:54-57) */
+  int32_t  invariant_check_interval; /* RandomScheduler ctor arg (RandomScheduler.scala:43) */
+  uint32_t looking_for;        /* 0 = any violation (explore(_, None)); else only this code */
+  uint32_t reserved;
+} demi_fuzz_params;
+
+typedef struct demi_perf {
+  uint64_t prefixes;           /* units processed by the last batch call       */
+  uint64_t deliveries;         /* sum of steps                                 */
+  uint64_t violations;
+  double   kernel_ms;          /* CUDA-event time of the kernel(s)             */
+  double   h2d_ms, d2h_ms;
+  uint64_t h2d_bytes, d2h_bytes;
+  uint32_t kernel_launches;
+  uint32_t reserved;
+} demi_perf;
+
+typedef struct demi_handle demi_handle;
+
+/* ---------------------------------------------------------------- lifecycle */
+const char* demi_version(void);
+/* Last error text for this handle (or for the failed demi_create if h==NULL). */
+const char* demi_last_error(const demi_handle* h);
+int32_t demi_device_count(void);
+
+/* new RandomScheduler/STSScheduler/DPORwHeuristics(schedulerConfig, ...) */
+int32_t demi_create(const demi_config* cfg, demi_handle** out);
+void    demi_destroy(demi_handle* h);
+
+/* The external-event program == the `_trace: Seq[ExternalEvent]` argument of
+ * RandomScheduler.explore (RandomScheduler.scala:234) / TestOracle.test. */
+int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, uint32_t n);
+
+/* ------------------------------------------------------------- random fuzz */
+/* RunnerUtils.fuzz inner loop (RunnerUtils.scala:75-91): n_prefixes independent
+ * `new RandomScheduler(cfg, 1, interval, new FullyRandom(seed=seed_base+i)).explore(trace)`
+ * executions.  `out` (host) receives n_prefixes records. */
+int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p,
+                        demi_fuzz_result* out_host);
+/* Same, results stay in HBM: `out_dev` is a device pointer with room for
+ * n_prefixes records; `stream` is a cudaStream_t (0 = default). No sync. */
+int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p,
+                            void* out_dev, void* stream);
+/* Device-side summary of a finished batch without copying the records:
+ * number of violating prefixes and sum of steps. */
+int32_t demi_fuzz_summary_dev(demi_handle* h, const void* results_dev, uint64_t n,
+                              void* stream, uint64_t* n_violations, uint64_t* sum_steps);
+/* Re-run one seed in recording mode and return its EventTrace
+ * (== the EventTrace returned by explore(), RandomScheduler.scala:255-259).
+ * `dep_parent[node]` (cap_nodes entries, may be NULL) receives the DepTracker
+ * tree (DepTracker.scala:111-116).  n_events and n_nodes receive the counts. */
+int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, int64_t seed,
+                        demi_event* events, uint32_t cap_events, uint32_t* n_events,
+                        uint16_t* dep_parent, uint32_t cap_nodes, uint32_t* n_nodes,
+                        demi_fuzz_result* result);
+
+/* ------------------------------------------------------------- statistics */
+int32_t demi_stats(const demi_handle* h, demi_perf* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMI_B200_H */

@@ -1,0 +1,84 @@
+/*
+ * demi_limits.h — capacity rules and hash constants that are part of the
+ * engine's observable behaviour (a prefix that overflows a structure reports
+ * DEMI_PS_*_OVF instead of a result), so the CUDA engine and the CPU oracle
+ * must apply the same numbers.  Interface constants only; no algorithm here.
+ */
+#ifndef DEMI_LIMITS_H
+#define DEMI_LIMITS_H
+
+#include <stdint.h>
+
+/* messagesToSend / timersToResend / justScheduledTimers / timer registry /
+ * timersCancelledThisStep capacities (entries). */
+#define DEMI_TIMERSET_CAP 16
+
+/* Pending-set capacity class for a (model, max_messages) pair: smallest power
+ * of two >= the model's worst-case bound, clamped to [64, 8192]. */
+static inline uint32_t demi_pow2_at_least(uint32_t x, uint32_t lo, uint32_t hi) {
+  uint32_t c = lo;
+  while (c < x && c < hi) c <<= 1;
+  return c;
+}
+
+/* Worst-case pending bound per model (see DESIGN.md §3 for the derivations):
+ *  pingpong3: every external Send may be pending at once  -> n_ext_sends + 8
+ *  raft5:     10 timers + net +4 per delivery              -> 16 + 4*(max_messages+1)
+ *  bcast32:   net +30 per delivery                         -> 8 + 31*(max_messages+1) */
+static inline uint32_t demi_pending_bound(int model, int32_t max_messages, uint32_t n_ext_sends) {
+  uint32_t d = (max_messages < 0) ? 0u : (uint32_t)max_messages;
+  if (d > 100000u) d = 100000u;
+  switch (model) {
+    case 1: return n_ext_sends + 8u;
+    case 2: return n_ext_sends + 16u + 4u * (d + 1u);
+    case 3: return n_ext_sends + 8u + 31u * (d + 1u);
+    default: return 64u;
+  }
+}
+static inline uint32_t demi_pending_cap(int model, int32_t max_messages, uint32_t n_ext_sends) {
+  return demi_pow2_at_least(demi_pending_bound(model, max_messages, n_ext_sends), 64u, 8192u);
+}
+/* messagesToSend capacity: externals of one segment + timers. */
+static inline uint32_t demi_tosend_cap(uint32_t n_ext_sends) {
+  return demi_pow2_at_least(n_ext_sends + DEMI_TIMERSET_CAP, 32u, 1024u);
+}
+/* DepTracker node capacity: one node per enabled message + root. u16 ids. */
+static inline uint32_t demi_node_cap(uint32_t pending_cap) {
+  uint32_t c = 2u * pending_cap + 64u;
+  return c > 65535u ? 65535u : c;
+}
+
+/* ---- hashes ---------------------------------------------------------------
+ * Order-sensitive and cheap on a GPU: a 64-bit SUM of per-item terms; each
+ * term is two independent 32-bit multiply-xor hashes (lo | hi<<32) of the
+ * item's words and its sequence number.  32-bit IMADs only. */
+#if defined(__CUDACC__)
+#define DEMI_HD __host__ __device__ __forceinline__
+#else
+#define DEMI_HD static inline
+#endif
+
+DEMI_HD uint32_t demi_fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+DEMI_HD uint64_t demi_hash6(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+  uint32_t lo = (a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (c * 0xC2B2AE3Du) ^
+                (d * 0x27D4EB2Fu) ^ (e * 0x165667B1u) ^ (f * 0xD3A2646Du);
+  uint32_t hi = (a * 0xFD7046C5u) ^ (b * 0xB55A4F09u) ^ (c * 0x2545F491u) ^
+                (d * 0x9FB21C65u) ^ (e * 0x6C8E9CF5u) ^ (f * 0x7FEB352Du);
+  return (uint64_t)demi_fmix32(lo + 0x6A09E667u) | ((uint64_t)demi_fmix32(hi + 0xBB67AE85u) << 32);
+}
+/* One EventTrace element: words as laid out in demi_event (w0 = kind | src<<8 |
+ * dst<<16 | type<<24, w3 = uniq | node<<16), seq = position in the trace,
+ * parent = DepTracker parent of `node` for sends (else 0). */
+DEMI_HD uint64_t demi_event_term(uint32_t w0, uint32_t p0, uint32_t p1, uint32_t w3,
+                                 uint32_t seq, uint32_t parent) {
+  return demi_hash6(w0, p0, p1, w3, seq, parent);
+}
+/* One 32-bit word of actor state at word index i. */
+DEMI_HD uint64_t demi_state_term(uint32_t word, uint32_t i) {
+  return demi_hash6(word, i, 0x5D, 0, 0, 0);
+}
+
+#endif /* DEMI_LIMITS_H */
