@@ -1,0 +1,90 @@
+"""ctypes binding of the C ABI declared in include/demi_b200.h.
+
+This is the only way Python reaches the engine; the library must exist
+(`python -m demi_b200.build`) — there is no Python or CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdemi_b200.so")
+
+# ---- status codes (include/demi_b200.h)
+OK, ERR_INVALID, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_REPLAY = 0, -1, -2, -3, -4, -5, -6
+DEADLETTERS, TIMER_SND = 0xFF, 0xFE
+MODEL_PINGPONG3, MODEL_RAFT5, MODEL_BCAST32 = 1, 2, 3
+EXT_START, EXT_KILL, EXT_SEND, EXT_WAIT_QUIESCENCE, EXT_PARTITION, EXT_UNPARTITION = 1, 2, 3, 4, 5, 6
+EV_MSG_SEND, EV_MSG_EVENT, EV_SPAWN, EV_KILL, EV_PARTITION, EV_UNPARTITION, EV_BEGIN_WAIT_QUIESCENCE, EV_QUIESCENCE = range(1, 9)
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("model", C.c_int32), ("model_flags", C.c_uint32),
+                ("blocked_mask", C.c_uint32), ("ignore_timers", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class FuzzParams(C.Structure):
+    _fields_ = [("seed_base", C.c_int64), ("n_prefixes", C.c_uint64), ("max_messages", C.c_int32),
+                ("invariant_check_interval", C.c_int32), ("looking_for", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Perf(C.Structure):
+    _fields_ = [("prefixes", C.c_uint64), ("deliveries", C.c_uint64), ("violations", C.c_uint64),
+                ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+EXT_DTYPE = np.dtype([("kind", "u1"), ("a", "u1"), ("b", "u1"), ("type", "u1"),
+                      ("p0", "<u4"), ("p1", "<u4"), ("id", "<u4")])
+EVENT_DTYPE = np.dtype([("kind", "u1"), ("src", "u1"), ("dst", "u1"), ("type", "u1"),
+                        ("p0", "<u4"), ("p1", "<u4"), ("uniq", "<u2"), ("node", "<u2")])
+RESULT_DTYPE = np.dtype([("violation", "<u4"), ("steps", "<u4"), ("state_hash", "<u8"), ("trace_hash", "<u8"),
+                         ("n_nodes", "<u2"), ("n_events", "<u2"), ("max_pending", "<u2"), ("status", "<u2")])
+assert EXT_DTYPE.itemsize == 16 and EVENT_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 32
+
+# every symbol include/demi_b200.h declares
+EXPORTS = [
+    "demi_version", "demi_last_error", "demi_device_count", "demi_create", "demi_destroy",
+    "demi_set_externals", "demi_fuzz_batch", "demi_fuzz_batch_dev", "demi_fuzz_summary_dev",
+    "demi_fuzz_trace", "demi_stats",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libdemi_b200.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "demi_b200: native library %s is missing; run `python -m demi_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.demi_version.restype = C.c_char_p
+    L.demi_last_error.restype = C.c_char_p
+    L.demi_last_error.argtypes = [vp]
+    L.demi_device_count.restype = C.c_int32
+    L.demi_create.restype = C.c_int32
+    L.demi_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.demi_destroy.restype = None
+    L.demi_destroy.argtypes = [vp]
+    L.demi_set_externals.restype = C.c_int32
+    L.demi_set_externals.argtypes = [vp, vp, C.c_uint32]
+    L.demi_fuzz_batch.restype = C.c_int32
+    L.demi_fuzz_batch.argtypes = [vp, C.POINTER(FuzzParams), vp]
+    L.demi_fuzz_batch_dev.restype = C.c_int32
+    L.demi_fuzz_batch_dev.argtypes = [vp, C.POINTER(FuzzParams), vp, vp]
+    L.demi_fuzz_summary_dev.restype = C.c_int32
+    L.demi_fuzz_summary_dev.argtypes = [vp, vp, C.c_uint64, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.demi_fuzz_trace.restype = C.c_int32
+    L.demi_fuzz_trace.argtypes = [vp, C.POINTER(FuzzParams), C.c_int64, vp, C.c_uint32, C.POINTER(C.c_uint32),
+                                  vp, C.c_uint32, C.POINTER(C.c_uint32), vp]
+    L.demi_stats.restype = C.c_int32
+    L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
+    _lib = L
+    return L

@@ -1,0 +1,62 @@
+"""Build the in-tree native libraries.
+
+  demi_b200/libdemi_b200.so  — the CUDA engine + C ABI (nvcc, sm_100a only)
+  oracle/liboracle.so        — the CPU oracle (gcc; test infrastructure only)
+
+Both are git-ignored and travel to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "demi_b200", "csrc")
+LIB = os.path.join(ROOT, "demi_b200", "libdemi_b200.so")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(root, exts):
+    out = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(exts):
+                out.append(os.path.join(d, f))
+    return out
+
+
+def build_engine(force=False, verbose=False):
+    srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    cus = sorted(s for s in srcs if s.endswith(".cu"))
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus
+    subprocess.check_call(cmd, cwd=ROOT)
+    return LIB
+
+
+def build_oracle(force=False):
+    srcs = _sources(ORACLE_DIR, (".c", ".h")) + _sources(os.path.join(ROOT, "include"), (".h",))
+    if not force and _newer(ORACLE_LIB, srcs):
+        return ORACLE_LIB
+    subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle.so"])
+    return ORACLE_LIB
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    print(build_engine(force=force, verbose="-v" in sys.argv))
+    print(build_oracle(force=force))

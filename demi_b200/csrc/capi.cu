@@ -1,0 +1,330 @@
+// capi.cu — the C ABI (include/demi_b200.h) over the CUDA engine.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <climits>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "fuzz_kernel.cuh"
+
+using namespace demi;
+
+static thread_local std::string g_create_error;
+
+struct demi_handle {
+  demi_config cfg{};
+  std::string err;
+  int sm_count = 0;
+  // external program
+  std::vector<demi_ext_event> ext_host;
+  demi_ext_event* ext_dev = nullptr;
+  uint32_t n_ext_sends = 0;
+  // device buffers
+  demi_fuzz_result* results_dev = nullptr; size_t results_cap = 0;
+  uint4* node_scratch = nullptr; size_t node_scratch_bytes = 0;
+  uint4* pend_scratch = nullptr; size_t pend_scratch_bytes = 0;
+  unsigned long long* counters_dev = nullptr;      // [0]=sum_steps [1]=n_violations
+  uint32_t* rec_counts_dev = nullptr;
+  // pinned staging for host transfers
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  demi_perf perf{};
+};
+
+static int32_t fail(demi_handle* h, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+#define CUDA_TRY(h, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return fail((h), DEMI_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ------------------------------------------------------------ kernel table
+constexpr int WARPS = 4;
+typedef void (*kernel_fn)(const KernelArgs);
+struct Variant {
+  int model; uint32_t pcap, tcap; bool pend_global, record;
+  kernel_fn fn; size_t smem_per_warp;
+};
+template <class MODEL, int PCAP, int TCAP, bool PG, bool REC>
+static Variant make_variant() {
+  using M = Machine<MODEL, PCAP, TCAP, PG, REC>;
+  return Variant{MODEL::ID, (uint32_t)PCAP, (uint32_t)TCAP, PG, REC,
+                 fuzz_kernel<MODEL, PCAP, TCAP, PG, REC, WARPS>, sizeof(typename M::Smem)};
+}
+static const std::vector<Variant>& variants() {
+  static const std::vector<Variant> v = {
+    make_variant<PingPong3, 128, 128, false, false>(),
+    make_variant<PingPong3, 8192, 1024, true, false>(),
+    make_variant<PingPong3, 8192, 1024, true, true>(),
+    make_variant<Raft5, 256, 32, false, false>(),
+    make_variant<Raft5, 512, 32, false, false>(),
+    make_variant<Raft5, 8192, 1024, true, false>(),
+    make_variant<Raft5, 8192, 1024, true, true>(),
+    make_variant<Bcast32, 8192, 32, true, false>(),
+    make_variant<Bcast32, 8192, 1024, true, false>(),
+    make_variant<Bcast32, 8192, 1024, true, true>(),
+  };
+  return v;
+}
+static const Variant* pick_variant(int model, uint32_t pcap, uint32_t tcap, bool record) {
+  for (const Variant& v : variants())
+    if (v.model == model && v.record == record && v.pcap >= pcap && v.tcap >= tcap) return &v;
+  return nullptr;
+}
+
+// ---------------------------------------------------------------- lifecycle
+extern "C" const char* demi_version(void) { return "demi_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* demi_last_error(const demi_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int32_t demi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
+  if (!cfg || !out) return fail(nullptr, DEMI_ERR_INVALID, "demi_create: null argument");
+  *out = nullptr;
+  if (cfg->model != DEMI_MODEL_PINGPONG3 && cfg->model != DEMI_MODEL_RAFT5 && cfg->model != DEMI_MODEL_BCAST32)
+    return fail(nullptr, DEMI_ERR_INVALID, "demi_create: unknown model %d", cfg->model);
+  int n = demi_device_count();
+  if (n <= 0) return fail(nullptr, DEMI_ERR_NO_DEVICE, "demi_create: no CUDA device (this engine has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= n)
+    return fail(nullptr, DEMI_ERR_INVALID, "demi_create: device %d out of range (%d devices)", cfg->device, n);
+  demi_handle* h = new demi_handle();
+  h->cfg = *cfg;
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters_dev, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 2 * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    fail(nullptr, DEMI_ERR_CUDA, "demi_create: %s", cudaGetErrorString(e));
+    delete h;
+    return DEMI_ERR_CUDA;
+  }
+  *out = h;
+  return DEMI_OK;
+}
+
+extern "C" void demi_destroy(demi_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
+  cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, uint32_t n) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!ev && n) return fail(h, DEMI_ERR_INVALID, "demi_set_externals: null events");
+  const int n_actors = h->cfg.model == DEMI_MODEL_PINGPONG3 ? 3 : h->cfg.model == DEMI_MODEL_RAFT5 ? 5 : 32;
+  uint32_t sends = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const demi_ext_event& e = ev[i];
+    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION)
+      return fail(h, DEMI_ERR_INVALID, "demi_set_externals: event %u has unknown kind %u", i, e.kind);
+    bool needs_a = e.kind != DEMI_EXT_WAIT_QUIESCENCE;
+    bool needs_b = e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION;
+    if ((needs_a && e.a >= n_actors) || (needs_b && e.b >= n_actors))
+      return fail(h, DEMI_ERR_INVALID, "demi_set_externals: event %u names an unknown actor", i);
+    // MessageTypes.sanityCheckTrace (ExternalEvents.scala:138-149): no two consecutive WaitQuiescence
+    if (e.kind == DEMI_EXT_WAIT_QUIESCENCE && i > 0 && ev[i - 1].kind == DEMI_EXT_WAIT_QUIESCENCE)
+      return fail(h, DEMI_ERR_INVALID, "demi_set_externals: consecutive WaitQuiescence at %u", i);
+    if (e.kind == DEMI_EXT_SEND) sends++;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaFree(h->ext_dev); h->ext_dev = nullptr;
+  h->ext_host.assign(ev, ev + n);
+  h->n_ext_sends = sends;
+  if (n) {
+    CUDA_TRY(h, cudaMalloc(&h->ext_dev, n * sizeof(demi_ext_event)));
+    CUDA_TRY(h, cudaMemcpy(h->ext_dev, ev, n * sizeof(demi_ext_event), cudaMemcpyHostToDevice));
+  }
+  return DEMI_OK;
+}
+
+// ------------------------------------------------------------------- launch
+struct LaunchPlan { const Variant* v; int grid; size_t smem; KernelArgs args; };
+
+static int32_t ensure(demi_handle* h, void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return DEMI_OK;
+  cudaFree(*p); *p = nullptr; *cap = 0;
+  CUDA_TRY(h, cudaMalloc(p, need));
+  *cap = need;
+  return DEMI_OK;
+}
+
+static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool record, LaunchPlan* plan) {
+  if (!p) return fail(h, DEMI_ERR_INVALID, "null params");
+  if (h->ext_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_externals has not been called");
+  if (p->n_prefixes > 0xFFFFFFFFull) return fail(h, DEMI_ERR_INVALID, "n_prefixes > 2^32-1 per call");
+  const uint32_t pcap = demi_pending_cap(h->cfg.model, p->max_messages, h->n_ext_sends);
+  const uint32_t tcap = demi_tosend_cap(h->n_ext_sends);
+  const Variant* v = pick_variant(h->cfg.model, pcap, tcap, record);
+  if (!v) return fail(h, DEMI_ERR_CAPACITY, "no kernel variant for pending_cap=%u tosend_cap=%u", pcap, tcap);
+  const size_t smem = v->smem_per_warp * WARPS;
+  CUDA_TRY(h, cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks_per_sm = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, v->fn, WARPS * 32, smem));
+  if (blocks_per_sm < 1) return fail(h, DEMI_ERR_CAPACITY, "kernel variant does not fit on an SM (smem %zu)", smem);
+  uint64_t want = (p->n_prefixes + WARPS - 1) / WARPS;
+  uint64_t full = (uint64_t)h->sm_count * (uint64_t)blocks_per_sm;
+  int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, full));
+  if (record) grid = 1;
+  const uint64_t total_warps = (uint64_t)grid * WARPS;
+  const uint32_t node_cap = demi_node_cap(pcap);
+
+  int32_t rc;
+  if ((rc = ensure(h, (void**)&h->node_scratch, &h->node_scratch_bytes,
+                   total_warps * node_cap * sizeof(uint4))) != DEMI_OK) return rc;
+  if (v->pend_global)
+    if ((rc = ensure(h, (void**)&h->pend_scratch, &h->pend_scratch_bytes,
+                     total_warps * (uint64_t)v->pcap * sizeof(uint4))) != DEMI_OK) return rc;
+
+  KernelArgs a{};
+  a.model_flags = h->cfg.model_flags;
+  a.blocked_mask = h->cfg.blocked_mask;
+  a.ignore_timers = h->cfg.ignore_timers;
+  a.max_messages = p->max_messages < 0 ? INT_MAX : p->max_messages;   // maxMessages = Int.MaxValue (RandomScheduler.scala:54)
+  a.interval = p->invariant_check_interval;
+  a.looking_for = p->looking_for;
+  a.seed_base = p->seed_base;
+  a.n_prefixes = p->n_prefixes;
+  a.ext = h->ext_dev;
+  a.n_ext = (uint32_t)h->ext_host.size();
+  a.node_cap = node_cap;
+  a.pending_cap = pcap;
+  a.tosend_cap = tcap;
+  a.node_scratch = h->node_scratch;
+  a.pend_scratch = h->pend_scratch;
+  a.sum_steps = h->counters_dev;
+  a.n_violations = h->counters_dev + 1;
+  plan->v = v; plan->grid = grid; plan->smem = smem; plan->args = a;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p, void* out_dev, void* stream) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!out_dev) return fail(h, DEMI_ERR_INVALID, "demi_fuzz_batch_dev: null output");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LaunchPlan plan;
+  int32_t rc = plan_launch(h, p, false, &plan);
+  if (rc != DEMI_OK) return rc;
+  if (p->n_prefixes == 0) return DEMI_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  plan.args.results = (demi_fuzz_result*)out_dev;
+  CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), s));
+  plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
+  CUDA_TRY(h, cudaGetLastError());
+  h->perf.kernel_launches = 1;
+  h->perf.prefixes = p->n_prefixes;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p, demi_fuzz_result* out_host) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!out_host) return fail(h, DEMI_ERR_INVALID, "demi_fuzz_batch: null output");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!p) return fail(h, DEMI_ERR_INVALID, "null params");
+  const size_t bytes = (size_t)p->n_prefixes * sizeof(demi_fuzz_result);
+  int32_t rc = ensure(h, (void**)&h->results_dev, &h->results_cap, std::max<size_t>(bytes, 32));
+  if (rc != DEMI_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  rc = demi_fuzz_batch_dev(h, p, h->results_dev, h->stream);
+  if (rc != DEMI_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->results_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long c[2] = {0, 0};
+  CUDA_TRY(h, cudaMemcpyAsync(c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->perf.kernel_ms = ms;
+  h->perf.deliveries = c[0];
+  h->perf.violations = c[1];
+  h->perf.d2h_bytes = bytes + sizeof(c);
+  h->perf.h2d_bytes = 0;
+  return DEMI_OK;
+}
+
+// Counts from the last *_dev batch launched on `stream` (waits for it).
+extern "C" int32_t demi_fuzz_summary_dev(demi_handle* h, const void* /*results_dev*/, uint64_t /*n*/,
+                                         void* stream, uint64_t* n_violations, uint64_t* sum_steps) {
+  if (!h) return DEMI_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  unsigned long long c[2] = {0, 0};
+  CUDA_TRY(h, cudaMemcpyAsync(c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (sum_steps) *sum_steps = c[0];
+  if (n_violations) *n_violations = c[1];
+  h->perf.deliveries = c[0];
+  h->perf.violations = c[1];
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, int64_t seed,
+                                   demi_event* events, uint32_t cap_events, uint32_t* n_events,
+                                   uint16_t* dep_parent, uint32_t cap_nodes, uint32_t* n_nodes,
+                                   demi_fuzz_result* result) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!p) return fail(h, DEMI_ERR_INVALID, "null params");
+  if (!events || !cap_events) return fail(h, DEMI_ERR_INVALID, "demi_fuzz_trace: events buffer required");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  demi_fuzz_params q = *p;
+  q.seed_base = seed; q.n_prefixes = 1;
+  LaunchPlan plan;
+  int32_t rc = plan_launch(h, &q, true, &plan);
+  if (rc != DEMI_OK) return rc;
+  demi_event* ev_dev = nullptr; uint16_t* par_dev = nullptr; demi_fuzz_result* res_dev = nullptr;
+  const uint32_t cap_ev = std::max<uint32_t>(cap_events, 1), cap_n = std::max<uint32_t>(cap_nodes, 1);
+  CUDA_TRY(h, cudaMalloc(&ev_dev, (size_t)cap_ev * sizeof(demi_event)));
+  CUDA_TRY(h, cudaMalloc(&par_dev, (size_t)cap_n * sizeof(uint16_t)));
+  CUDA_TRY(h, cudaMalloc(&res_dev, sizeof(demi_fuzz_result)));
+  plan.args.results = res_dev;
+  plan.args.rec_events = ev_dev; plan.args.rec_cap = cap_events;
+  plan.args.rec_counts = h->rec_counts_dev;
+  plan.args.rec_parent = dep_parent ? par_dev : nullptr; plan.args.rec_parent_cap = cap_nodes;
+  CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), h->stream));
+  plan.v->fn<<<1, WARPS * 32, plan.smem, h->stream>>>(plan.args);
+  cudaError_t e = cudaGetLastError();
+  demi_fuzz_result r{}; uint32_t counts[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&r, res_dev, sizeof(r), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts, h->rec_counts_dev, sizeof(counts), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && r.status == 0) {
+    e = cudaMemcpy(events, ev_dev, (size_t)std::min(counts[0], cap_events) * sizeof(demi_event), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dep_parent)
+      e = cudaMemcpy(dep_parent, par_dev, (size_t)std::min(counts[1], cap_nodes) * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(ev_dev); cudaFree(par_dev); cudaFree(res_dev);
+  if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_fuzz_trace: %s", cudaGetErrorString(e));
+  if (n_events) *n_events = counts[0];
+  if (n_nodes) *n_nodes = counts[1];
+  if (result) *result = r;
+  if (r.status) return fail(h, DEMI_ERR_CAPACITY, "demi_fuzz_trace: prefix status %u", (unsigned)r.status);
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_stats(const demi_handle* h, demi_perf* out) {
+  if (!h || !out) return DEMI_ERR_INVALID;
+  *out = h->perf;
+  return DEMI_OK;
+}

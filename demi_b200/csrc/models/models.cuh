@@ -1,0 +1,232 @@
+// models.cuh — built-in actor models (the "state-transition functor").
+//
+// In the reference the transition function is the application's own Akka
+// receive(), reached through Instrumenter.dispatch_new_message
+// (Instrumenter.scala:913-1017) and ActorCell.receiveMessage
+// (WeaveActor.aj:90-108).  The Raft application DEMi was evaluated on
+// (akka-raft) is not part of the reference tree (README.md:12,27-28), so these
+// are *models of* such applications; their specification is DESIGN.md §3.
+//
+// Interface a model provides to Machine<>:
+//   N_ACTORS, STATE_WORDS
+//   init_word(i, flags)                      initial value of state word i
+//   receive(out, self, st, src, type, p0, p1, flags)    scalar, runs on lane 0
+//   invariant_lane(states, flags, lane)      lane-parallel; engine takes the
+//                                            minimum non-zero code over lanes
+#pragma once
+#include "../machine.cuh"
+
+namespace demi {
+
+// ---------------------------------------------------------------- pingpong3
+// BASELINE.json configs[0].  Ping(k) to X => X sends Pong(k) to (X+1)%3.
+// state: w0 = pings received, w1 = pongs received.
+struct PingPong3 {
+  static constexpr int N_ACTORS = 3;
+  static constexpr int STATE_WORDS = 2;
+  static constexpr int ID = DEMI_MODEL_PINGPONG3;
+  enum { PING = 1, PONG = 2 };
+  __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
+  __device__ static __forceinline__ void receive(Outbox& out, uint32_t self, uint32_t* st, uint32_t /*src*/,
+                                                 uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
+    if (type == PING) {
+      st[0]++;
+      out.send((self + 1) % 3, PONG, p0, 0);
+    } else if (type == PONG) {
+      st[1]++;
+    }
+  }
+  // flags bit0: test hook — code 7 once actor 0 has received >= (flags>>8) pongs
+  __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t flags, uint32_t lane) {
+    if (lane == 0 && (flags & 1u) && states[1] >= (flags >> 8)) return 7;
+    return 0;
+  }
+};
+
+// -------------------------------------------------------------------- raft5
+// 5-node Raft (Ongaro & Ousterhout, Fig. 2), tick-driven timers, log capacity
+// 8, one entry per AppendEntries.  40-byte state, byte layout below.
+struct Raft5 {
+  static constexpr int N_ACTORS = 5;
+  static constexpr int STATE_WORDS = 10;
+  static constexpr int ID = DEMI_MODEL_RAFT5;
+  enum { ROLE = 0, TERM = 1, VOTED = 2, VOTES = 3, LOGLEN = 4, COMMIT = 5, HEARD = 6,
+         LOGTERM = 8, LOGVAL = 16, NEXT = 24, MATCH = 29 };
+  enum { INIT = 0, FOLLOWER = 1, CANDIDATE = 2, LEADER = 3 };
+  enum { BOOT = 1, CLIENT_CMD = 2, ELECTION_TICK = 3, REQUEST_VOTE = 4, VOTE_REPLY = 5,
+         HEARTBEAT_TICK = 6, APPEND_ENTRIES = 7, APPEND_REPLY = 8 };
+  static constexpr uint32_t LOG_CAP = 8;
+  static constexpr uint32_t NONE = 0xFF;
+  static constexpr uint32_t BUG_DOUBLE_VOTE = 1u;
+  static constexpr uint32_t BUG_STALE_COMMIT = 2u;
+
+  __device__ static __forceinline__ uint32_t init_word(uint32_t i, uint32_t) {
+    return (i % STATE_WORDS == 0) ? (NONE << 16) : 0u;      // byte 2 = votedFor = none
+  }
+
+  __device__ static __forceinline__ void step_down(Outbox& out, uint8_t* s, uint32_t t) {
+    if (s[ROLE] == LEADER) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
+    if (t > s[TERM]) { s[TERM] = (uint8_t)t; s[VOTED] = (uint8_t)NONE; }
+    s[ROLE] = FOLLOWER;
+    s[VOTES] = 0;
+  }
+  __device__ static __forceinline__ void send_append(Outbox& out, const uint8_t* s, uint32_t j) {
+    uint32_t prev = s[NEXT + j];
+    uint32_t pt = prev ? s[LOGTERM + prev - 1] : 0u;
+    uint32_t has = prev < s[LOGLEN] ? 1u : 0u;
+    uint32_t et = has ? s[LOGTERM + prev] : 0u, ev = has ? s[LOGVAL + prev] : 0u;
+    out.send(j, APPEND_ENTRIES, (uint32_t)s[TERM] | (prev << 8) | (pt << 16) | ((uint32_t)s[COMMIT] << 24),
+             has | (et << 8) | (ev << 16));
+  }
+
+  __device__ static __noinline__ void receive(Outbox& out, uint32_t self, uint32_t* stw, uint32_t src,
+                                              uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
+    uint8_t* s = reinterpret_cast<uint8_t*>(stw);
+    const uint32_t last_idx = s[LOGLEN];
+    const uint32_t last_term = last_idx ? s[LOGTERM + last_idx - 1] : 0u;
+    const uint32_t t = p0 & 0xFF;
+    if (type != BOOT && type != CLIENT_CMD && s[ROLE] == INIT) return;
+    switch (type) {
+      case BOOT:
+        if (s[ROLE] == INIT) { s[ROLE] = FOLLOWER; out.schedule_repeating(ELECTION_TICK, 0, 0); }
+        break;
+      case CLIENT_CMD:
+        if (s[ROLE] == LEADER && s[LOGLEN] < LOG_CAP) {
+          s[LOGTERM + s[LOGLEN]] = s[TERM];
+          s[LOGVAL + s[LOGLEN]] = (uint8_t)(p0 & 0x7F);
+          s[LOGLEN]++;
+        }
+        break;
+      case ELECTION_TICK:
+        if (s[ROLE] == LEADER) break;
+        if (s[HEARD]) { s[HEARD] = 0; break; }
+        if (s[TERM] == 255) break;
+        s[TERM]++;
+        s[ROLE] = CANDIDATE;
+        s[VOTED] = (uint8_t)self;
+        s[VOTES] = (uint8_t)(1u << self);
+        for (uint32_t j = 0; j < 5; j++)
+          if (j != self) out.send(j, REQUEST_VOTE, (uint32_t)s[TERM] | (last_idx << 8) | (last_term << 16), 0);
+        break;
+      case REQUEST_VOTE: {
+        uint32_t li = (p0 >> 8) & 0xFF, lt = (p0 >> 16) & 0xFF;
+        if (t > s[TERM]) step_down(out, s, t);
+        bool up_to_date = lt > last_term || (lt == last_term && li >= last_idx);
+        bool can_vote = (s[VOTED] == NONE || s[VOTED] == src) || (flags & BUG_DOUBLE_VOTE);
+        uint32_t grant = (t == s[TERM] && can_vote && up_to_date) ? 1u : 0u;
+        if (grant) { s[VOTED] = (uint8_t)src; s[HEARD] = 1; }
+        out.send(src, VOTE_REPLY, (uint32_t)s[TERM] | (grant << 8), 0);
+        break;
+      }
+      case VOTE_REPLY: {
+        uint32_t g = (p0 >> 8) & 1u;
+        if (t > s[TERM]) { step_down(out, s, t); break; }
+        if (s[ROLE] == CANDIDATE && t == s[TERM] && g) {
+          s[VOTES] |= (uint8_t)(1u << src);
+          if (__popc((uint32_t)s[VOTES]) >= 3) {
+            s[ROLE] = LEADER;
+            for (uint32_t j = 0; j < 5; j++) { s[NEXT + j] = s[LOGLEN]; s[MATCH + j] = 0; }
+            if (s[LOGLEN] < LOG_CAP) {                       // leader no-op entry
+              s[LOGTERM + s[LOGLEN]] = s[TERM];
+              s[LOGVAL + s[LOGLEN]] = (uint8_t)(0x80u | self);
+              s[LOGLEN]++;
+            }
+            for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
+            out.schedule_repeating(HEARTBEAT_TICK, 0, 0);
+          }
+        }
+        break;
+      }
+      case HEARTBEAT_TICK:
+        if (s[ROLE] == LEADER)
+          for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
+        break;
+      case APPEND_ENTRIES: {
+        uint32_t prev = (p0 >> 8) & 0xFF, pt = (p0 >> 16) & 0xFF, lc = (p0 >> 24) & 0xFF;
+        uint32_t has = p1 & 1u, et = (p1 >> 8) & 0xFF, ev = (p1 >> 16) & 0xFF;
+        if (t < s[TERM]) { out.send(src, APPEND_REPLY, (uint32_t)s[TERM], 0); break; }
+        if (t > s[TERM] || s[ROLE] != FOLLOWER) step_down(out, s, t);
+        s[HEARD] = 1;
+        bool ok = prev <= s[LOGLEN] && (prev == 0 || s[LOGTERM + prev - 1] == pt);
+        if (!ok) { out.send(src, APPEND_REPLY, (uint32_t)s[TERM], 0); break; }
+        uint32_t mi = prev;
+        if (has) {
+          if (s[LOGLEN] > prev && s[LOGTERM + prev] != et) {          // conflict: truncate
+            for (uint32_t k = prev; k < LOG_CAP; k++) { s[LOGTERM + k] = 0; s[LOGVAL + k] = 0; }
+            s[LOGLEN] = (uint8_t)prev;
+          }
+          if (s[LOGLEN] == prev && prev < LOG_CAP) {
+            s[LOGTERM + prev] = (uint8_t)et; s[LOGVAL + prev] = (uint8_t)ev;
+            s[LOGLEN] = (uint8_t)(prev + 1);
+          }
+          if (s[LOGLEN] > prev) mi = prev + 1;
+        }
+        uint32_t nc = lc < mi ? lc : mi;
+        if (nc > s[COMMIT]) s[COMMIT] = (uint8_t)nc;
+        out.send(src, APPEND_REPLY, (uint32_t)s[TERM] | (1u << 8) | (mi << 16), 0);
+        break;
+      }
+      case APPEND_REPLY: {
+        uint32_t ok = (p0 >> 8) & 1u, mi = (p0 >> 16) & 0xFF;
+        if (t > s[TERM]) { step_down(out, s, t); break; }
+        if (s[ROLE] != LEADER || t != s[TERM]) break;
+        if (ok) {
+          if (mi > s[MATCH + src]) s[MATCH + src] = (uint8_t)mi;
+          if (mi > s[NEXT + src]) s[NEXT + src] = (uint8_t)mi;
+          for (uint32_t idx = s[LOGLEN]; idx > s[COMMIT]; idx--) {
+            if (s[LOGTERM + idx - 1] != s[TERM] && !(flags & BUG_STALE_COMMIT)) continue;
+            uint32_t cnt = 1;
+            for (uint32_t k = 0; k < 5; k++) if (k != self && s[MATCH + k] >= idx) cnt++;
+            if (cnt >= 3) { s[COMMIT] = (uint8_t)idx; break; }
+          }
+        } else if (s[NEXT + src] > 0) {
+          s[NEXT + src]--;
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+
+  // lanes 0..9 each own one unordered pair (i<j).  code 1: two leaders in one
+  // term; code 2: committed prefixes disagree.
+  __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t, uint32_t lane) {
+    if (lane >= 10) return 0;
+    // pair index -> (i,j): (0,1)(0,2)(0,3)(0,4)(1,2)(1,3)(1,4)(2,3)(2,4)(3,4)
+    uint32_t i = lane < 4 ? 0u : lane < 7 ? 1u : lane < 9 ? 2u : 3u;
+    uint32_t j = lane < 4 ? lane + 1 : lane < 7 ? lane - 2 : lane < 9 ? lane - 4 : 4u;
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(states + i * STATE_WORDS);
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(states + j * STATE_WORDS);
+    if (a[ROLE] == LEADER && b[ROLE] == LEADER && a[TERM] == b[TERM]) return 1;
+    uint32_t c = a[COMMIT] < b[COMMIT] ? a[COMMIT] : b[COMMIT];
+    for (uint32_t k = 0; k < c; k++)
+      if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) return 2;
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------ bcast32
+// BASELINE.json configs[4]: 32-actor broadcast storm.
+// state: w0 = floods received, w1 = max ttl seen + 1.
+struct Bcast32 {
+  static constexpr int N_ACTORS = 32;
+  static constexpr int STATE_WORDS = 2;
+  static constexpr int ID = DEMI_MODEL_BCAST32;
+  enum { FLOOD = 1 };
+  __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
+  __device__ static __forceinline__ void receive(Outbox& out, uint32_t self, uint32_t* st, uint32_t /*src*/,
+                                                 uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
+    if (type != FLOOD) return;
+    st[0]++;
+    if (p0 + 1 > st[1]) st[1] = p0 + 1;
+    if (p0 > 0)
+      for (uint32_t j = 0; j < 32; j++) if (j != self) out.send(j, FLOOD, p0 - 1, 0);
+  }
+  // code 3 once some actor has received >= flags floods (flags != 0)
+  __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t flags, uint32_t lane) {
+    if (!flags) return 0;
+    return states[lane * 2] >= flags ? 3u : 0u;
+  }
+};
+
+}  // namespace demi
