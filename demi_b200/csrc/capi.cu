@@ -1,6 +1,7 @@
 // capi.cu — the C ABI (include/demi_b200.h) over the CUDA engine.
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <climits>
+#include <cstdlib>
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
@@ -9,6 +10,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "fuzz_kernel.cuh"
+#include "lane_kernel.cuh"
 
 using namespace demi;
 
@@ -27,6 +29,13 @@ struct demi_handle {
   uint4* node_scratch = nullptr; size_t node_scratch_bytes = 0;
   uint4* pend_scratch = nullptr; size_t pend_scratch_bytes = 0;
   unsigned long long* counters_dev = nullptr;      // [0]=sum_steps [1]=n_violations
+  // lane engine
+  uint4* ext_sends_dev = nullptr;
+  bool has_partitions = false, ext_sends_distinct = true;
+  uint4* lane_pend = nullptr; size_t lane_pend_bytes = 0;
+  uint32_t* ovf_list = nullptr; size_t ovf_list_bytes = 0;
+  uint32_t* ovf_count = nullptr;
+  int use_lane_engine = 1;
   uint32_t* rec_counts_dev = nullptr;
   // pinned staging for host transfers
   void* pinned = nullptr; size_t pinned_bytes = 0;
@@ -78,6 +87,16 @@ static const Variant* pick_variant(int model, uint32_t pcap, uint32_t tcap, bool
   return nullptr;
 }
 
+// lane-engine table
+struct LaneVariant { int model; int bd; uint32_t lpcap; kernel_fn fn; size_t smem_per_block; };
+template <class MODEL, int BD, int LPCAP>
+static LaneVariant make_lane_variant() {
+  using M = LaneMachine<MODEL, BD, LPCAP>;
+  return LaneVariant{MODEL::ID, BD, (uint32_t)LPCAP, fuzz_lane_kernel<MODEL, BD, LPCAP>,
+                     (size_t)M::WORDS * BD * sizeof(uint32_t)};
+}
+static const LaneVariant* pick_lane_variant(const demi_handle* h);
+
 // ---------------------------------------------------------------- lifecycle
 extern "C" const char* demi_version(void) { return "demi_b200 0.1 (sm_100a)"; }
 
@@ -110,6 +129,8 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaMalloc(&h->counters_dev, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 2 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ovf_count, sizeof(uint32_t));
+  if (getenv("DEMI_DISABLE_LANE_ENGINE")) h->use_lane_engine = 0;
   if (e != cudaSuccess) {
     fail(nullptr, DEMI_ERR_CUDA, "demi_create: %s", cudaGetErrorString(e));
     delete h;
@@ -124,6 +145,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
   cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
+  cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -158,7 +180,35 @@ extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, 
     CUDA_TRY(h, cudaMalloc(&h->ext_dev, n * sizeof(demi_ext_event)));
     CUDA_TRY(h, cudaMemcpy(h->ext_dev, ev, n * sizeof(demi_ext_event), cudaMemcpyHostToDevice));
   }
+  // lane-engine side tables: the Send events in order; whether two Sends are
+  // identical (they would share a DepTracker Unique under the root)
+  std::vector<uint4> sv;
+  h->has_partitions = false; h->ext_sends_distinct = true;
+  for (uint32_t i = 0; i < n; i++) {
+    const demi_ext_event& e = ev[i];
+    if (e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION) h->has_partitions = true;
+    if (e.kind != DEMI_EXT_SEND) continue;
+    uint4 m = make_uint4(DEMI_DEADLETTERS | ((uint32_t)e.a << 8) | ((uint32_t)e.type << 16) |
+                         ((uint32_t)DEMI_MF_EXTERNAL << 24), e.p0, e.p1, 0u);
+    for (const uint4& o : sv) if (o.x == m.x && o.y == m.y && o.z == m.z) h->ext_sends_distinct = false;
+    sv.push_back(m);
+  }
+  cudaFree(h->ext_sends_dev); h->ext_sends_dev = nullptr;
+  if (!sv.empty()) {
+    CUDA_TRY(h, cudaMalloc(&h->ext_sends_dev, sv.size() * sizeof(uint4)));
+    CUDA_TRY(h, cudaMemcpy(h->ext_sends_dev, sv.data(), sv.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  }
   return DEMI_OK;
+}
+
+static const LaneVariant* pick_lane_variant(const demi_handle* h) {
+  static const std::vector<LaneVariant> v = {
+    make_lane_variant<Raft5, 256, 96>(),
+    make_lane_variant<PingPong3, 256, 128>(),
+  };
+  if (!h->use_lane_engine || h->cfg.blocked_mask || !h->ext_sends_distinct) return nullptr;
+  for (const LaneVariant& lv : v) if (lv.model == h->cfg.model) return &lv;
+  return nullptr;
 }
 
 // ------------------------------------------------------------------- launch
@@ -232,9 +282,36 @@ extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p
   cudaStream_t s = (cudaStream_t)stream;
   plan.args.results = (demi_fuzz_result*)out_dev;
   CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), s));
+  h->perf.kernel_launches = 0;
+  const LaneVariant* lv = pick_lane_variant(h);
+  if (lv) {
+    // K1-lane handles every prefix it can prove exact; the rest are deferred to the warp engine
+    const size_t lsmem = lv->smem_per_block;
+    CUDA_TRY(h, cudaFuncSetAttribute(lv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    int bps = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lv->fn, lv->bd, lsmem));
+    if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "lane kernel does not fit on an SM");
+    uint64_t want = (p->n_prefixes + lv->bd - 1) / lv->bd;
+    int lgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * bps));
+    const uint64_t lwarps = (uint64_t)lgrid * (lv->bd / 32);
+    int32_t rc2;
+    if ((rc2 = ensure(h, (void**)&h->lane_pend, &h->lane_pend_bytes, lwarps * lv->lpcap * 32 * sizeof(uint4))) != DEMI_OK) return rc2;
+    if ((rc2 = ensure(h, (void**)&h->ovf_list, &h->ovf_list_bytes, std::max<size_t>(p->n_prefixes * sizeof(uint32_t), 64))) != DEMI_OK) return rc2;
+    CUDA_TRY(h, cudaMemsetAsync(h->ovf_count, 0, sizeof(uint32_t), s));
+    KernelArgs la = plan.args;
+    la.lane_pend = h->lane_pend;
+    la.ext_sends = h->ext_sends_dev;
+    la.has_partitions = h->has_partitions ? 1u : 0u;
+    la.ovf_list = h->ovf_list; la.ovf_count = h->ovf_count;
+    lv->fn<<<lgrid, lv->bd, lsmem, s>>>(la);
+    CUDA_TRY(h, cudaGetLastError());
+    h->perf.kernel_launches++;
+    plan.args.index_list = h->ovf_list;
+    plan.args.index_count = h->ovf_count;
+  }
   plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
   CUDA_TRY(h, cudaGetLastError());
-  h->perf.kernel_launches = 1;
+  h->perf.kernel_launches++;
   h->perf.prefixes = p->n_prefixes;
   return DEMI_OK;
 }

@@ -1,0 +1,439 @@
+// lane_kernel.cuh — K1-lane: the high-throughput random-fuzz kernel.  One
+// THREAD owns one schedule prefix (one RandomScheduler execution, reference:
+// schedulers/RandomScheduler.scala:234-272, :352-485); a warp advances 32
+// prefixes in lock-step.  Same semantics as machine.cuh, restated for a scalar
+// owner:
+//
+//   registers      java.util.Random state, counters, network masks, and the
+//                  timer sets as BITMASKS over the model's finite timer universe
+//                  (justScheduledTimers / timerToCancellable / timersCancelled-
+//                  ThisStep), messagesToSend and timersToResend as byte queues
+//   shared memory  actor states, the receive() outbox and partition rows,
+//                  thread-interleaved (word w of thread t at [w*BD + t]: every
+//                  access is bank-conflict free whatever each lane indexes)
+//   HBM / L1 / L2  the pending-message array (RandomizedHashSet.arr), 16-byte
+//                  entries interleaved per warp (entry i of lane l at
+//                  [(i*32 + l)])
+//
+// Exactness: every structure here is a bounded, duplicate-free restatement.
+// Whenever an execution could leave that regime (a capacity would overflow, or
+// the DepTracker child-reuse rule (DepTracker.scala:94-108) could fire) the
+// thread stops and appends the prefix index to the defer list; the general
+// warp engine (fuzz_kernel.cuh) then re-runs exactly those prefixes.  A
+// prefix that completes here has, by construction, the same result as in the
+// general engine.
+#pragma once
+#include "machine.cuh"
+#include "models/models.cuh"
+
+namespace demi {
+
+constexpr uint32_t LANE_DEFER = 0xFFFFu;      // internal status: hand over to the warp engine
+constexpr int LANE_TOSEND_CAP = 16;
+constexpr int LANE_RESEND_CAP = 8;
+
+// One actor's state, thread-interleaved in shared memory.
+struct LaneState {
+  uint32_t* base;      // &smem[word0 * BD + tid]
+  uint32_t bd;
+  __device__ __forceinline__ uint8_t& operator[](uint32_t i) const {
+    return reinterpret_cast<uint8_t*>(base + (i >> 2) * bd)[i & 3];
+  }
+  __device__ __forceinline__ uint8_t& b(uint32_t i) const { return (*this)[i]; }
+  __device__ __forceinline__ uint32_t& w(uint32_t i) const { return base[i * bd]; }
+};
+template <int SW>
+struct LaneAll {
+  uint32_t* base; uint32_t bd;
+  __device__ __forceinline__ LaneState actor(uint32_t a) const { return LaneState{base + a * SW * bd, bd}; }
+};
+
+// receive()'s outbox, thread-interleaved in shared memory (3 words per op).
+template <int CAP>
+struct LaneOutbox {
+  uint32_t* base; uint32_t bd;
+  uint32_t n, self;
+  bool overflow;
+  __device__ __forceinline__ void push(uint32_t op, uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (n >= CAP) { overflow = true; return; }
+    base[(n * 3 + 0) * bd] = op | (dst << 8) | (type << 16);
+    base[(n * 3 + 1) * bd] = p0;
+    base[(n * 3 + 2) * bd] = p1;
+    n++;
+  }
+  __device__ __forceinline__ void send(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) { push(OP_SEND, dst, type, p0, p1); }
+  __device__ __forceinline__ void schedule_once(uint32_t type, uint32_t p0, uint32_t p1) { push(OP_SCHED_ONCE, self, type, p0, p1); }
+  __device__ __forceinline__ void schedule_repeating(uint32_t type, uint32_t p0, uint32_t p1) { push(OP_SCHED_REPEAT, self, type, p0, p1); }
+  __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { push(OP_CANCEL, self, type, p0, p1); }
+};
+
+// small FIFO of bytes in two 64-bit registers
+struct ByteQueue16 {
+  uint64_t lo, hi; uint32_t n;
+  __device__ __forceinline__ void clear() { lo = hi = 0; n = 0; }
+  __device__ __forceinline__ uint32_t get(uint32_t i) const {
+    uint64_t v = i < 8 ? lo : hi;
+    return (uint32_t)(v >> ((i & 7) * 8)) & 0xFFu;
+  }
+  __device__ __forceinline__ void push(uint32_t b) {      // caller checks n < 16
+    uint64_t v = (uint64_t)b << ((n & 7) * 8);
+    if (n < 8) lo |= v; else hi |= v;
+    n++;
+  }
+  __device__ __forceinline__ void remove_at(uint32_t i) { // order preserving
+    ByteQueue16 q; q.clear();
+    for (uint32_t k = 0; k < n; k++) if (k != i) q.push(get(k));
+    *this = q;
+  }
+};
+
+template <class MODEL, int BD, int LPCAP>
+struct LaneMachine {
+  static constexpr int N = MODEL::N_ACTORS;
+  static constexpr int SW = MODEL::STATE_WORDS;
+  static constexpr int OB = MODEL::LANE_OUTBOX;
+  static constexpr int WORDS = N * SW + OB * 3 + N;    // states + outbox + partition rows
+
+  uint32_t* smw;             // &smem[tid]; word w at smw[w*BD]
+  uint4* pend;               // entry i at pend[i*32]
+  const KernelArgs* A;
+
+  JRandom rng;
+  uint32_t n_pending, max_pending;
+  ByteQueue16 tosend;        // byte: timer slot, or 0x80|k for the k-th external Send
+  uint64_t resend; uint32_t n_resend;
+  uint32_t just, registry, cancelled;            // bit per timer slot
+  uint32_t root_timers, window_timers;           // duplicate guards for the child-reuse rule
+  uint32_t n_nodes, parent_event, n_events, n_uniq;
+  int32_t nsched, nmod;
+  uint32_t ext_idx, ext_send_idx;
+  uint32_t violation, status;
+  uint32_t inaccessible, killed;
+  uint64_t thash;
+
+  __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OB * 3 + a) * BD]; }
+  __device__ __forceinline__ LaneState actor(uint32_t a) { return LaneState{smw + a * SW * BD, BD}; }
+
+  __device__ __forceinline__ void defer() { status = LANE_DEFER; }
+
+  // EventTrace.+= (EventTrace.scala:88-110)
+  __device__ __forceinline__ void record_event(uint32_t kind, uint32_t src, uint32_t dst, uint32_t type,
+                                               uint32_t p0, uint32_t p1, uint32_t uniq, uint32_t node, uint32_t parent) {
+    uint32_t w0 = kind | (src << 8) | (dst << 16) | (type << 24);
+    thash += demi_event_term(w0, p0, p1, uniq | (node << 16), n_events, parent);
+    n_events++;
+  }
+
+  // RandomizedHashSet.insert (schedulers/Util.scala:126-136)
+  __device__ __forceinline__ void pending_insert(uint4 e) {
+    if (n_pending >= A->pending_cap || n_pending >= LPCAP) { defer(); return; }
+    pend[n_pending * 32] = e;
+    n_pending++;
+    if (n_pending > max_pending) max_pending = n_pending;
+  }
+  // RandomizedHashSet.remove (schedulers/Util.scala:146-163)
+  __device__ __forceinline__ uint4 pending_remove_at(uint32_t i) {
+    uint4 v = pend[i * 32];
+    uint4 last = pend[(n_pending - 1) * 32];
+    pend[i * 32] = last;
+    n_pending--;
+    return v;
+  }
+
+  // EventOrchestrator.crosses_partition (EventOrchestrator.scala:345-351)
+  __device__ __forceinline__ bool crosses_partition(uint32_t snd, uint32_t rcv) {
+    bool snd_actor = snd < DEMI_MAX_ACTORS;
+    if (snd == rcv && !((killed >> snd) & 1u)) return false;
+    if (A->has_partitions && snd_actor) {
+      if ((part_row(snd) >> rcv) & 1u) return true;
+      if ((part_row(rcv) >> snd) & 1u) return true;
+    }
+    if ((inaccessible >> rcv) & 1u) return true;
+    if (snd_actor && ((inaccessible >> snd) & 1u)) return true;
+    return false;
+  }
+
+  // RandomScheduler.event_produced (RandomScheduler.scala:274-321) after
+  // Instrumenter.aroundDispatch's cancelled-timer drop (Instrumenter.scala:1090-1096).
+  // DepTracker.getMessage (DepTracker.scala:82-109): in the regime this engine
+  // accepts no child is ever reused, so the Unique id is simply the next one.
+  __device__ __forceinline__ void event_produced(uint32_t hdr, uint32_t p0, uint32_t p1) {
+    if (status) return;
+    uint32_t src = hdr_src(hdr), dst = hdr_dst(hdr), type = hdr_type(hdr), flags = hdr_flags(hdr);
+    int slot = MODEL::timer_slot(dst, type, p0, p1);
+    if (cancelled && slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
+    if (n_nodes >= A->node_cap) { defer(); return; }
+    uint32_t uniq = ++n_uniq;
+    bool is_timer = false;
+    uint32_t node;
+    if (flags & DEMI_MF_EXTERNAL) {
+      if (slot >= 0) { defer(); return; }       // an external that equals a timer key could share its Unique
+      parent_event = 0;                         // reportNewlyEnabledExternal (DepTracker.scala:119-122)
+      node = n_nodes++;                         // (identical external Sends are screened on the host)
+      pending_insert(make_uint4(hdr, p0, p1, uniq | (node << 16)));
+    } else {
+      is_timer = (src == DEMI_DEADLETTERS);
+      if (is_timer) {
+        // two equal timer sends under one parent would share a Unique: defer those
+        if (slot < 0) { defer(); return; }
+        uint32_t bit = 1u << slot;
+        if (parent_event == 0) { if (root_timers & bit) { defer(); return; } root_timers |= bit; }
+        else { if (window_timers & bit) { defer(); return; } window_timers |= bit; }
+      }
+      node = n_nodes++;
+      if (!crosses_partition(src, dst)) pending_insert(make_uint4(hdr, p0, p1, uniq | (node << 16)));
+    }
+    if (status) return;
+    record_event(DEMI_EV_MSG_SEND, is_timer ? DEMI_TIMER_SND : src, dst, type, p0, p1, uniq, node, parent_event);
+  }
+
+  // ExternalEventInjector.handle_timer (ExternalEventInjector.scala:282-297)
+  __device__ __forceinline__ void handle_timer(uint32_t slot) {
+    if (A->ignore_timers) return;
+    if (tosend.n >= LANE_TOSEND_CAP || tosend.n >= A->tosend_cap) { defer(); return; }
+    tosend.push(slot);
+  }
+  // RandomScheduler.enqueue_timer (RandomScheduler.scala:549-559)
+  __device__ __forceinline__ void enqueue_timer(uint32_t slot) {
+    if ((just >> slot) & 1u) {
+      if (n_resend >= LANE_RESEND_CAP) { defer(); return; }
+      resend |= (uint64_t)slot << (n_resend * 8);
+      n_resend++;
+      return;
+    }
+    handle_timer(slot);
+  }
+  // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365)
+  __device__ __forceinline__ void send_external_messages() {
+    for (uint32_t i = 0; i < tosend.n && !status; i++) {
+      uint32_t b = tosend.get(i);
+      if (b & 0x80u) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
+        event_produced(raw.x, raw.y, raw.z);
+      } else {
+        uint32_t dst, type, p0, p1;
+        MODEL::slot_msg(b, dst, type, p0, p1);
+        event_produced(make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER), p0, p1);
+      }
+    }
+    tosend.clear();
+  }
+
+  // Cancellable.cancel(): Instrumenter.cancelTimer (Instrumenter.scala:159-168) ->
+  // RandomScheduler.notify_timer_cancel (RandomScheduler.scala:525-534)
+  __device__ __forceinline__ void cancel_timer(uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    int slot = MODEL::timer_slot(self, type, p0, p1);
+    if (slot < 0) { defer(); return; }
+    uint32_t bit = 1u << slot;
+    if (!(cancelled & bit) && __popc(cancelled) >= DEMI_TIMERSET_CAP) { defer(); return; }
+    cancelled |= bit;
+    registry &= ~bit;
+    for (uint32_t i = 0; i < tosend.n; i++)           // handle_timer_cancel (ExternalEventInjector.scala:601-610)
+      if (tosend.get(i) == (uint32_t)slot) { tosend.remove_at(i); return; }
+    for (uint32_t i = 0; i < n_pending; i++) {        // FullyRandom.remove (RandomScheduler.scala:653-664)
+      uint4 q = pend[i * 32];
+      if (hdr_src(q.x) == DEMI_DEADLETTERS && hdr_dst(q.x) == self && hdr_type(q.x) == type &&
+          q.y == p0 && q.z == p1) { pending_remove_at(i); return; }
+    }
+  }
+
+  __device__ __forceinline__ uint32_t check_invariant() {
+    uint32_t v = MODEL::invariant(LaneAll<SW>{smw, BD}, A->model_flags);
+    if (!A->looking_for) return v;                    // violationMatches (RandomScheduler.scala:138-154)
+    return (v && v == A->looking_for) ? A->looking_for : 0u;
+  }
+
+  // EventOrchestrator.inject_until_quiescence (EventOrchestrator.scala:132-189)
+  __device__ __forceinline__ void inject_until_quiescence() {
+    bool loop = true;
+    while (loop && ext_idx < A->n_ext && !status) {
+      uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext) + ext_idx);
+      uint32_t kind = raw.x & 0xFF, a = (raw.x >> 8) & 0xFF, b = (raw.x >> 16) & 0xFF;
+      switch (kind) {
+        case DEMI_EXT_START:
+          record_event(DEMI_EV_SPAWN, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
+          inaccessible &= ~(1u << a); killed &= ~(1u << a);
+          break;
+        case DEMI_EXT_KILL:
+          record_event(DEMI_EV_KILL, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
+          killed |= 1u << a; inaccessible |= 1u << a;
+          break;
+        case DEMI_EXT_SEND:
+          if (tosend.n >= LANE_TOSEND_CAP || ext_send_idx >= 0x80u) { defer(); break; }
+          tosend.push(0x80u | ext_send_idx);
+          ext_send_idx++;
+          break;
+        case DEMI_EXT_PARTITION:
+          record_event(DEMI_EV_PARTITION, a, b, 0, 0, 0, 0, 0, 0);
+          part_row(a) |= 1u << b;
+          break;
+        case DEMI_EXT_UNPARTITION:
+          record_event(DEMI_EV_UNPARTITION, a, b, 0, 0, 0, 0, 0, 0);
+          part_row(a) &= ~(1u << b);
+          break;
+        case DEMI_EXT_WAIT_QUIESCENCE:
+          record_event(DEMI_EV_BEGIN_WAIT_QUIESCENCE, DEMI_DEADLETTERS, DEMI_DEADLETTERS, 0, 0, 0, 0, 0, 0);
+          loop = false;
+          break;
+        default: break;
+      }
+      ext_idx++;
+    }
+  }
+
+  // RandomScheduler.schedule_new_message (RandomScheduler.scala:352-485); blockedActors is empty here
+  __device__ __forceinline__ bool schedule_new_message(uint4& pick) {
+    if (status | violation) return false;
+    if (nsched > A->max_messages) { ext_idx = A->n_ext; return false; }
+    if (A->interval > 0 && nmod == 0 && nsched != 0) {
+      violation = check_invariant();
+      if (violation) return false;
+    }
+    send_external_messages();
+    if (status) return false;
+    if (n_pending == 0) return false;
+    pick = pending_remove_at(rng.next_int(n_pending));          // Util.scala:171-176
+    nsched++;
+    if (nsched == 0x7FFFFFFF) nsched = 1;
+    if (++nmod == A->interval) nmod = 0;
+    uint32_t src = hdr_src(pick.x), dst = hdr_dst(pick.x), type = hdr_type(pick.x);
+    record_event(DEMI_EV_MSG_EVENT, src, dst, type, pick.y, pick.z, pick.w & 0xFFFF, pick.w >> 16, 0);
+    parent_event = pick.w >> 16;                                // reportNewlyDelivered (DepTracker.scala:132-135)
+    window_timers = 0;
+    // updateRepeatingTimer :405-421
+    int slot = MODEL::timer_slot(dst, type, pick.y, pick.z);
+    if (slot >= 0 && ((registry >> slot) & 1u)) {
+      just |= 1u << slot;
+    } else {
+      for (uint32_t i = 0; i < n_resend; i++) handle_timer((uint32_t)(resend >> (i * 8)) & 0xFFu);
+      resend = 0; n_resend = 0;
+      just = 0;
+    }
+    return !status;
+  }
+
+  // Instrumenter.dispatch_new_message (Instrumenter.scala:913-1017)
+  __device__ __forceinline__ void dispatch_new_message(const uint4& pick) {
+    uint32_t src = hdr_src(pick.x), dst = hdr_dst(pick.x), type = hdr_type(pick.x);
+    int slot = MODEL::timer_slot(dst, type, pick.y, pick.z);
+    if (slot >= 0 && ((registry >> slot) & 1u)) enqueue_timer((uint32_t)slot);     // re-arm :1008-1016
+    if (status) return;
+    LaneOutbox<OB> ob;
+    ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
+    MODEL::receive(ob, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
+    if (ob.overflow) { defer(); return; }
+    // equal sends out of one receive() would share a Unique (child reuse): defer
+    for (uint32_t i = 1; i < ob.n; i++)
+      for (uint32_t j = 0; j < i; j++)
+        if (ob.base[(i * 3) * BD] == ob.base[(j * 3) * BD] && ob.base[(i * 3 + 1) * BD] == ob.base[(j * 3 + 1) * BD] &&
+            ob.base[(i * 3 + 2) * BD] == ob.base[(j * 3 + 2) * BD] && (ob.base[(i * 3) * BD] & 0xFF) == OP_SEND) {
+          defer(); return;
+        }
+    for (uint32_t i = 0; i < ob.n && !status; i++) {
+      uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
+      uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+      if (kind == OP_SEND) {
+        event_produced(make_hdr(dst, odst, otype, 0), q0, q1);
+      } else if (kind == OP_CANCEL) {
+        cancel_timer(odst, otype, q0, q1);
+      } else {
+        int s2 = MODEL::timer_slot(odst, otype, q0, q1);
+        if (s2 < 0) { defer(); break; }
+        if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
+        if (kind == OP_SCHED_REPEAT) {
+          if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); break; }
+          registry |= 1u << s2;
+        }
+        enqueue_timer((uint32_t)s2);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void reset(int64_t seed) {
+    rng.seed(seed);
+    for (uint32_t i = 0; i < N * SW; i++) smw[i * BD] = MODEL::init_word(i, A->model_flags);
+    for (uint32_t a = 0; a < N; a++) part_row(a) = 0;
+    n_pending = max_pending = 0;
+    tosend.clear(); resend = 0; n_resend = 0;
+    just = registry = cancelled = root_timers = window_timers = 0;
+    n_nodes = 1; parent_event = 0; n_events = n_uniq = 0;
+    nsched = 0; nmod = 0; ext_idx = 0; ext_send_idx = 0;
+    violation = status = 0;
+    inaccessible = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    killed = 0; thash = 0;
+  }
+
+  __device__ __forceinline__ void run(int64_t seed, demi_fuzz_result& out) {
+    reset(seed);
+    for (;;) {
+      inject_until_quiescence();
+      uint4 pick;
+      while (schedule_new_message(pick)) {
+        dispatch_new_message(pick);
+        if (status) break;
+      }
+      if (status | violation) break;
+      if (ext_idx < A->n_ext) {
+        record_event(DEMI_EV_QUIESCENCE, DEMI_DEADLETTERS, DEMI_DEADLETTERS, 0, 0, 0, 0, 0, 0);
+        continue;
+      }
+      break;
+    }
+    if (!status && nsched <= A->max_messages && !violation) violation = check_invariant();
+    out.status = (uint16_t)status;
+    if (!status) {
+      uint64_t sh = 0;
+      for (uint32_t i = 0; i < N * SW; i++) sh += demi_state_term(smw[i * BD], i);
+      out.violation = violation; out.steps = (uint32_t)nsched;
+      out.state_hash = sh; out.trace_hash = thash;
+      out.n_nodes = (uint16_t)n_nodes;
+      out.n_events = (uint16_t)(n_events > 65535u ? 65535u : n_events);
+      out.max_pending = (uint16_t)max_pending;
+    }
+  }
+};
+
+template <class MODEL, int BD, int LPCAP>
+__global__ void __launch_bounds__(BD, 3)
+fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
+  using M = LaneMachine<MODEL, BD, LPCAP>;
+  extern __shared__ __align__(16) uint32_t lane_smem[];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t gthread = (uint64_t)blockIdx.x * BD + tid;
+  const uint64_t total = (uint64_t)gridDim.x * BD;
+  const uint64_t gwarp = gthread >> 5;
+
+  M m;
+  m.smw = lane_smem + tid;
+  m.pend = args.lane_pend + gwarp * (uint64_t)LPCAP * 32 + (tid & 31);
+  m.A = &args;
+
+  unsigned long long my_steps = 0, my_viol = 0;
+  for (uint64_t idx = gthread; idx < args.n_prefixes; idx += total) {
+    demi_fuzz_result r;
+    m.run(args.seed_base + (int64_t)idx, r);
+    if (r.status == LANE_DEFER) {
+      uint32_t pos = atomicAdd(args.ovf_count, 1u);
+      args.ovf_list[pos] = (uint32_t)idx;
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(args.results + idx);
+      dst[0] = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
+      dst[1] = make_uint4((uint32_t)r.trace_hash, (uint32_t)(r.trace_hash >> 32),
+                          (uint32_t)r.n_nodes | ((uint32_t)r.n_events << 16),
+                          (uint32_t)r.max_pending | ((uint32_t)r.status << 16));
+      my_steps += r.steps;
+      my_viol += r.violation ? 1u : 0u;
+    }
+  }
+  // warp-aggregate the summary counters
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_xor_sync(FULL_MASK, my_steps, o);
+    my_viol += __shfl_xor_sync(FULL_MASK, my_viol, o);
+  }
+  if ((tid & 31) == 0 && args.sum_steps && (my_steps | my_viol)) {
+    atomicAdd(args.sum_steps, my_steps);
+    atomicAdd(args.n_violations, my_viol);
+  }
+}
+
+}  // namespace demi

@@ -60,6 +60,14 @@ struct Outbox {
   __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { push(OP_CANCEL, self, type, p0, p1); }
 };
 
+// State accessor of one actor over contiguous (shared) memory: warp engine.
+struct ContigState {
+  uint32_t* p;
+  __device__ __forceinline__ uint8_t& operator[](uint32_t i) const { return reinterpret_cast<uint8_t*>(p)[i]; }
+  __device__ __forceinline__ uint8_t& b(uint32_t i) const { return reinterpret_cast<uint8_t*>(p)[i]; }
+  __device__ __forceinline__ uint32_t& w(uint32_t i) const { return p[i]; }
+};
+
 // Lane-distributed small ordered set of (receiver,msg) keys; lane i holds entry i.
 struct LaneSet {
   uint32_t key, p0, p1;   // this lane's entry
@@ -140,6 +148,10 @@ struct KernelArgs {
   demi_event* rec_events; uint32_t rec_cap; uint32_t* rec_counts; uint16_t* rec_parent; uint32_t rec_parent_cap;
   // summary counters
   unsigned long long* sum_steps; unsigned long long* n_violations;
+  // lane engine (lane_kernel.cuh)
+  uint4*    lane_pend;        // [total_warps][LPCAP][32] pending entries
+  const uint4* ext_sends;     // the program's Send events as {hdr|EXTERNAL, p0, p1, 0}, in order
+  uint32_t  has_partitions;   // program contains Partition/UnPartition events
 };
 
 // -----------------------------------------------------------------------------
@@ -521,6 +533,12 @@ struct Machine {
     return !status;
   }
 
+  __device__ __noinline__ void receive_scalar(Outbox& ob, uint32_t self, uint32_t src, uint32_t type,
+                                              uint32_t p0, uint32_t p1) {
+    ContigState st{&sm->states[self * SW]};
+    MODEL::receive(ob, self, st, src, type, p0, p1, A->model_flags);
+  }
+
   // Instrumenter.dispatch_new_message (Instrumenter.scala:913-1017)
   __device__ __forceinline__ void dispatch_new_message(const uint4& pick) {
     uint32_t src = hdr_src(pick.x), dst = hdr_dst(pick.x), type = hdr_type(pick.x);
@@ -533,7 +551,7 @@ struct Machine {
     __syncwarp();
     if (lane == 0) {
       Outbox ob; ob.ops = sm->outbox; ob.n = 0; ob.self = dst; ob.overflow = false;
-      MODEL::receive(ob, dst, &sm->states[dst * SW], src, type, pick.y, pick.z, A->model_flags);
+      receive_scalar(ob, dst, src, type, pick.y, pick.z);
       n_ops = ob.overflow ? 0xFFFFFFFFu : ob.n;
     }
     n_ops = __shfl_sync(FULL_MASK, n_ops, 0);

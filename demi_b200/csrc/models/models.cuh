@@ -7,12 +7,20 @@
 // (akka-raft) is not part of the reference tree (README.md:12,27-28), so these
 // are *models of* such applications; their specification is DESIGN.md §3.
 //
-// Interface a model provides to Machine<>:
+// Interface a model provides to the engines:
 //   N_ACTORS, STATE_WORDS
 //   init_word(i, flags)                      initial value of state word i
-//   receive(out, self, st, src, type, p0, p1, flags)    scalar, runs on lane 0
-//   invariant_lane(states, flags, lane)      lane-parallel; engine takes the
-//                                            minimum non-zero code over lanes
+//   receive<S,O>(out, self, st, src, type, p0, p1, flags)   scalar transition.
+//       S = state accessor of ONE actor (st.b(i) byte i, st.w(i) word i), so the
+//       same source runs over contiguous shared memory (warp engine, lane 0)
+//       and over thread-interleaved shared memory (lane engine, every thread).
+//   invariant_lane(states, flags, lane)      warp engine: lane-parallel; the
+//                                            engine takes the minimum non-zero code
+//   invariant<A>(all, flags)                 lane engine: scalar over all actors;
+//                                            all.actor(a) is an S accessor
+//   timer_slot / slot_msg                    lane engine: the model's finite timer
+//                                            universe (<= 32 (receiver,msg) keys)
+//   LANE_OUTBOX                              lane engine: max ops of one receive()
 #pragma once
 #include "../machine.cuh"
 
@@ -27,14 +35,25 @@ struct PingPong3 {
   static constexpr int ID = DEMI_MODEL_PINGPONG3;
   enum { PING = 1, PONG = 2 };
   __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
-  __device__ static __forceinline__ void receive(Outbox& out, uint32_t self, uint32_t* st, uint32_t /*src*/,
+  static constexpr int LANE_OUTBOX = 2;
+  template <class S, class O>
+  __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
                                                  uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
     if (type == PING) {
-      st[0]++;
+      st.w(0)++;
       out.send((self + 1) % 3, PONG, p0, 0);
     } else if (type == PONG) {
-      st[1]++;
+      st.w(1)++;
     }
+  }
+  template <class A>
+  __device__ static __forceinline__ uint32_t invariant(A all, uint32_t flags) {
+    if ((flags & 1u) && all.actor(0).w(1) >= (flags >> 8)) return 7;
+    return 0;
+  }
+  __device__ static __forceinline__ int timer_slot(uint32_t, uint32_t, uint32_t, uint32_t) { return -1; }
+  __device__ static __forceinline__ void slot_msg(uint32_t, uint32_t& dst, uint32_t& type, uint32_t& p0, uint32_t& p1) {
+    dst = type = p0 = p1 = 0;
   }
   // flags bit0: test hook — code 7 once actor 0 has received >= (flags>>8) pongs
   __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t flags, uint32_t lane) {
@@ -64,13 +83,26 @@ struct Raft5 {
     return (i % STATE_WORDS == 0) ? (NONE << 16) : 0u;      // byte 2 = votedFor = none
   }
 
-  __device__ static __forceinline__ void step_down(Outbox& out, uint8_t* s, uint32_t t) {
+  static constexpr int LANE_OUTBOX = 6;
+  // timer universe: (actor, ELECTION_TICK) -> 2*actor, (actor, HEARTBEAT_TICK) -> 2*actor+1
+  __device__ static __forceinline__ int timer_slot(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
+    if ((type != ELECTION_TICK && type != HEARTBEAT_TICK) || p0 || p1 || dst >= 5) return -1;
+    return (int)(dst * 2 + (type == HEARTBEAT_TICK ? 1u : 0u));
+  }
+  __device__ static __forceinline__ void slot_msg(uint32_t slot, uint32_t& dst, uint32_t& type, uint32_t& p0, uint32_t& p1) {
+    dst = slot >> 1; type = (slot & 1u) ? HEARTBEAT_TICK : ELECTION_TICK; p0 = 0; p1 = 0;
+  }
+
+  // S is an accessor: s[i] is byte i of this actor's state
+  template <class S, class O>
+  __device__ static __forceinline__ void step_down(O& out, S& s, uint32_t t) {
     if (s[ROLE] == LEADER) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
     if (t > s[TERM]) { s[TERM] = (uint8_t)t; s[VOTED] = (uint8_t)NONE; }
     s[ROLE] = FOLLOWER;
     s[VOTES] = 0;
   }
-  __device__ static __forceinline__ void send_append(Outbox& out, const uint8_t* s, uint32_t j) {
+  template <class S, class O>
+  __device__ static __forceinline__ void send_append(O& out, S& s, uint32_t j) {
     uint32_t prev = s[NEXT + j];
     uint32_t pt = prev ? s[LOGTERM + prev - 1] : 0u;
     uint32_t has = prev < s[LOGLEN] ? 1u : 0u;
@@ -79,9 +111,9 @@ struct Raft5 {
              has | (et << 8) | (ev << 16));
   }
 
-  __device__ static __noinline__ void receive(Outbox& out, uint32_t self, uint32_t* stw, uint32_t src,
-                                              uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
-    uint8_t* s = reinterpret_cast<uint8_t*>(stw);
+  template <class S, class O>
+  __device__ static __forceinline__ void receive(O& out, uint32_t self, S s, uint32_t src,
+                                                 uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
     const uint32_t last_idx = s[LOGLEN];
     const uint32_t last_term = last_idx ? s[LOGTERM + last_idx - 1] : 0u;
     const uint32_t t = p0 & 0xFF;
@@ -203,6 +235,21 @@ struct Raft5 {
       if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) return 2;
     return 0;
   }
+  template <class A>
+  __device__ static __forceinline__ uint32_t invariant(A all, uint32_t) {
+    uint32_t code = 0;
+    for (uint32_t i = 0; i < 5; i++)
+      for (uint32_t j = i + 1; j < 5; j++) {
+        auto a = all.actor(i);
+        auto b = all.actor(j);
+        if (a[ROLE] == LEADER && b[ROLE] == LEADER && a[TERM] == b[TERM]) return 1;
+        if (code) continue;
+        uint32_t c = a[COMMIT] < b[COMMIT] ? a[COMMIT] : b[COMMIT];
+        for (uint32_t k = 0; k < c; k++)
+          if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) code = 2;
+      }
+    return code;
+  }
 };
 
 // ------------------------------------------------------------------ bcast32
@@ -214,11 +261,12 @@ struct Bcast32 {
   static constexpr int ID = DEMI_MODEL_BCAST32;
   enum { FLOOD = 1 };
   __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
-  __device__ static __forceinline__ void receive(Outbox& out, uint32_t self, uint32_t* st, uint32_t /*src*/,
+  template <class S, class O>
+  __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
                                                  uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
     if (type != FLOOD) return;
-    st[0]++;
-    if (p0 + 1 > st[1]) st[1] = p0 + 1;
+    st.w(0)++;
+    if (p0 + 1 > st.w(1)) st.w(1) = p0 + 1;
     if (p0 > 0)
       for (uint32_t j = 0; j < 32; j++) if (j != self) out.send(j, FLOOD, p0 - 1, 0);
   }

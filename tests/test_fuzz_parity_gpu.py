@@ -33,8 +33,18 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["lane+warp", "warp-only"])
+def engine_mode(request, monkeypatch):
+    """Both engines must be bit-exact: K1-lane (+ deferred prefixes on the warp engine) and the warp engine alone."""
+    if request.param == "warp-only":
+        monkeypatch.setenv("DEMI_DISABLE_LANE_ENGINE", "1")
+    else:
+        monkeypatch.delenv("DEMI_DISABLE_LANE_ENGINE", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_fuzz_batch_matches_oracle(case, oracle):
+def test_fuzz_batch_matches_oracle(case, oracle, engine_mode):
     _, model, prog, flags, maxm, interval, n, blocked, ignore = case
     ext = D.pack_externals(prog())
     eng = D.Engine(D.SchedulerConfig(model, model_flags=flags, blocked_mask=blocked, ignoreTimers=bool(ignore)))
@@ -46,7 +56,7 @@ def test_fuzz_batch_matches_oracle(case, oracle):
     assert (gpu["status"] == 0).all()
 
 
-def test_partition_kill_segments(oracle):
+def test_partition_kill_segments(oracle, engine_mode):
     """Kill / Partition / UnPartition between quiescent segments (EventOrchestrator.scala:132-189)."""
     ev = [D.Start(a) for a in range(3)]
     ev += [D.Send(k % 3, 1, k) for k in range(12)]
