@@ -238,10 +238,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "prefixes/s", "h2d_bytes_per_step": int(ext.nbytes),
                     "d2h_bytes_per_step": n * RESULT_BYTES + 16, "steps": e2e_steps,
                     "violations_last_step_rank0": last_viol},
-            "gpu_launches": K,
+            "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                         "kernel": "fuzz_kernel<Raft5,256,32>", "algorithmic_bytes_per_prefix": RESULT_BYTES,
+                         "kernel": "fuzz_lane_kernel<Raft5,256,96> (+ fuzz_kernel<Raft5,256,32> for deferred prefixes)", "algorithmic_bytes_per_prefix": RESULT_BYTES,
                          "kernel_ms": k_ms,
                          "note": "on-chip-state fuzz regime (SURVEY §8d R1): the only algorithmic HBM traffic is "
                                  "the 32 B result record, so the kernel is issue-slot bound, not HBM bound; see "

@@ -1,0 +1,169 @@
+"""Pins the CPU oracle against the known-answer material derivable from the
+reference: there are no golden vectors in DEMi itself."""
+import numpy as np
+
+from demi_b200 import _native as N
+from demi_b200 import events as E
+
+
+def u32(x):
+    return x & 0xFFFFFFFF
+
+
+def test_java_util_random_known_values(oracle):
+    # Java SE spec values: new Random(42).nextInt(), new Random(0).nextInt()
+    assert oracle.kat_jrandom(42, 0, 2) == [-1170105035, 234785527]
+    assert oracle.kat_jrandom(0, 0, 2) == [-1155484576, -723955400]
+
+
+def test_java_util_random_bounded_follows_spec(oracle):
+    for seed in (42, 0, 1, -5, 2**40 + 17):
+        raw = oracle.kat_jrandom(seed, 0, 64)
+        # nextInt(n), n not a power of two, no rejection for small n: next(31) % n
+        b10 = oracle.kat_jrandom(seed, 10, 64)
+        assert b10 == [(u32(r) >> 1) % 10 for r in raw]
+        # power of two: (n * next(31)) >> 31
+        b16 = oracle.kat_jrandom(seed, 16, 64)
+        assert b16 == [(16 * (u32(r) >> 1)) >> 31 for r in raw]
+        assert all(0 <= v < 10 for v in b10)
+
+
+def test_java_util_random_rejection_loop(oracle):
+    # bound just above 2^30 rejects about half of the draws: replay the spec in python
+    bound = (1 << 30) + 1
+    seed = 12345
+    mask = (1 << 48) - 1
+    s = (seed ^ 0x5DEECE66D) & mask
+
+    def next31():
+        nonlocal s
+        s = (s * 0x5DEECE66D + 0xB) & mask
+        return s >> 17
+
+    exp = []
+    for _ in range(50):
+        bits = next31()
+        val = bits % bound
+        while bits - val + (bound - 1) >= (1 << 31):      # int32 overflow => negative
+            bits = next31()
+            val = bits % bound
+        exp.append(val)
+    assert oracle.kat_jrandom(seed, bound, 50) == exp
+
+
+def test_randomized_hashset_swap_remove_order(oracle):
+    # insert a,b,c,d; remove index 1 -> [a,d,c]  (schedulers/Util.scala:155-160)
+    arr, removed = oracle.kat_hashset(1, [10, 11, 12, 13, -1001])
+    assert arr == [10, 13, 12] and removed == [11]
+    # removing the last element just shrinks
+    arr, removed = oracle.kat_hashset(1, [10, 11, 12, -1002])
+    assert arr == [10, 11] and removed == [12]
+
+
+def test_randomized_hashset_remove_random_uses_nextint_of_length(oracle):
+    seed = 7
+    tags = list(range(100, 110))
+    arr, removed = oracle.kat_hashset(seed, tags + [-1] * 10)
+    # replay: idx = nextInt(len); v = arr[idx]; arr[idx] = arr[last]; shrink (Util.scala:171-176)
+    mask = (1 << 48) - 1
+    s = (seed ^ 0x5DEECE66D) & mask
+    cur, exp = list(tags), []
+    while cur:
+        n = len(cur)
+        s = (s * 0x5DEECE66D + 0xB) & mask
+        r = s >> 17
+        idx = (n * r) >> 31 if n & (n - 1) == 0 else r % n       # no rejection for tiny n
+        exp.append(cur[idx])
+        cur[idx] = cur[-1]
+        cur.pop()
+    assert removed == exp and arr == []
+
+
+def test_find_non_blocked_reappends_rejected_draws_in_draw_order(oracle):
+    # receivers = tag & 31; block receiver 1.  (schedulers/Util.scala:470-489)
+    tags = [32 * k + (1 if k % 2 else 2) for k in range(8)]       # odd k -> receiver 1 (blocked)
+    seed = 3
+    arr, removed = oracle.kat_hashset(seed, tags + [-2], blocked_mask=1 << 1)
+    mask = (1 << 48) - 1
+    s = (seed ^ 0x5DEECE66D) & mask
+    cur, blocked, got = list(tags), [], None
+    while True:
+        n = len(cur)
+        s = (s * 0x5DEECE66D + 0xB) & mask
+        r = s >> 17
+        idx = (n * r) >> 31 if n & (n - 1) == 0 else r % n
+        v = cur[idx]
+        cur[idx] = cur[-1]
+        cur.pop()
+        if (v & 31) == 1:
+            blocked.append(v)
+            if not cur:
+                break
+            continue
+        got = v
+        break
+    assert removed == [got if got is not None else -1]
+    assert arr == cur + blocked
+    # everything blocked -> None, and all elements are back (in draw order)
+    arr2, removed2 = oracle.kat_hashset(seed, [1, 33, 65, -2], blocked_mask=1 << 1)
+    assert removed2 == [-1] and sorted(arr2) == [1, 33, 65]
+
+
+def test_pingpong_config0_plumbing(oracle):
+    """BASELINE.json configs[0]: 3-actor ping-pong, 100 external messages, seed = 1 (CPU only)."""
+    ext = E.pack_externals(E.pingpong3_program(100))
+    ev, par, res = oracle.fuzz_trace(N.MODEL_PINGPONG3, ext, 1, -1, 0)
+    assert res["status"] == 0 and res["violation"] == 0
+    assert res["steps"] == 200                                     # 100 pings + 100 pongs delivered
+    sends = ev[ev["kind"] == N.EV_MSG_SEND]
+    dels = ev[ev["kind"] == N.EV_MSG_EVENT]
+    assert len(sends) == 200 and len(dels) == 200
+    # every delivery was sent before it, exactly once (Uniq ids pair sends with deliveries)
+    assert sorted(sends["uniq"]) == sorted(dels["uniq"]) == list(range(1, 201))
+    pos_send = {int(u): i for i, u in enumerate(ev["uniq"]) if ev["kind"][i] == N.EV_MSG_SEND}
+    for i, e in enumerate(ev):
+        if e["kind"] == N.EV_MSG_EVENT:
+            assert pos_send[int(e["uniq"])] < i
+    # dep tree: externals hang off the root, each pong off the delivery of its ping
+    assert par[0] == 0 and len(par) == res["n_nodes"] == 201
+    ping_nodes = {int(e["node"]) for e in sends if e["type"] == 1}
+    for e in sends:
+        if e["type"] == 1:
+            assert par[int(e["node"])] == 0
+        else:
+            assert int(par[int(e["node"])]) in ping_nodes
+    # determinism
+    ev2, par2, res2 = oracle.fuzz_trace(N.MODEL_PINGPONG3, ext, 1, -1, 0)
+    assert (ev == ev2).all() and res == res2
+    ev3, _, _ = oracle.fuzz_trace(N.MODEL_PINGPONG3, ext, 2, -1, 0)
+    assert not (ev3 == ev).all()
+
+
+def test_raft_model_sanity(oracle):
+    ext = E.pack_externals(E.raft5_program())
+    good = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 20000, 50, 5, model_flags=0)
+    assert (good["violation"] == 0).all() and (good["status"] == 0).all() and (good["steps"] == 51).all()
+    bad = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 20000, 50, 5, model_flags=1)
+    assert (bad["violation"] == 1).sum() > 100                      # the seeded double-vote bug is found
+    assert (bad["status"] == 0).all()
+    # maxMessages exceeded => the final invariant check is skipped (RandomScheduler.scala:256)
+    assert ((bad["violation"] == 0) | (bad["steps"] % 5 == 0)).all()
+    # looking for a code that never occurs finds nothing (violationMatches, RandomScheduler.scala:138-154)
+    none = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 2000, 50, 5, model_flags=1, looking_for=9)
+    assert (none["violation"] == 0).all()
+    # thread count does not change results
+    one = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 3000, 50, 5, model_flags=1, threads=1)
+    assert (one == bad[:3000]).all()
+
+
+def test_timer_rules(oracle):
+    """ignoreTimers (ExternalEventInjector.scala:283-285): with timers ignored raft5 only boots and quiesces."""
+    ext = E.pack_externals(E.raft5_program(client_cmds=2))
+    r = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 200, -1, 0, ignore_timers=1)
+    assert (r["steps"] == 7).all() and (r["violation"] == 0).all()
+    ev, _, _ = oracle.fuzz_trace(N.MODEL_RAFT5, ext, 5, 50, 5)
+    timers = ev[(ev["kind"] == N.EV_MSG_SEND) & (ev["src"] == N.TIMER_SND)]
+    assert len(timers) > 0 and set(timers["type"]) <= {3, 6}
+    # a timer delivery is recorded with sender deadLetters, its send with "Timer" (RandomScheduler.scala:319)
+    td = ev[(ev["kind"] == N.EV_MSG_EVENT) & (ev["src"] == N.DEADLETTERS) & (ev["type"] == 3)]
+    assert len(td) > 0
