@@ -42,6 +42,19 @@ EVENT_DTYPE = np.dtype([("kind", "u1"), ("src", "u1"), ("dst", "u1"), ("type", "
                         ("p0", "<u4"), ("p1", "<u4"), ("uniq", "<u2"), ("node", "<u2")])
 RESULT_DTYPE = np.dtype([("violation", "<u4"), ("steps", "<u4"), ("state_hash", "<u8"), ("trace_hash", "<u8"),
                          ("n_nodes", "<u2"), ("n_events", "<u2"), ("max_pending", "<u2"), ("status", "<u2")])
+REPLAY_DTYPE = np.dtype([("violation", "<u2"), ("status", "<u2"), ("delivered", "<u2"), ("ignored", "<u2"),
+                         ("state_hash", "<u8")])
+RF_FILTER_KNOWN_ABSENTS, RF_STRICT = 1, 2
+RS_DIVERGED, RS_UNSUPPORTED = 16, 17
+
+
+class DDMinOut(C.Structure):
+    _fields_ = [("mcs_size", C.c_uint32), ("total_replays", C.c_uint32), ("n_iterations", C.c_uint32),
+                ("replays_executed", C.c_uint32), ("batches", C.c_uint32), ("verified", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
+
+
+assert REPLAY_DTYPE.itemsize == 16
 assert EXT_DTYPE.itemsize == 16 and EVENT_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 32
 
 # every symbol include/demi_b200.h declares
@@ -49,6 +62,7 @@ EXPORTS = [
     "demi_version", "demi_last_error", "demi_device_count", "demi_create", "demi_destroy",
     "demi_set_externals", "demi_fuzz_batch", "demi_fuzz_batch_dev", "demi_fuzz_summary_dev",
     "demi_fuzz_trace", "demi_stats",
+    "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin",
 ]
 
 _lib = None
@@ -84,6 +98,15 @@ def lib():
     L.demi_fuzz_trace.restype = C.c_int32
     L.demi_fuzz_trace.argtypes = [vp, C.POINTER(FuzzParams), C.c_int64, vp, C.c_uint32, C.POINTER(C.c_uint32),
                                   vp, C.c_uint32, C.POINTER(C.c_uint32), vp]
+    L.demi_set_trace.restype = C.c_int32
+    L.demi_set_trace.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32]
+    L.demi_replay_batch.restype = C.c_int32
+    L.demi_replay_batch.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.demi_replay_batch_dev.restype = C.c_int32
+    L.demi_replay_batch_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    L.demi_ddmin.restype = C.c_int32
+    L.demi_ddmin.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int32, vp, C.c_uint32, vp, C.c_uint32,
+                             C.POINTER(DDMinOut)]
     L.demi_stats.restype = C.c_int32
     L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
     _lib = L

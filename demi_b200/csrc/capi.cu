@@ -14,44 +14,9 @@
 
 using namespace demi;
 
-static thread_local std::string g_create_error;
+#include "engine.hpp"
 
-struct demi_handle {
-  demi_config cfg{};
-  std::string err;
-  int sm_count = 0;
-  // external program
-  std::vector<demi_ext_event> ext_host;
-  demi_ext_event* ext_dev = nullptr;
-  uint32_t n_ext_sends = 0;
-  // device buffers
-  demi_fuzz_result* results_dev = nullptr; size_t results_cap = 0;
-  uint4* node_scratch = nullptr; size_t node_scratch_bytes = 0;
-  uint4* pend_scratch = nullptr; size_t pend_scratch_bytes = 0;
-  unsigned long long* counters_dev = nullptr;      // [0]=sum_steps [1]=n_violations
-  // lane engine
-  uint4* ext_sends_dev = nullptr;
-  bool has_partitions = false, ext_sends_distinct = true;
-  uint4* lane_pend = nullptr; size_t lane_pend_bytes = 0;
-  uint32_t* ovf_list = nullptr; size_t ovf_list_bytes = 0;
-  uint32_t* ovf_count = nullptr;
-  int use_lane_engine = 1;
-  uint32_t* rec_counts_dev = nullptr;
-  // pinned staging for host transfers
-  void* pinned = nullptr; size_t pinned_bytes = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  demi_perf perf{};
-};
-
-static int32_t fail(demi_handle* h, int32_t code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-  if (h) h->err = buf; else g_create_error = buf;
-  return code;
-}
-#define CUDA_TRY(h, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
-  return fail((h), DEMI_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+thread_local std::string g_create_error;
 
 // ------------------------------------------------------------ kernel table
 constexpr int WARPS = 4;
@@ -146,6 +111,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
   cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
   cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count);
+  demi_replay_free(h);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);

@@ -1,0 +1,366 @@
+// capi_replay.cu — C ABI for STSSched replay batches (K2) and DDMin.
+//
+// DDMin (minification/DeltaDebugging.scala:27-109) is sequential by definition:
+// every test depends on the outcome of the previous one.  Here the recursion is
+// still walked in exactly that order (so the decisions, the MCS and the
+// MinimizationStats counters are the sequential ones), but test outcomes come
+// from a memo that is filled speculatively: whenever the walk needs a test that
+// has not been evaluated, the possible futures of the current ddmin2 frame (and of
+// the interference siblings waiting on the recursion stack) are expanded a few
+// levels deep and evaluated in ONE kernel launch.
+#include <map>
+#include <deque>
+#include "replay_kernel.cuh"
+#include "engine.hpp"
+
+using namespace demi;
+
+typedef void (*replay_fn)(const ReplayArgs);
+struct ReplayVariant { int model; int bd; replay_fn fn; size_t smem; int n_actors; };
+template <class MODEL, int BD>
+static ReplayVariant make_rv() {
+  using M = ReplayMachine<MODEL, BD>;
+  return ReplayVariant{MODEL::ID, BD, replay_lane_kernel<MODEL, BD>, (size_t)M::WORDS * BD * sizeof(uint32_t), MODEL::N_ACTORS};
+}
+static const ReplayVariant* pick_rv(int model) {
+  static const std::vector<ReplayVariant> v = {
+    make_rv<PingPong3, 256>(), make_rv<Raft5, 256>(), make_rv<Bcast32, 128>(),
+  };
+  for (const ReplayVariant& r : v) if (r.model == model) return &r;
+  return nullptr;
+}
+
+void demi_replay_free(demi_handle* h) {
+  cudaFree(h->trace_dev); cudaFree(h->trace_ext_dev); cudaFree(h->ev_ordinal_dev); cudaFree(h->send_ext_index_dev);
+  cudaFree(h->rp_table); cudaFree(h->rp_tosend); cudaFree(h->rp_pruned); cudaFree(h->rp_masks); cudaFree(h->rp_results);
+  cudaFree(h->rp_counters);
+}
+
+extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint32_t n_events,
+                                  const demi_ext_event* externals, uint32_t n_externals) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!events || !n_events || !externals || !n_externals)
+    return fail(h, DEMI_ERR_INVALID, "demi_set_trace: empty trace or externals");   // assume(!original_trace.isEmpty)
+  if (n_externals > 4096) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: more than 4096 external events");
+  if (n_events >= (1u << 31)) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: trace too long");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const uint32_t ext_mask = demi_external_type_mask(h->cfg.model);
+  // FIFO correspondence of external MsgSends and original Sends (EventTrace.scala:385-386, :419-436)
+  std::vector<uint16_t> ordinal(n_events, 0xFFFF);
+  std::map<uint32_t, uint16_t> uniq_to_ord;
+  uint32_t ord = 0, max_uniq = 0, n_send_events = 0;
+  for (uint32_t i = 0; i < n_events; i++) {
+    const demi_event& e = events[i];
+    if (e.kind < DEMI_EV_MSG_SEND || e.kind > DEMI_EV_QUIESCENCE)
+      return fail(h, DEMI_ERR_INVALID, "demi_set_trace: event %u has unknown kind %u", i, e.kind);
+    if (e.kind == DEMI_EV_MSG_SEND) {
+      n_send_events++;
+      if (e.uniq > max_uniq) max_uniq = e.uniq;
+      if ((ext_mask >> (e.type & 31)) & 1u) {
+        if (ord >= 0xFFFF) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: too many external sends");
+        ordinal[i] = (uint16_t)ord; uniq_to_ord[e.uniq] = (uint16_t)ord; ord++;
+      }
+    }
+  }
+  for (uint32_t i = 0; i < n_events; i++)
+    if (events[i].kind == DEMI_EV_MSG_EVENT) {
+      auto it = uniq_to_ord.find(events[i].uniq);
+      if (it != uniq_to_ord.end()) ordinal[i] = it->second;
+      if (events[i].uniq > max_uniq) max_uniq = events[i].uniq;
+    }
+  std::vector<uint16_t> sidx;
+  for (uint32_t i = 0; i < n_externals; i++) if (externals[i].kind == DEMI_EXT_SEND) sidx.push_back((uint16_t)i);
+  h->trace_host.assign(events, events + n_events);
+  h->trace_ext_host.assign(externals, externals + n_externals);
+  h->send_ext_index_host = sidx;
+  h->trace_n_uniq = max_uniq + 1;
+  h->trace_n_send_events = n_send_events;
+  h->trace_n_ext_sends = (uint32_t)sidx.size();
+  cudaFree(h->trace_dev); cudaFree(h->trace_ext_dev); cudaFree(h->ev_ordinal_dev); cudaFree(h->send_ext_index_dev);
+  h->trace_dev = h->trace_ext_dev = nullptr; h->ev_ordinal_dev = h->send_ext_index_dev = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->trace_dev, n_events * sizeof(demi_event)));
+  CUDA_TRY(h, cudaMalloc(&h->trace_ext_dev, n_externals * sizeof(demi_ext_event)));
+  CUDA_TRY(h, cudaMalloc(&h->ev_ordinal_dev, n_events * sizeof(uint16_t)));
+  CUDA_TRY(h, cudaMalloc(&h->send_ext_index_dev, std::max<size_t>(sidx.size(), 1) * sizeof(uint16_t)));
+  CUDA_TRY(h, cudaMemcpy(h->trace_dev, events, n_events * sizeof(demi_event), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->trace_ext_dev, externals, n_externals * sizeof(demi_ext_event), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->ev_ordinal_dev, ordinal.data(), n_events * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  if (!sidx.empty())
+    CUDA_TRY(h, cudaMemcpy(h->send_ext_index_dev, sidx.data(), sidx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  if (!h->rp_counters) CUDA_TRY(h, cudaMalloc(&h->rp_counters, 2 * sizeof(unsigned long long)));
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, uint32_t n_masks, uint32_t mask_words,
+                                         uint32_t looking_for, uint32_t flags, void* out_dev, void* stream) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (h->trace_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
+  if (!masks_dev || !out_dev) return fail(h, DEMI_ERR_INVALID, "demi_replay_batch_dev: null buffer");
+  const uint32_t n_ext = (uint32_t)h->trace_ext_host.size();
+  if (mask_words * 64 < n_ext) return fail(h, DEMI_ERR_INVALID, "mask_words %u too small for %u externals", mask_words, n_ext);
+  if (n_masks == 0) return DEMI_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const ReplayVariant* rv = pick_rv(h->cfg.model);
+  if (!rv) return fail(h, DEMI_ERR_INVALID, "no replay kernel for model %d", h->cfg.model);
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaFuncSetAttribute(rv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv->smem));
+  int bps = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, rv->fn, rv->bd, rv->smem));
+  if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "replay kernel does not fit on an SM");
+  uint64_t want = ((uint64_t)n_masks + rv->bd - 1) / rv->bd;
+  int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * bps));
+  const uint64_t warps = (uint64_t)grid * (rv->bd / 32);
+
+  ReplayArgs a{};
+  a.model_flags = h->cfg.model_flags; a.blocked_mask = h->cfg.blocked_mask; a.ignore_timers = h->cfg.ignore_timers;
+  a.looking_for = looking_for; a.flags = flags;
+  a.events = (const uint4*)h->trace_dev; a.n_events = (uint32_t)h->trace_host.size();
+  a.ev_ordinal = h->ev_ordinal_dev;
+  a.ext = (const uint4*)h->trace_ext_dev; a.n_ext = n_ext;
+  a.send_ext_index = h->send_ext_index_dev; a.n_sends = h->trace_n_ext_sends;
+  a.external_type_mask = demi_external_type_mask(h->cfg.model);
+  a.n_uniq_words = (h->trace_n_uniq + 31) / 32;
+  a.masks = (const uint64_t*)masks_dev; a.n_masks = n_masks; a.mask_words = mask_words;
+  a.results = (demi_replay_result*)out_dev;
+  a.pending_cap = demi_replay_pending_cap(h->trace_n_send_events);
+  a.tosend_cap = demi_tosend_cap(h->trace_n_ext_sends);
+  a.table_slots = demi_pow2_at_least(4 * a.pending_cap, 256, 1u << 16);
+  int32_t rc;
+  const size_t table_bytes = warps * a.table_slots * 32 * sizeof(uint4);
+  const bool fresh_table = h->rp_table_bytes < table_bytes;
+  if ((rc = ensure_bytes(h, &h->rp_table, &h->rp_table_bytes, table_bytes)) != DEMI_OK) return rc;
+  if ((rc = ensure_bytes(h, &h->rp_tosend, &h->rp_tosend_bytes, warps * a.tosend_cap * 32 * sizeof(uint32_t))) != DEMI_OK) return rc;
+  if (flags & DEMI_RF_FILTER_KNOWN_ABSENTS)
+    if ((rc = ensure_bytes(h, &h->rp_pruned, &h->rp_pruned_bytes,
+                           warps * (a.n_uniq_words + rv->n_actors) * 32 * sizeof(uint32_t))) != DEMI_OK) return rc;
+  (void)fresh_table;
+  // generations restart at 1 every launch: clear the stamps
+  CUDA_TRY(h, cudaMemsetAsync(h->rp_table, 0, table_bytes, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->rp_counters, 0, 2 * sizeof(unsigned long long), s));
+  a.table = (uint4*)h->rp_table; a.tosend = (uint32_t*)h->rp_tosend;
+  a.pruned = (flags & DEMI_RF_FILTER_KNOWN_ABSENTS) ? (uint32_t*)h->rp_pruned : nullptr;
+  a.counters = h->rp_counters;
+  rv->fn<<<grid, rv->bd, rv->smem, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->perf.kernel_launches = 1;
+  h->perf.prefixes = n_masks;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_replay_batch(demi_handle* h, const uint64_t* masks, uint32_t n_masks, uint32_t mask_words,
+                                     uint32_t looking_for, uint32_t flags, demi_replay_result* out_host) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!masks || !out_host) return fail(h, DEMI_ERR_INVALID, "demi_replay_batch: null buffer");
+  if (n_masks == 0) return DEMI_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int32_t rc;
+  const size_t mbytes = (size_t)n_masks * mask_words * sizeof(uint64_t), rbytes = (size_t)n_masks * sizeof(demi_replay_result);
+  if ((rc = ensure_bytes(h, &h->rp_masks, &h->rp_masks_bytes, mbytes)) != DEMI_OK) return rc;
+  if ((rc = ensure_bytes(h, &h->rp_results, &h->rp_results_bytes, rbytes)) != DEMI_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->rp_masks, masks, mbytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  rc = demi_replay_batch_dev(h, h->rp_masks, n_masks, mask_words, looking_for, flags, h->rp_results, h->stream);
+  if (rc != DEMI_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->rp_results, rbytes, cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long c[2] = {0, 0};
+  CUDA_TRY(h, cudaMemcpyAsync(c, h->rp_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->perf.kernel_ms = ms; h->perf.violations = c[0]; h->perf.deliveries = c[1];
+  h->perf.h2d_bytes = mbytes; h->perf.d2h_bytes = rbytes + sizeof(c);
+  return DEMI_OK;
+}
+
+// ---------------------------------------------------------------------- DDMin
+namespace {
+
+typedef std::vector<uint64_t> Mask;
+
+struct Atom { uint32_t first, second; };
+
+struct DDMinDriver {
+  demi_handle* h;
+  uint32_t looking_for, flags, mw, n_ext;
+  const demi_ext_event* ext;
+  std::map<Mask, bool> memo;           // mask -> violation reproduced?
+  uint32_t original_num_events = 0, total_inputs_pruned = 0, total_replays = 0;
+  std::vector<uint32_t> iteration_sizes;
+  uint32_t replays_executed = 0, batches = 0;
+  int32_t error = DEMI_OK;
+  bool malformed = false;
+  // interference siblings waiting on the recursion stack: (dag, remainder)
+  std::vector<std::pair<Mask, Mask>> pending_siblings;
+  static constexpr size_t BATCH_TARGET = 4096;
+
+  static bool bit(const Mask& m, uint32_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
+  static void setbit(Mask& m, uint32_t i) { m[i >> 6] |= 1ull << (i & 63); }
+  static uint32_t popcount(const Mask& m) { uint32_t c = 0; for (uint64_t w : m) c += (uint32_t)__builtin_popcountll(w); return c; }
+  static Mask unite(const Mask& a, const Mask& b) { Mask r(a.size()); for (size_t i = 0; i < a.size(); i++) r[i] = a[i] | b[i]; return r; }
+
+  // UnmodifiedEventDag.get_atomic_events (minification/Util.scala:197-265)
+  bool atomic_events(const Mask& dag, std::vector<Atom>& atoms) const {
+    std::vector<int32_t> last_start(DEMI_MAX_ACTORS, -1);
+    std::map<std::pair<int, int>, int32_t> last_part;
+    atoms.clear();
+    for (uint32_t i = 0; i < n_ext; i++) {
+      if (!bit(dag, i)) continue;
+      const demi_ext_event& e = ext[i];
+      switch (e.kind) {
+        case DEMI_EXT_KILL:
+          if (last_start[e.a] < 0) return false;                  // "Kill without preceding Start"
+          atoms.push_back({(uint32_t)last_start[e.a], i}); last_start[e.a] = -1; break;
+        case DEMI_EXT_START: last_start[e.a] = (int32_t)i; break;
+        case DEMI_EXT_PARTITION: last_part[{e.a, e.b}] = (int32_t)i; break;
+        case DEMI_EXT_UNPARTITION: {
+          auto it = last_part.find({e.a, e.b});
+          if (it == last_part.end() || it->second < 0) return false;   // "UnPartition without preceding Partition"
+          atoms.push_back({(uint32_t)it->second, i}); it->second = -1; break;
+        }
+        default: atoms.push_back({i, 0xFFFFFFFFu}); break;
+      }
+    }
+    for (int a = 0; a < DEMI_MAX_ACTORS; a++) if (last_start[a] >= 0) atoms.push_back({(uint32_t)last_start[a], 0xFFFFFFFFu});
+    for (auto& kv : last_part) if (kv.second >= 0) atoms.push_back({(uint32_t)kv.second, 0xFFFFFFFFu});
+    std::stable_sort(atoms.begin(), atoms.end(), [](const Atom& x, const Atom& y) { return x.first < y.first; });
+    return true;
+  }
+  // MinificationUtil.split_list(atoms, 2) (minification/Util.scala:9-37) + remove_events:
+  // halves[0] = events of the first chunk, halves[1] = events of the second.
+  bool halves(const Mask& dag, Mask out[2], size_t& n_atoms) const {
+    std::vector<Atom> atoms;
+    if (!atomic_events(dag, atoms)) return false;
+    n_atoms = atoms.size();
+    size_t n0 = atoms.size() / 2 + (atoms.size() % 2 ? 1 : 0);
+    out[0].assign(mw, 0); out[1].assign(mw, 0);
+    for (size_t i = 0; i < atoms.size(); i++) {
+      Mask& s = out[i < n0 ? 0 : 1];
+      setbit(s, atoms[i].first);
+      if (atoms[i].second != 0xFFFFFFFFu) setbit(s, atoms[i].second);
+    }
+    return true;
+  }
+
+  // speculative closure of the tests ddmin2(dag, rem) may issue, `depth` levels deep
+  void expand(const Mask& dag, const Mask& rem, int depth, std::vector<Mask>& want) {
+    if (want.size() >= 4 * BATCH_TARGET) return;
+    Mask hv[2]; size_t na;
+    if (!halves(dag, hv, na) || na <= 1) return;
+    for (int k = 0; k < 2; k++) {
+      Mask t = unite(hv[k], rem);
+      if (!memo.count(t)) want.push_back(t);
+    }
+    if (depth <= 0) return;
+    expand(hv[0], rem, depth - 1, want);                       // left half violates
+    expand(hv[1], rem, depth - 1, want);                       // right half violates
+    expand(hv[0], unite(hv[1], rem), depth - 1, want);         // interference
+    expand(hv[1], unite(hv[0], rem), depth - 1, want);
+  }
+
+  void evaluate(std::vector<Mask>& want) {
+    std::sort(want.begin(), want.end());
+    want.erase(std::unique(want.begin(), want.end()), want.end());
+    if (want.empty()) return;
+    std::vector<uint64_t> flat(want.size() * mw);
+    for (size_t i = 0; i < want.size(); i++) std::copy(want[i].begin(), want[i].end(), flat.begin() + i * mw);
+    std::vector<demi_replay_result> res(want.size());
+    int32_t rc = demi_replay_batch(h, flat.data(), (uint32_t)want.size(), mw, looking_for, flags, res.data());
+    if (rc != DEMI_OK) { error = rc; return; }
+    for (size_t i = 0; i < want.size(); i++) {
+      if (res[i].status != 0) { error = fail(h, DEMI_ERR_CAPACITY, "demi_ddmin: a replay reported status %u", (unsigned)res[i].status); return; }
+      memo[want[i]] = res[i].violation != 0;
+    }
+    replays_executed += (uint32_t)want.size();
+    batches++;
+  }
+
+  // TestOracle.test for the sequential walk
+  bool test(const Mask& m, const Mask& cur_dag, const Mask& cur_rem) {
+    auto it = memo.find(m);
+    if (it == memo.end()) {
+      std::vector<Mask> want;
+      want.push_back(m);
+      // depth: 4^d frames * 2 tests; stay near BATCH_TARGET
+      int depth = 5;
+      expand(cur_dag, cur_rem, depth, want);
+      for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend() && want.size() < BATCH_TARGET; ++it2)
+        expand(it2->first, it2->second, 3, want);
+      evaluate(want);
+      if (error != DEMI_OK) return false;
+      it = memo.find(m);
+    }
+    return it->second;
+  }
+
+  // DDMin.ddmin2 (DeltaDebugging.scala:73-109)
+  Mask ddmin2(const Mask& dag, const Mask& rem) {
+    if (error != DEMI_OK) return dag;
+    Mask hv[2]; size_t na;
+    if (!halves(dag, hv, na)) { malformed = true; error = fail(h, DEMI_ERR_INVALID, "demi_ddmin: Kill/UnPartition without preceding Start/Partition"); return dag; }
+    if (na <= 1) return dag;                                             // base case :74-77
+    const uint32_t dag_len = popcount(dag);
+    for (int k = 0; k < 2; k++) {                                        // :88-102
+      Mask t = unite(hv[k], rem);
+      bool violates = test(t, dag, rem);
+      if (error != DEMI_OK) return dag;
+      total_replays++;
+      iteration_sizes.push_back(original_num_events - total_inputs_pruned);
+      if (violates) {
+        total_inputs_pruned += dag_len - popcount(hv[k]);
+        return ddmin2(hv[k], rem);
+      }
+    }
+    // interference :104-108 — the right-hand recursion does not depend on the left-hand result
+    Mask rem_l = unite(hv[1], rem), rem_r = unite(hv[0], rem);
+    pending_siblings.push_back({hv[1], rem_r});
+    Mask left = ddmin2(hv[0], rem_l);
+    pending_siblings.pop_back();
+    Mask right = ddmin2(hv[1], rem_r);
+    return unite(left, right);
+  }
+};
+
+}  // namespace
+
+extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t flags, int32_t check_unmodified,
+                              uint64_t* mcs_mask, uint32_t mask_words,
+                              uint32_t* iteration_sizes, uint32_t cap_iterations, demi_ddmin_out* out) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!mcs_mask || !out) return fail(h, DEMI_ERR_INVALID, "demi_ddmin: null output");
+  if (h->trace_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
+  const uint32_t n_ext = (uint32_t)h->trace_ext_host.size();
+  if (mask_words * 64 < n_ext) return fail(h, DEMI_ERR_INVALID, "mask_words too small");
+  memset(out, 0, sizeof(*out));
+  DDMinDriver d;
+  d.h = h; d.looking_for = looking_for; d.flags = flags; d.mw = mask_words; d.n_ext = n_ext;
+  d.ext = h->trace_ext_host.data();
+  // STSSched ignores WaitQuiescence: drop them from the DAG (RunnerUtils.scala:678-684)
+  Mask dag(mask_words, 0), zero(mask_words, 0);
+  for (uint32_t i = 0; i < n_ext; i++) if (d.ext[i].kind != DEMI_EXT_WAIT_QUIESCENCE) DDMinDriver::setbit(dag, i);
+  if (check_unmodified) {                                                 // DeltaDebugging.scala:41-47
+    bool v = d.test(dag, dag, zero);
+    if (d.error != DEMI_OK) return d.error;
+    if (!v) return fail(h, DEMI_ERR_INVALID, "Unmodified trace does not trigger violation");
+  }
+  d.original_num_events = DDMinDriver::popcount(dag);
+  Mask mcs = d.ddmin2(dag, zero);
+  if (d.error != DEMI_OK) return d.error;
+  d.iteration_sizes.push_back(d.original_num_events - d.total_inputs_pruned);     // fencepost :60
+  // assert(original_num_events - total_inputs_pruned == mcs.length) :58
+  if (d.original_num_events - d.total_inputs_pruned != DDMinDriver::popcount(mcs))
+    return fail(h, DEMI_ERR_STATE, "demi_ddmin: bookkeeping assertion failed (DeltaDebugging.scala:58)");
+  std::copy(mcs.begin(), mcs.end(), mcs_mask);
+  // verify_mcs (DeltaDebugging.scala:64-71; RunnerUtils.scala:689-701)
+  bool verified = d.test(mcs, mcs, zero);
+  if (d.error != DEMI_OK) return d.error;
+  out->mcs_size = DDMinDriver::popcount(mcs);
+  out->total_replays = d.total_replays;
+  out->n_iterations = (uint32_t)d.iteration_sizes.size();
+  out->replays_executed = d.replays_executed;
+  out->batches = d.batches;
+  out->verified = verified ? 1u : 0u;
+  if (iteration_sizes)
+    for (uint32_t i = 0; i < cap_iterations && i < out->n_iterations; i++) iteration_sizes[i] = d.iteration_sizes[i];
+  return DEMI_OK;
+}

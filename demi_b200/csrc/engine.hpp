@@ -1,0 +1,77 @@
+// engine.hpp — the handle behind the C ABI, shared by capi.cu and capi_replay.cu.
+#pragma once
+#include <climits>
+#include <cstdlib>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/demi_b200.h"
+#include "../../include/demi_limits.h"
+
+extern thread_local std::string g_create_error;
+
+struct demi_handle {
+  demi_config cfg{};
+  std::string err;
+  int sm_count = 0;
+  // external program
+  std::vector<demi_ext_event> ext_host;
+  demi_ext_event* ext_dev = nullptr;
+  uint32_t n_ext_sends = 0;
+  // device buffers
+  demi_fuzz_result* results_dev = nullptr; size_t results_cap = 0;
+  uint4* node_scratch = nullptr; size_t node_scratch_bytes = 0;
+  uint4* pend_scratch = nullptr; size_t pend_scratch_bytes = 0;
+  unsigned long long* counters_dev = nullptr;      // [0]=sum_steps [1]=n_violations
+  // lane engine
+  uint4* ext_sends_dev = nullptr;
+  bool has_partitions = false, ext_sends_distinct = true;
+  uint4* lane_pend = nullptr; size_t lane_pend_bytes = 0;
+  uint32_t* ovf_list = nullptr; size_t ovf_list_bytes = 0;
+  uint32_t* ovf_count = nullptr;
+  int use_lane_engine = 1;
+  uint32_t* rec_counts_dev = nullptr;
+  // pinned staging for host transfers
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  demi_perf perf{};
+  // ---- STSSched replay / DDMin (capi_replay.cu)
+  std::vector<demi_event> trace_host;
+  std::vector<demi_ext_event> trace_ext_host;
+  std::vector<uint16_t> send_ext_index_host;
+  void* trace_dev = nullptr; void* trace_ext_dev = nullptr;
+  uint16_t* ev_ordinal_dev = nullptr; uint16_t* send_ext_index_dev = nullptr;
+  uint32_t trace_n_uniq = 0, trace_n_send_events = 0, trace_n_ext_sends = 0;
+  void* rp_table = nullptr; size_t rp_table_bytes = 0;
+  void* rp_tosend = nullptr; size_t rp_tosend_bytes = 0;
+  void* rp_pruned = nullptr; size_t rp_pruned_bytes = 0;
+  void* rp_masks = nullptr; size_t rp_masks_bytes = 0;
+  void* rp_results = nullptr; size_t rp_results_bytes = 0;
+  unsigned long long* rp_counters = nullptr;
+};
+void demi_replay_free(demi_handle* h);
+
+inline int32_t ensure_bytes(demi_handle* h, void** p, size_t* cap, size_t need);
+
+inline int32_t fail(demi_handle* h, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+#define CUDA_TRY(h, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return fail((h), DEMI_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+
+inline int32_t ensure_bytes(demi_handle* h, void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return DEMI_OK;
+  cudaFree(*p); *p = nullptr; *cap = 0;
+  CUDA_TRY(h, cudaMalloc(p, need));
+  *cap = need;
+  return DEMI_OK;
+}

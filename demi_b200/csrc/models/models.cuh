@@ -36,6 +36,7 @@ struct PingPong3 {
   enum { PING = 1, PONG = 2 };
   __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
   static constexpr int LANE_OUTBOX = 2;
+  static constexpr int REPLAY_OUTBOX = 2;
   template <class S, class O>
   __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
                                                  uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
@@ -84,6 +85,7 @@ struct Raft5 {
   }
 
   static constexpr int LANE_OUTBOX = 6;
+  static constexpr int REPLAY_OUTBOX = 6;
   // timer universe: (actor, ELECTION_TICK) -> 2*actor, (actor, HEARTBEAT_TICK) -> 2*actor+1
   __device__ static __forceinline__ int timer_slot(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
     if ((type != ELECTION_TICK && type != HEARTBEAT_TICK) || p0 || p1 || dst >= 5) return -1;
@@ -259,16 +261,27 @@ struct Bcast32 {
   static constexpr int N_ACTORS = 32;
   static constexpr int STATE_WORDS = 2;
   static constexpr int ID = DEMI_MODEL_BCAST32;
-  enum { FLOOD = 1 };
+  enum { FLOOD = 1, INJECT = 2 };      // INJECT: the external seed message, handled like FLOOD
   __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
   template <class S, class O>
   __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
                                                  uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
-    if (type != FLOOD) return;
+    if (type != FLOOD && type != INJECT) return;
     st.w(0)++;
     if (p0 + 1 > st.w(1)) st.w(1) = p0 + 1;
     if (p0 > 0)
       for (uint32_t j = 0; j < 32; j++) if (j != self) out.send(j, FLOOD, p0 - 1, 0);
+  }
+  static constexpr int REPLAY_OUTBOX = 32;
+  template <class A>
+  __device__ static __forceinline__ uint32_t invariant(A all, uint32_t flags) {
+    if (!flags) return 0;
+    for (uint32_t a = 0; a < 32; a++) if (all.actor(a).w(0) >= flags) return 3;
+    return 0;
+  }
+  __device__ static __forceinline__ int timer_slot(uint32_t, uint32_t, uint32_t, uint32_t) { return -1; }
+  __device__ static __forceinline__ void slot_msg(uint32_t, uint32_t& dst, uint32_t& type, uint32_t& p0, uint32_t& p1) {
+    dst = type = p0 = p1 = 0;
   }
   // code 3 once some actor has received >= flags floods (flags != 0)
   __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t flags, uint32_t lane) {

@@ -117,6 +117,6 @@ def pingpong3_program(n_sends=100):
 
 def bcast32_program(ttl=3):
     ev = [Start(a) for a in range(32)]
-    ev.append(Send(0, 1, ttl))                          # Bcast32::FLOOD
+    ev.append(Send(0, 2, ttl))                          # Bcast32::INJECT
     ev.append(WaitQuiescence())
     return ev

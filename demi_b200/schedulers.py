@@ -92,6 +92,39 @@ class Engine(object):
                                             par.ctypes.data, cap_nodes, C.byref(nn), res.ctypes.data))
         return ev[:ne.value].copy(), par[:nn.value].copy(), res[0]
 
+    # ---- STSSched replay / DDMin
+    def set_trace(self, events, externals):
+        ev = np.ascontiguousarray(events, dtype=N.EVENT_DTYPE)
+        ext = externals if isinstance(externals, np.ndarray) else pack_externals(externals)
+        ext = np.ascontiguousarray(ext, dtype=N.EXT_DTYPE)
+        self._trace, self._trace_ext = ev, ext
+        self._check(N.lib().demi_set_trace(self._h, ev.ctypes.data, len(ev), ext.ctypes.data, len(ext)))
+
+    def mask_words(self):
+        return max(1, (len(self._trace_ext) + 63) // 64)
+
+    def replay_batch(self, masks, looking_for=0, flags=0, out=None):
+        mw = self.mask_words()
+        masks = np.ascontiguousarray(masks, dtype=np.uint64).reshape(-1, mw)
+        if out is None:
+            out = np.empty(len(masks), dtype=N.REPLAY_DTYPE)
+        self._check(N.lib().demi_replay_batch(self._h, masks.ctypes.data, len(masks), mw, looking_for or 0, flags,
+                                              out.ctypes.data))
+        return out
+
+    def replay_batch_dev(self, masks_ptr, n_masks, out_ptr, looking_for=0, flags=0, stream=0):
+        self._check(N.lib().demi_replay_batch_dev(self._h, C.c_void_p(masks_ptr), n_masks, self.mask_words(),
+                                                  looking_for or 0, flags, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def ddmin(self, looking_for, flags=0, check_unmodified=True, cap_iterations=1 << 16):
+        mw = self.mask_words()
+        mcs = np.zeros(mw, dtype=np.uint64)
+        iters = np.zeros(cap_iterations, dtype=np.uint32)
+        out = N.DDMinOut()
+        self._check(N.lib().demi_ddmin(self._h, looking_for or 0, flags, 1 if check_unmodified else 0,
+                                       mcs.ctypes.data, mw, iters.ctypes.data, cap_iterations, C.byref(out)))
+        return mcs, iters[:min(out.n_iterations, cap_iterations)].copy(), out
+
     def stats(self):
         s = N.Perf()
         self._check(N.lib().demi_stats(self._h, C.byref(s)))
@@ -153,3 +186,109 @@ class RandomScheduler(object):
         self.stats = stats
         r = self.explore(events, violation_fingerprint)
         return None if r is None else r[0]
+
+
+def mask_of(externals, subseq):
+    """Seq[ExternalEvent] subsequence -> bitmask over the positions of `externals`."""
+    pos = {e._id: i for i, e in enumerate(externals)}
+    m = np.zeros(max(1, (len(externals) + 63) // 64), dtype=np.uint64)
+    for e in subseq:
+        i = pos[e._id]
+        m[i // 64] |= np.uint64(1) << np.uint64(i % 64)
+    return m
+
+
+def events_of(externals, mask):
+    return [e for i, e in enumerate(externals) if (int(mask[i // 64]) >> (i % 64)) & 1]
+
+
+class MinimizationStats(object):
+    """The counters of minification/Minimizer.scala:30-237 that DDMin drives."""
+
+    def __init__(self):
+        self.total_replays = 0
+        self.iteration_size = []
+
+    def increment_replays(self, n=1):
+        self.total_replays += n
+
+    def record_iteration_size(self, n):
+        self.iteration_size.append(n)
+
+
+class STSScheduler(object):
+    """STSScheduler(schedulerConfig, original_trace, allowPeek=false) — schedulers/STSScheduler.scala:84-86.
+    test() is TestOracle.test (:199-310): Some(trace) iff the violation was reproduced.
+    Peek (allowPeek=true) needs JVM actor-system checkpoints and is not offered."""
+
+    def __init__(self, schedulerConfig, original_trace, original_externals, allowPeek=False,
+                 filterKnownAbsents=False, engine=None):
+        if allowPeek:
+            raise NotImplementedError("STSSched with Peek is outside the accelerated path")
+        self.schedulerConfig = schedulerConfig
+        self.original_trace = original_trace
+        self.original_externals = list(original_externals)
+        self.flags = N.RF_FILTER_KNOWN_ABSENTS if filterKnownAbsents else 0
+        self.engine = engine or Engine(schedulerConfig)
+        self.engine.set_trace(original_trace, pack_externals(self.original_externals))
+        self.test_invariant = True
+
+    def getName(self):
+        return "STSSchedNoPeek"
+
+    def setInvariant(self, invariant):
+        self.test_invariant = invariant
+
+    def test(self, subseq, violation_fingerprint, stats=None):
+        if self.test_invariant is None:
+            raise ValueError("Must invoke setInvariant before test()")      # :208-210
+        if stats is not None:
+            stats.increment_replays()
+        r = self.engine.replay_batch(mask_of(self.original_externals, subseq), violation_fingerprint, self.flags)[0]
+        if r["status"]:
+            raise DemiError(N.ERR_CAPACITY, "replay status %d" % r["status"])
+        return r if r["violation"] else None
+
+    def test_batch(self, subseqs, violation_fingerprint):
+        masks = np.stack([mask_of(self.original_externals, s) for s in subseqs])
+        return self.engine.replay_batch(masks, violation_fingerprint, self.flags)
+
+
+class ReplayScheduler(STSScheduler):
+    """Strict replay (schedulers/ReplayScheduler.scala:71-140): an expected delivery
+    that is not pending raises ReplayException."""
+
+    class ReplayException(RuntimeError):
+        pass
+
+    def replay(self, violation_fingerprint=0):
+        full = [e for e in self.original_externals]
+        r = self.engine.replay_batch(mask_of(self.original_externals, full), violation_fingerprint,
+                                     self.flags | N.RF_STRICT)[0]
+        if r["status"] == N.RS_DIVERGED:
+            raise ReplayScheduler.ReplayException("Expected event not pending after %d deliveries" % r["delivered"])
+        if r["status"]:
+            raise DemiError(N.ERR_CAPACITY, "replay status %d" % r["status"])
+        return r
+
+
+class DDMin(object):
+    """DDMin(oracle, checkUnmodifed) — minification/DeltaDebugging.scala:7-109, with an
+    STSScheduler as the TestOracle (RunnerUtils.stsSchedDDMin, RunnerUtils.scala:642-707)."""
+
+    def __init__(self, oracle, checkUnmodifed=False, stats=None):
+        self.oracle = oracle
+        self.checkUnmodifed = checkUnmodifed
+        self._stats = stats or MinimizationStats()
+        self.last = None
+
+    def minimize(self, violation_fingerprint):
+        """Returns the MCS as a list of ExternalEvents (WaitQuiescence dropped, RunnerUtils.scala:678-684)."""
+        mcs, iters, out = self.oracle.engine.ddmin(violation_fingerprint, self.oracle.flags, self.checkUnmodifed)
+        self._stats.total_replays = out.total_replays
+        self._stats.iteration_size = [int(x) for x in iters]
+        self.last = out
+        return events_of(self.oracle.original_externals, mcs)
+
+    def verify_mcs(self, mcs, violation_fingerprint):
+        return self.oracle.test(mcs, violation_fingerprint)

@@ -194,6 +194,51 @@ int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, int64_t seed,
                         uint16_t* dep_parent, uint32_t cap_nodes, uint32_t* n_nodes,
                         demi_fuzz_result* result);
 
+/* ----------------------------------------------- STSSched replay and DDMin */
+/* Result of one STSScheduler.test (STSScheduler.scala:199-310). 16 bytes. */
+typedef struct demi_replay_result {
+  uint16_t violation;    /* matched violation code, 0 = test passes (None)          */
+  uint16_t status;       /* 0 ok, DEMI_PS_* overflow, DEMI_RS_DIVERGED (strict mode) */
+  uint16_t delivered;    /* expected deliveries that were pending and delivered      */
+  uint16_t ignored;      /* expected deliveries skipped ("Ignoring message", :528)   */
+  uint64_t state_hash;   /* hash of final actor states + delivered-message sequence  */
+} demi_replay_result;
+#define DEMI_RS_DIVERGED 16
+#define DEMI_RS_UNSUPPORTED 17      /* the test left the regime the batched engine restates exactly */
+#define DEMI_RF_FILTER_KNOWN_ABSENTS 0x1u  /* SchedulerConfig.filterKnownAbsents (SchedulerConfig.scala:14) */
+#define DEMI_RF_STRICT               0x2u  /* ReplayScheduler semantics: an absent expected delivery diverges */
+
+/* The recorded execution to minimise: STSScheduler.original_trace
+ * (STSScheduler.scala:85) and EventTrace.original_externals (EventTrace.scala:20).
+ * Usually the output of demi_fuzz_trace for a violating seed. */
+int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint32_t n_events,
+                       const demi_ext_event* externals, uint32_t n_externals);
+/* n_masks independent STSScheduler.test(subseq, fingerprint) calls.  Mask i is
+ * `mask_words` uint64 words; bit j selects external event j of the trace's
+ * original_externals.  looking_for = the ViolationFingerprint code (0 = any). */
+int32_t demi_replay_batch(demi_handle* h, const uint64_t* masks, uint32_t n_masks, uint32_t mask_words,
+                          uint32_t looking_for, uint32_t flags, demi_replay_result* out_host);
+int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, uint32_t n_masks, uint32_t mask_words,
+                              uint32_t looking_for, uint32_t flags, void* out_dev, void* stream);
+
+/* DDMin.minimize over the trace's externals with STSSched as the TestOracle
+ * (RunnerUtils.stsSchedDDMin, RunnerUtils.scala:642-707; DeltaDebugging.scala:27-109).
+ * WaitQuiescence externals are dropped first (RunnerUtils.scala:678-684).  The
+ * decision sequence, the MCS and the MinimizationStats counters are those of the
+ * sequential algorithm; tests are evaluated speculatively in batches. */
+typedef struct demi_ddmin_out {
+  uint32_t mcs_size;            /* number of external events in the MCS                 */
+  uint32_t total_replays;       /* tests the sequential algorithm issued (stats.total_replays) */
+  uint32_t n_iterations;        /* entries written to iteration_sizes                   */
+  uint32_t replays_executed;    /* tests actually evaluated on the GPU (incl. speculation) */
+  uint32_t batches;             /* kernel launches                                      */
+  uint32_t verified;            /* verify_mcs: 1 if the MCS still reproduces (DeltaDebugging.scala:64-71) */
+  uint32_t reserved[2];
+} demi_ddmin_out;
+int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t flags, int32_t check_unmodified,
+                   uint64_t* mcs_mask, uint32_t mask_words,
+                   uint32_t* iteration_sizes, uint32_t cap_iterations, demi_ddmin_out* out);
+
 /* ------------------------------------------------------------- statistics */
 int32_t demi_stats(const demi_handle* h, demi_perf* out);
 

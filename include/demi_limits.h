@@ -48,6 +48,16 @@ static inline uint32_t demi_node_cap(uint32_t pending_cap) {
   return c > 65535u ? 65535u : c;
 }
 
+/* STSSched replay: at most every recorded send can be pending at once. */
+static inline uint32_t demi_replay_pending_cap(uint32_t n_send_events) {
+  return demi_pow2_at_least(n_send_events + 8u, 64u, 8192u);
+}
+/* EventTypes.externalMessageFilter by message type, per built-in model
+ * (pingpong3: PING; raft5: BOOT, CLIENT_CMD; bcast32: INJECT). */
+static inline uint32_t demi_external_type_mask(int model) {
+  switch (model) { case 1: return 1u << 1; case 2: return (1u << 1) | (1u << 2); case 3: return 1u << 2; default: return 0; }
+}
+
 /* ---- hashes ---------------------------------------------------------------
  * Order-sensitive and cheap on a GPU: a 64-bit SUM of per-item terms; each
  * term is two independent 32-bit multiply-xor hashes (lo | hi<<32) of the

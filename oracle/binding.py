@@ -86,3 +86,103 @@ def kat_hashset(seed, ops, blocked_mask=0):
     n = lib().oracle_kat_hashset(C.c_int64(seed), C.c_uint32(blocked_mask), ops_a, C.c_int32(len(ops)),
                                  arr, removed, C.byref(nr))
     return list(arr[:n]), list(removed[:nr.value])
+
+
+# ------------------------------------------------------------ STS replay / DDMin
+REPLAY_DTYPE = np.dtype([("violation", "<u2"), ("status", "<u2"), ("delivered", "<u2"), ("ignored", "<u2"),
+                         ("state_hash", "<u8")])
+RF_FILTER_KNOWN_ABSENTS, RF_STRICT = 1, 2
+_EXT_TYPE_MASK = {1: 1 << 1, 2: (1 << 1) | (1 << 2), 3: 1 << 2}
+
+
+class ReplayInput(C.Structure):
+    _fields_ = [("events", C.c_void_p), ("n_events", C.c_uint32), ("externals", C.c_void_p),
+                ("n_externals", C.c_uint32), ("external_type_mask", C.c_uint32),
+                ("pending_cap", C.c_uint32), ("tosend_cap", C.c_uint32)]
+
+
+def _pow2_at_least(x, lo, hi):
+    c = lo
+    while c < x and c < hi:
+        c <<= 1
+    return c
+
+
+def make_replay_input(model, events, ext):
+    events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    n_send_ev = int((events["kind"] == 1).sum())
+    n_ext_sends = int((ext["kind"] == 3).sum())
+    ri = ReplayInput(events.ctypes.data, len(events), ext.ctypes.data, len(ext), _EXT_TYPE_MASK[model],
+                     _pow2_at_least(n_send_ev + 8, 64, 8192), _pow2_at_least(n_ext_sends + 16, 32, 1024))
+    ri._keep = (events, ext)
+    return ri
+
+
+def mask_words(n_ext):
+    return max(1, (n_ext + 63) // 64)
+
+
+def full_mask(ext, drop_wait_quiescence=True):
+    mw = mask_words(len(ext))
+    m = np.zeros(mw, dtype=np.uint64)
+    for i, e in enumerate(ext):
+        if drop_wait_quiescence and e["kind"] == 4:
+            continue
+        m[i // 64] |= np.uint64(1) << np.uint64(i % 64)
+    return m
+
+
+def replay_batch(model, events, ext, masks, looking_for=0, flags=0, model_flags=0, blocked_mask=0,
+                 ignore_timers=0, threads=None):
+    ri = make_replay_input(model, events, ext)
+    masks = np.ascontiguousarray(masks, dtype=np.uint64).reshape(-1, mask_words(len(ext)))
+    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers)
+    out = np.zeros(len(masks), dtype=REPLAY_DTYPE)
+    lib().oracle_replay_batch(C.byref(cfg), C.byref(ri), C.c_void_p(masks.ctypes.data), C.c_uint32(len(masks)),
+                              C.c_uint32(masks.shape[1]), C.c_uint32(looking_for), C.c_uint32(flags),
+                              C.c_void_p(out.ctypes.data), C.c_int(threads or (os.cpu_count() or 1)))
+    return out
+
+
+def project(model, events, ext, mask, filter_known_absents=False):
+    ri = make_replay_input(model, events, ext)
+    mask = np.ascontiguousarray(mask, dtype=np.uint64)
+    keep = np.zeros(len(events), dtype=np.uint8)
+    lib().oracle_sts_project(C.byref(ri), C.c_void_p(mask.ctypes.data), C.c_int(1 if filter_known_absents else 0),
+                             C.c_void_p(keep.ctypes.data))
+    return keep
+
+
+def ddmin_sts(model, events, ext, looking_for, flags=0, model_flags=0, check_unmodified=True, cap_iter=65536):
+    ri = make_replay_input(model, events, ext)
+    cfg = Config(0, model, model_flags, 0, 0)
+    mw = mask_words(len(ext))
+    mcs = np.zeros(mw, dtype=np.uint64)
+    iters = np.zeros(cap_iter, dtype=np.uint32)
+    tr, ni, ver = C.c_uint32(), C.c_uint32(), C.c_int()
+    rc = lib().oracle_ddmin_sts(C.byref(cfg), C.byref(ri), C.c_uint32(looking_for), C.c_uint32(flags),
+                                C.c_int(1 if check_unmodified else 0), C.c_void_p(mcs.ctypes.data), C.c_uint32(mw),
+                                C.byref(tr), C.c_void_p(iters.ctypes.data), C.c_uint32(cap_iter), C.byref(ni),
+                                C.byref(ver))
+    return rc, mcs, tr.value, iters[:ni.value].copy(), ver.value
+
+
+def ddmin_superset(ext, K, cap=65536):
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    mw = mask_words(len(ext))
+    K = np.ascontiguousarray(K, dtype=np.uint64)
+    mcs = np.zeros(mw, dtype=np.uint64)
+    iters = np.zeros(cap, dtype=np.uint32)
+    log = np.zeros((cap, mw), dtype=np.uint64)
+    tr, ni, nl = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib().oracle_ddmin_superset(C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.c_void_p(K.ctypes.data),
+                                     C.c_uint32(mw), C.c_void_p(mcs.ctypes.data), C.byref(tr),
+                                     C.c_void_p(iters.ctypes.data), C.c_uint32(cap), C.byref(ni),
+                                     C.c_void_p(log.ctypes.data), C.c_uint32(cap), C.byref(nl))
+    return rc, mcs, tr.value, iters[:ni.value].copy(), log[:nl.value].copy()
+
+
+def split_first_len(n, ways, which):
+    lib().oracle_split_first_len.restype = C.c_uint32
+    return lib().oracle_split_first_len(C.c_uint32(n), C.c_uint32(ways), C.c_uint32(which))

@@ -218,10 +218,10 @@ static uint32_t raft_invariant(const uint32_t* st, uint32_t flags) {
 /* BASELINE.json configs[4]: 32-actor broadcast storm.  Flood(ttl) => count++,
  * remember the largest ttl seen, re-broadcast Flood(ttl-1) to all 31 peers
  * while ttl > 0.   state: w0 = count, w1 = max ttl seen + 1. */
-enum { BC_FLOOD = 1 };
+enum { BC_FLOOD = 1, BC_INJECT = 2 };   /* INJECT: the external seed message, handled like FLOOD */
 static void bc_init(uint32_t* st, uint32_t flags) { (void)st; (void)flags; }
 static void bc_receive(om_machine* m, int self, uint32_t* st, const demi_msg* msg) {
-  if (msg->type != BC_FLOOD) return;
+  if (msg->type != BC_FLOOD && msg->type != BC_INJECT) return;
   st[0]++;
   if (msg->p0 + 1 > st[1]) st[1] = msg->p0 + 1;
   if (msg->p0 > 0)
