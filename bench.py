@@ -84,6 +84,28 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_cores():
+    """Host threads the CPU arm may really use: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -103,7 +125,7 @@ def run_reference(args):
     build.build_oracle()
     from oracle import binding as O
     ext = events.pack_externals(events.raft5_program())
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     n = 125_000 * cores        # ~1 s of work per step at ~1.2e5 prefixes/s/core
     for w in range(args.warmup):
         O.fuzz_batch(MODEL_RAFT5, ext, 1 + w * n, n, MAX_MESSAGES, INTERVAL, model_flags=MODEL_FLAGS, threads=cores)
@@ -168,8 +190,10 @@ def main():
     results_dev = torch.empty(n * RESULT_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
+    from demi_b200 import sharding
+
     def seed_of(step):      # disjoint seed ranges per (step, rank)
-        return 1 + (step * world + rank) * n
+        return sharding.seed_range(step, rank, world, n)
 
     def barrier():
         if world > 1:
@@ -251,7 +275,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import binding as O
             build.build_oracle()
-            cores = os.cpu_count() or 1
+            cores = host_cores()
             ncpu = 125_000 * cores
             O.fuzz_batch(MODEL_RAFT5, ext, 1, 50_000, MAX_MESSAGES, INTERVAL, model_flags=MODEL_FLAGS, threads=cores)
             t0 = time.perf_counter()
