@@ -1,0 +1,88 @@
+package akka.dispatch.verification
+
+import java.nio.{ByteBuffer, ByteOrder}
+
+/** The native half of the drop-in: one `@native` method per entry point of
+  * include/demi_b200.h (bound by jni/DemiNative.c).  Not compiled in this
+  * repository's image (no scalac); this is the binding a DEMi maintainer adds
+  * next to `src/main/scala/verification/schedulers/`. */
+object DemiNative {
+  System.loadLibrary("demijni")
+  @native def create(cfg: ByteBuffer): Long
+  @native def destroy(h: Long): Unit
+  @native def lastError(h: Long): String
+  @native def setExternals(h: Long, events: ByteBuffer, n: Int): Int
+  @native def fuzzBatch(h: Long, params: ByteBuffer, out: ByteBuffer): Int
+  @native def fuzzTrace(h: Long, params: ByteBuffer, seed: Long, events: ByteBuffer, capEvents: Int,
+                        depParent: ByteBuffer, capNodes: Int, counts: ByteBuffer, result: ByteBuffer): Int
+  @native def setTrace(h: Long, events: ByteBuffer, nEvents: Int, externals: ByteBuffer, nExternals: Int): Int
+  @native def replayBatch(h: Long, masks: ByteBuffer, nMasks: Int, maskWords: Int, lookingFor: Int, flags: Int,
+                          out: ByteBuffer): Int
+  @native def ddmin(h: Long, lookingFor: Int, flags: Int, checkUnmodified: Int, mcsMask: ByteBuffer, maskWords: Int,
+                    iterationSizes: ByteBuffer, capIterations: Int, out: ByteBuffer): Int
+  @native def stats(h: Long, out: ByteBuffer): Int
+
+  def direct(n: Int): ByteBuffer = ByteBuffer.allocateDirect(n).order(ByteOrder.LITTLE_ENDIAN)
+}
+
+/** Flat encoding of the model-level vocabulary: an application registers, once,
+  * how its actors and messages map to (actor index, type, p0, p1). */
+trait ModelCodec {
+  def model: Int                                   // DEMI_MODEL_*
+  def modelFlags: Int
+  def actorIndex(name: String): Int
+  def encode(msg: Any): (Int, Int, Int)            // (type, p0, p1)  == the MessageFingerprint
+  def violationCode(fp: ViolationFingerprint): Int
+}
+
+/** RandomScheduler whose explore() runs `max_executions` executions as ONE batch
+  * on the GPU model and then confirms the first violating schedule on the real
+  * application with ReplayScheduler (the reference's own validate_replay step,
+  * RunnerUtils.scala:101-128). Signatures are unchanged. */
+class GpuRandomScheduler(schedulerConfig: SchedulerConfig, codec: ModelCodec,
+                         max_executions: Int = 1, invariant_check_interval: Int = 0, seed: Long = 0L)
+    extends RandomScheduler(schedulerConfig, max_executions, invariant_check_interval,
+                            new FullyRandom(seed = seed)) {
+  private val cfg = DemiNative.direct(32)
+  cfg.putInt(0, 0).putInt(4, codec.model).putInt(8, codec.modelFlags)
+  private val h = DemiNative.create(cfg)
+  require(h > 0, "demi_create failed: " + h)
+
+  private def packExternals(trace: Seq[ExternalEvent]): ByteBuffer = {
+    val b = DemiNative.direct(16 * trace.length)
+    for ((e, i) <- trace.zipWithIndex) {
+      val o = 16 * i
+      e match {
+        case s: Start => b.put(o, 1.toByte).put(o + 1, codec.actorIndex(s.name).toByte); b.putInt(o + 12, s._id)
+        case k: Kill => b.put(o, 2.toByte).put(o + 1, codec.actorIndex(k.name).toByte); b.putInt(o + 12, k._id)
+        case s: Send =>
+          val (t, p0, p1) = codec.encode(s.messageCtor())
+          b.put(o, 3.toByte).put(o + 1, codec.actorIndex(s.name).toByte).put(o + 3, t.toByte)
+          b.putInt(o + 4, p0).putInt(o + 8, p1).putInt(o + 12, s._id)
+        case w: WaitQuiescence => b.put(o, 4.toByte); b.putInt(o + 12, w._id)
+        case p: Partition =>
+          b.put(o, 5.toByte).put(o + 1, codec.actorIndex(p.a).toByte).put(o + 2, codec.actorIndex(p.b).toByte)
+          b.putInt(o + 12, p._id)
+        case u: UnPartition =>
+          b.put(o, 6.toByte).put(o + 1, codec.actorIndex(u.a).toByte).put(o + 2, codec.actorIndex(u.b).toByte)
+          b.putInt(o + 12, u._id)
+        case other => throw new IllegalArgumentException("not representable in the data-only model: " + other)
+      }
+    }
+    b
+  }
+
+  /** Seeds of all violating executions among seed .. seed + max_executions - 1. */
+  def exploreBatch(trace: Seq[ExternalEvent], lookingFor: Option[ViolationFingerprint]): Seq[Long] = {
+    if (test_invariant == null) throw new IllegalArgumentException("Must invoke setInvariant before test()")
+    val rc = DemiNative.setExternals(h, packExternals(trace), trace.length)
+    if (rc != 0) throw new IllegalArgumentException(DemiNative.lastError(h))
+    val p = DemiNative.direct(32)
+    p.putLong(0, seed).putLong(8, max_executions.toLong).putInt(16, if (maxMessages == Int.MaxValue) -1 else maxMessages)
+    p.putInt(20, invariant_check_interval).putInt(24, lookingFor.map(codec.violationCode).getOrElse(0))
+    val out = DemiNative.direct(32 * max_executions)
+    val rc2 = DemiNative.fuzzBatch(h, p, out)
+    if (rc2 != 0) throw new IllegalStateException(DemiNative.lastError(h))
+    (0 until max_executions).filter(i => out.getInt(32 * i) != 0).map(i => seed + i)
+  }
+}
