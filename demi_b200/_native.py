@@ -54,6 +54,17 @@ class DDMinOut(C.Structure):
                 ("reserved", C.c_uint32 * 2)]
 
 
+class DporParams(C.Structure):
+    _fields_ = [("max_messages", C.c_int32), ("depth_bound", C.c_int32), ("max_interleavings", C.c_uint32),
+                ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32), ("node_cap", C.c_uint32),
+                ("explored_slots", C.c_uint32), ("heap_cap", C.c_uint32)]
+
+
+DPOR_RESULT_DTYPE = np.dtype([("interleavings", "<u4"), ("violations", "<u4"), ("deliveries", "<u8"), ("races", "<u8"),
+                              ("n_nodes", "<u4"), ("n_explored", "<u4"), ("heap_left", "<u4"), ("exhausted", "<u4"),
+                              ("budget_exhausted", "<u4"), ("status", "<u4")])
+DPOR_VIOL_DTYPE = np.dtype([("schedule_hash", "<u8"), ("interleaving", "<u4"), ("length", "<u2"), ("code", "<u2")])
+assert DPOR_RESULT_DTYPE.itemsize == 48 and DPOR_VIOL_DTYPE.itemsize == 16 and C.sizeof(DporParams) == 32
 assert REPLAY_DTYPE.itemsize == 16
 assert EXT_DTYPE.itemsize == 16 and EVENT_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 32
 
@@ -62,7 +73,7 @@ EXPORTS = [
     "demi_version", "demi_last_error", "demi_device_count", "demi_create", "demi_destroy",
     "demi_set_externals", "demi_fuzz_batch", "demi_fuzz_batch_dev", "demi_fuzz_summary_dev",
     "demi_fuzz_trace", "demi_stats",
-    "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin",
+    "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin", "demi_dpor_batch",
 ]
 
 _lib = None
@@ -107,6 +118,8 @@ def lib():
     L.demi_ddmin.restype = C.c_int32
     L.demi_ddmin.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int32, vp, C.c_uint32, vp, C.c_uint32,
                              C.POINTER(DDMinOut)]
+    L.demi_dpor_batch.restype = C.c_int32
+    L.demi_dpor_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), vp, vp, C.c_uint32, vp, C.c_uint32]
     L.demi_stats.restype = C.c_int32
     L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
     _lib = L

@@ -125,6 +125,25 @@ class Engine(object):
                                        mcs.ctypes.data, mw, iters.ctypes.data, cap_iterations, C.byref(out)))
         return mcs, iters[:min(out.n_iterations, cap_iterations)].copy(), out
 
+    # ---- DPOR
+    def dpor_batch(self, programs, max_messages, max_interleavings, looking_for=0, stop_if_found=False, depth_bound=-1,
+                   node_cap=4096, explored_slots=1 << 16, heap_cap=1 << 15, cap_viol=64, want_hashes=False):
+        """`programs`: list of external-event programs (Start/Send only), one independent search each."""
+        packed = [p if isinstance(p, np.ndarray) else pack_externals(p) for p in programs]
+        offs = np.zeros(len(packed) + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(p) for p in packed])
+        ext = np.ascontiguousarray(np.concatenate(packed), dtype=N.EXT_DTYPE)
+        P = N.DporParams(max_messages, depth_bound, max_interleavings, looking_for or 0, 1 if stop_if_found else 0,
+                         node_cap, explored_slots, heap_cap)
+        res = np.zeros(len(packed), dtype=N.DPOR_RESULT_DTYPE)
+        viol = np.zeros((len(packed), cap_viol), dtype=N.DPOR_VIOL_DTYPE)
+        cap_h = max_interleavings + 1 if want_hashes else 0
+        hashes = np.zeros((len(packed), max(cap_h, 1)), dtype=np.uint64)
+        self._check(N.lib().demi_dpor_batch(self._h, ext.ctypes.data, offs.ctypes.data, len(packed), C.byref(P),
+                                            res.ctypes.data, viol.ctypes.data, cap_viol,
+                                            hashes.ctypes.data if want_hashes else None, cap_h))
+        return res, viol, hashes
+
     def stats(self):
         s = N.Perf()
         self._check(N.lib().demi_stats(self._h, C.byref(s)))
@@ -292,3 +311,43 @@ class DDMin(object):
 
     def verify_mcs(self, mcs, violation_fingerprint):
         return self.oracle.test(mcs, violation_fingerprint)
+
+
+class DPORwHeuristics(object):
+    """DPORwHeuristics(schedulerConfig, backtrackHeuristic = DefaultBacktrackOrdering, depth_bound,
+    stopIfViolationFound, trackHistory = true) — schedulers/DPORwHeuristics.scala:77-88.
+    test() explores interleavings of the external events in the reference's order until a matching
+    violation is found or the backtrack set / budget is exhausted."""
+
+    def __init__(self, schedulerConfig, depth_bound=None, stopIfViolationFound=True, max_interleavings=1000,
+                 engine=None):
+        self.schedulerConfig = schedulerConfig
+        self.depth_bound = -1 if depth_bound is None else depth_bound
+        self.stopIfViolationFound = stopIfViolationFound
+        self.max_interleavings = max_interleavings
+        self.max_messages = None
+        self.engine = engine or Engine(schedulerConfig)
+        self.last = None
+
+    def getName(self):
+        return "DPORwHeuristics"
+
+    def setMaxMessagesToSchedule(self, n):
+        self.max_messages = n
+
+    def setDepthBound(self, d):
+        self.depth_bound = d
+
+    def test(self, events, violation_fingerprint, stats=None):
+        """Some(record of the first violating interleaving) or None (DPORwHeuristics.scala:1193-1242)."""
+        if self.max_messages is None:
+            raise ValueError("setMaxMessagesToSchedule is required (models with repeating timers never quiesce)")
+        prog = [e for e in events if e.kind in (N.EXT_START, N.EXT_SEND)]   # convertToDPORTrace (:1279-1303)
+        res, viol, _ = self.engine.dpor_batch([prog], self.max_messages, self.max_interleavings,
+                                              violation_fingerprint, self.stopIfViolationFound, self.depth_bound)
+        self.last = res[0]
+        if stats is not None:
+            stats.increment_replays(int(res[0]["interleavings"]))
+        if res[0]["status"]:
+            raise DemiError(N.ERR_CAPACITY, "DPOR search status %d" % res[0]["status"])
+        return viol[0][0] if res[0]["violations"] else None

@@ -239,6 +239,53 @@ int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t flags, int32_t
                    uint64_t* mcs_mask, uint32_t mask_words,
                    uint32_t* iteration_sizes, uint32_t cap_iterations, demi_ddmin_out* out);
 
+/* --------------------------------------------------------------------- DPOR */
+/* DPORwHeuristics(schedulerConfig, backtrackHeuristic = DefaultBacktrackOrdering,
+ * depth_bound, stopIfViolationFound, trackHistory = true) driven like
+ * RunnerUtils.boundedDPOR (RunnerUtils.scala:881-978; DPORwHeuristics.scala:77-88,
+ * :1193-1242).  Externals must be Start / Send only (DPORwHeuristics.scala:684-721).
+ * One *search* explores interleavings strictly in the reference's order; a batch
+ * runs independent searches (one per external program) concurrently. */
+typedef struct demi_dpor_params {
+  int32_t  max_messages;        /* setMaxMessagesToSchedule (:121-126); <0 = unbounded (needs quiescing models) */
+  int32_t  depth_bound;         /* setDepthBound (:116-119); <0 = none                       */
+  uint32_t max_interleavings;   /* exploration budget per search                             */
+  uint32_t looking_for;         /* ViolationFingerprint code, 0 = any                        */
+  uint32_t stop_if_found;       /* stopIfViolationFound (:82)                                */
+  uint32_t node_cap;            /* capacities of the per-search structures                   */
+  uint32_t explored_slots;      /* power of two                                              */
+  uint32_t heap_cap;
+} demi_dpor_params;
+typedef struct demi_dpor_result {
+  uint32_t interleavings;       /* executions performed (interleavingCounter)                */
+  uint32_t violations;          /* executions that ended in a matching violation             */
+  uint64_t deliveries;
+  uint64_t races;               /* co-enabled pairs analysed (analyze_dep calls)             */
+  uint32_t n_nodes, n_explored, heap_left;
+  uint32_t exhausted;           /* backtrack set ran empty ("Tutto finito!", :1148)          */
+  uint32_t budget_exhausted;
+  uint32_t status;              /* 0 ok, DEMI_DS_*                                           */
+} demi_dpor_result;
+typedef struct demi_dpor_violation {
+  uint64_t schedule_hash;       /* id-independent hash of the delivered (snd,rcv,msg) sequence */
+  uint32_t interleaving;        /* index of the execution within its search                  */
+  uint16_t length;              /* deliveries                                                */
+  uint16_t code;
+} demi_dpor_violation;
+#define DEMI_DS_NODE_OVF 1
+#define DEMI_DS_QUEUE_OVF 2
+#define DEMI_DS_EXPLORED_OVF 3
+#define DEMI_DS_HEAP_OVF 4
+#define DEMI_DS_TRACE_OVF 5
+#define DEMI_DS_UNSUPPORTED 6
+/* `n_searches` independent searches.  Search s uses externals
+ * [ext_offsets[s], ext_offsets[s+1]) of `ext`.  Per search: one result record,
+ * up to cap_viol violation records (viol + s*cap_viol), and optionally the
+ * schedule hash of every executed interleaving (hashes + s*cap_hashes). */
+int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_offsets, uint32_t n_searches,
+                        const demi_dpor_params* params, demi_dpor_result* results,
+                        demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint32_t cap_hashes);
+
 /* ------------------------------------------------------------- statistics */
 int32_t demi_stats(const demi_handle* h, demi_perf* out);
 

@@ -186,3 +186,32 @@ def ddmin_superset(ext, K, cap=65536):
 def split_first_len(n, ways, which):
     lib().oracle_split_first_len.restype = C.c_uint32
     return lib().oracle_split_first_len(C.c_uint32(n), C.c_uint32(ways), C.c_uint32(which))
+
+
+# ----------------------------------------------------------------------- DPOR
+class DporParams(C.Structure):
+    _fields_ = [("max_messages", C.c_int32), ("depth_bound", C.c_int32), ("max_interleavings", C.c_uint32),
+                ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32), ("node_cap", C.c_uint32),
+                ("explored_slots", C.c_uint32), ("heap_cap", C.c_uint32)]
+
+
+DPOR_RESULT_DTYPE = np.dtype([("interleavings", "<u4"), ("violations", "<u4"), ("deliveries", "<u8"), ("races", "<u8"),
+                              ("n_nodes", "<u4"), ("n_explored", "<u4"), ("heap_left", "<u4"), ("exhausted", "<u4"),
+                              ("budget_exhausted", "<u4"), ("status", "<u4")])
+DPOR_VIOL_DTYPE = np.dtype([("schedule_hash", "<u8"), ("interleaving", "<u4"), ("length", "<u2"), ("code", "<u2")])
+
+
+def dpor_search(model, ext, max_messages, max_interleavings, looking_for=0, stop_if_found=0, depth_bound=-1,
+                model_flags=0, node_cap=1 << 16, explored_slots=1 << 20, heap_cap=1 << 18, cap_viol=4096):
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    cfg = Config(0, model, model_flags, 0, 0)
+    P = DporParams(max_messages, depth_bound, max_interleavings, looking_for, stop_if_found, node_cap,
+                   explored_slots, heap_cap)
+    res = np.zeros(1, dtype=DPOR_RESULT_DTYPE)
+    viol = np.zeros(cap_viol, dtype=DPOR_VIOL_DTYPE)
+    hashes = np.zeros(max_interleavings + 1, dtype=np.uint64)
+    rc = lib().oracle_dpor_search(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.byref(P),
+                                  C.c_void_p(res.ctypes.data), C.c_void_p(viol.ctypes.data), C.c_uint32(cap_viol),
+                                  C.c_void_p(hashes.ctypes.data), C.c_uint32(len(hashes)))
+    r = res[0]
+    return rc, r, viol[:min(int(r["violations"]), cap_viol)].copy(), hashes[:int(r["interleavings"])].copy()

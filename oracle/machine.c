@@ -11,6 +11,7 @@
 #include <limits.h>
 #include "machine.h"
 #include "sts.h"
+#include "dpor.h"
 
 /* ------------------------------------------------------------------ helpers */
 static int key_eq(const om_timer_key* k, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
@@ -184,6 +185,7 @@ static void send_external_messages(om_machine* m) {
 /* `!` inside receive(): Instrumenter.tell -> aroundDispatch -> event_produced,
  * synchronously and in program order (Instrumenter.scala:1098-1108). */
 void om_send(om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_dpor_mode()) { dpor_om_send(m, src, dst, type, p0, p1); return; }
   if (oracle_in_sts_mode()) { sts_om_send(m, src, dst, type, p0, p1); return; }
   demi_msg msg; msg.src = (uint8_t)src; msg.dst = (uint8_t)dst; msg.type = type; msg.flags = 0;
   msg.p0 = p0; msg.p1 = p1;
@@ -193,6 +195,7 @@ void om_send(om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_
  * (ongoing=false) -> handleTick -> enqueue_timer -> removeCancellable
  * (Instrumenter.scala:1145-1200). */
 void om_schedule_once(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_dpor_mode()) { dpor_om_schedule(m, self, type, p0, p1, 0); return; }
   if (oracle_in_sts_mode()) { sts_om_schedule(m, self, type, p0, p1, 0); return; }
   if (m->status) return;
   if (set_find(m->registry, m->n_registry, self, type, p0, p1) >= 0) return; /* "Non-unique timer" :1154-1157 */
@@ -200,6 +203,7 @@ void om_schedule_once(om_machine* m, int self, uint8_t type, uint32_t p0, uint32
 }
 /* scheduler.schedule (repeating): WeaveActor.aj:264-279, ongoing=true. */
 void om_schedule_repeating(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_dpor_mode()) { dpor_om_schedule(m, self, type, p0, p1, 1); return; }
   if (oracle_in_sts_mode()) { sts_om_schedule(m, self, type, p0, p1, 1); return; }
   if (m->status) return;
   if (set_find(m->registry, m->n_registry, self, type, p0, p1) >= 0) return;
@@ -212,6 +216,7 @@ void om_schedule_repeating(om_machine* m, int self, uint8_t type, uint32_t p0, u
  * matching ("deadLetters", rcv, msg) in pendingEvents.arr order
  * (FullyRandom.remove, RandomScheduler.scala:653-664). */
 void om_cancel_timer(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_dpor_mode()) { dpor_om_cancel(m, self, type, p0, p1); return; }
   if (oracle_in_sts_mode()) { sts_om_cancel(m, self, type, p0, p1); return; }
   if (m->status) return;
   if (set_find(m->cancelled, m->n_cancelled, self, type, p0, p1) < 0)
