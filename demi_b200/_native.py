@@ -26,7 +26,7 @@ class Config(C.Structure):
 
 class FuzzParams(C.Structure):
     _fields_ = [("seed_base", C.c_int64), ("n_prefixes", C.c_uint64), ("max_messages", C.c_int32),
-                ("invariant_check_interval", C.c_int32), ("looking_for", C.c_uint32), ("reserved", C.c_uint32)]
+                ("invariant_check_interval", C.c_int32), ("looking_for", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class Perf(C.Structure):
@@ -74,6 +74,7 @@ EXPORTS = [
     "demi_set_externals", "demi_fuzz_batch", "demi_fuzz_batch_dev", "demi_fuzz_summary_dev",
     "demi_fuzz_trace", "demi_stats",
     "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin", "demi_dpor_batch",
+    "demi_dedup_compact_dev", "demi_dedup_compact",
 ]
 
 _lib = None
@@ -118,6 +119,10 @@ def lib():
     L.demi_ddmin.restype = C.c_int32
     L.demi_ddmin.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int32, vp, C.c_uint32, vp, C.c_uint32,
                              C.POINTER(DDMinOut)]
+    L.demi_dedup_compact_dev.restype = C.c_int32
+    L.demi_dedup_compact_dev.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp, vp, vp, vp]
+    L.demi_dedup_compact.restype = C.c_int32
+    L.demi_dedup_compact.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp, vp, C.POINTER(C.c_uint64)]
     L.demi_dpor_batch.restype = C.c_int32
     L.demi_dpor_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), vp, vp, C.c_uint32, vp, C.c_uint32]
     L.demi_stats.restype = C.c_int32

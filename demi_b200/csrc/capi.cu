@@ -112,6 +112,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
   cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count);
   demi_replay_free(h);
+  cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -224,6 +225,7 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   a.looking_for = p->looking_for;
   a.seed_base = p->seed_base;
   a.n_prefixes = p->n_prefixes;
+  a.fuzz_flags = p->flags;
   a.ext = h->ext_dev;
   a.n_ext = (uint32_t)h->ext_host.size();
   a.node_cap = node_cap;

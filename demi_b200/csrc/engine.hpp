@@ -14,7 +14,11 @@
 
 extern thread_local std::string g_create_error;
 
+struct DedupScratch { void* keys = nullptr; size_t keys_b = 0; void* vals = nullptr; size_t vals_b = 0;
+                      void* keep = nullptr; size_t keep_b = 0; void* counts = nullptr; size_t counts_b = 0; };
+
 struct demi_handle {
+  DedupScratch dedup;
   demi_config cfg{};
   std::string err;
   int sm_count = 0;

@@ -384,6 +384,11 @@ struct LaneMachine {
     if (!status) {
       uint64_t sh = 0;
       for (uint32_t i = 0; i < N * SW; i++) sh += demi_state_term(smw[i * BD], i);
+      if (A->fuzz_flags & DEMI_FF_HASH_PENDING)
+        for (uint32_t i = 0; i < n_pending; i++) {
+          uint4 q = pend[i * 32];
+          sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);
+        }
       out.violation = violation; out.steps = (uint32_t)nsched;
       out.state_hash = sh; out.trace_hash = thash;
       out.n_nodes = (uint16_t)n_nodes;

@@ -126,6 +126,7 @@ struct KernelArgs {
   uint32_t looking_for;
   int64_t  seed_base;
   uint64_t n_prefixes;
+  uint32_t fuzz_flags;        // DEMI_FF_*
   // external-event program
   const demi_ext_event* ext;
   uint32_t n_ext;
@@ -623,6 +624,11 @@ struct Machine {
       __syncwarp();
       uint64_t sh = 0;
       for (uint32_t i = lane; i < N * SW; i += 32) sh += demi_state_term(sm->states[i], i);
+      if (A->fuzz_flags & DEMI_FF_HASH_PENDING)
+        for (uint32_t i = lane; i < n_pending; i += 32) {
+          uint4 q = pend_load(i);
+          sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);
+        }
       for (int o = 16; o > 0; o >>= 1) sh += __shfl_xor_sync(FULL_MASK, sh, o);
       out.violation = violation; out.steps = (uint32_t)nsched;
       out.state_hash = sh; out.trace_hash = thash;

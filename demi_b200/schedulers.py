@@ -66,15 +66,15 @@ class Engine(object):
         self._ext = arr
         self._check(N.lib().demi_set_externals(self._h, arr.ctypes.data, len(arr)))
 
-    def fuzz_batch(self, seed_base, n, max_messages, interval, looking_for=0, out=None):
-        p = N.FuzzParams(seed_base, n, max_messages, interval, looking_for or 0, 0)
+    def fuzz_batch(self, seed_base, n, max_messages, interval, looking_for=0, out=None, flags=0):
+        p = N.FuzzParams(seed_base, n, max_messages, interval, looking_for or 0, flags)
         if out is None:
             out = np.empty(n, dtype=N.RESULT_DTYPE)
         self._check(N.lib().demi_fuzz_batch(self._h, C.byref(p), out.ctypes.data))
         return out
 
-    def fuzz_batch_dev(self, seed_base, n, max_messages, interval, out_ptr, stream=0, looking_for=0):
-        p = N.FuzzParams(seed_base, n, max_messages, interval, looking_for or 0, 0)
+    def fuzz_batch_dev(self, seed_base, n, max_messages, interval, out_ptr, stream=0, looking_for=0, flags=0):
+        p = N.FuzzParams(seed_base, n, max_messages, interval, looking_for or 0, flags)
         self._check(N.lib().demi_fuzz_batch_dev(self._h, C.byref(p), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
     def fuzz_summary_dev(self, stream=0):
@@ -124,6 +124,21 @@ class Engine(object):
         self._check(N.lib().demi_ddmin(self._h, looking_for or 0, flags, 1 if check_unmodified else 0,
                                        mcs.ctypes.data, mw, iters.ctypes.data, cap_iterations, C.byref(out)))
         return mcs, iters[:min(out.n_iterations, cap_iterations)].copy(), out
+
+    # ---- state-hash dedup + compaction (K5 / K4)
+    def dedup_compact(self, results, mode=0):
+        results = np.ascontiguousarray(results, dtype=N.RESULT_DTYPE)
+        out = np.empty(len(results), dtype=N.RESULT_DTYPE)
+        idx = np.empty(len(results), dtype=np.uint32)
+        cnt = C.c_uint64()
+        self._check(N.lib().demi_dedup_compact(self._h, results.ctypes.data, len(results), mode, out.ctypes.data,
+                                               idx.ctypes.data, C.byref(cnt)))
+        return out[:cnt.value].copy(), idx[:cnt.value].copy()
+
+    def dedup_compact_dev(self, results_ptr, n, mode, out_ptr, out_index_ptr, out_count_ptr, stream=0):
+        self._check(N.lib().demi_dedup_compact_dev(self._h, C.c_void_p(results_ptr), n, mode, C.c_void_p(out_ptr),
+                                                   C.c_void_p(out_index_ptr), C.c_void_p(out_count_ptr),
+                                                   C.c_void_p(stream)))
 
     # ---- DPOR
     def dpor_batch(self, programs, max_messages, max_interleavings, looking_for=0, stop_if_found=False, depth_bound=-1,

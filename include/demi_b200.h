@@ -141,8 +141,9 @@ typedef struct demi_fuzz_params {
   int32_t  max_messages;       /* RandomScheduler.setMaxMessages (RandomScheduler.scala:54-57) */
   int32_t  invariant_check_interval; /* RandomScheduler ctor arg (RandomScheduler.scala:43) */
   uint32_t looking_for;        /* 0 = any violation (explore(_, None)); else only this code */
-  uint32_t reserved;
+  uint32_t flags;              /* DEMI_FF_* */
 } demi_fuzz_params;
+#define DEMI_FF_HASH_PENDING 0x1u  /* state_hash also covers the (canonical, order-free) pending multiset */
 
 typedef struct demi_perf {
   uint64_t prefixes;           /* units processed by the last batch call       */
@@ -285,6 +286,23 @@ typedef struct demi_dpor_violation {
 int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_offsets, uint32_t n_searches,
                         const demi_dpor_params* params, demi_dpor_result* results,
                         demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint32_t cap_hashes);
+
+/* ------------------------------------------- state-hash dedup + compaction */
+/* Frontier bookkeeping the north-star adds on top of the reference (the
+ * reference has no dedup; RunnerUtils.fuzz simply discards executions):
+ * K5 inserts every record's 64-bit state_hash into an open-addressing table
+ * and keeps, per distinct hash, the record with the smallest prefix index;
+ * K4 writes the kept records (mode DEMI_DM_UNIQUE) or the violating ones
+ * (DEMI_DM_VIOLATING) densely, in prefix-index order.  All buffers are device
+ * pointers; `*_count_dev` is one uint64.  No sync. */
+#define DEMI_DM_UNIQUE    0
+#define DEMI_DM_VIOLATING 1
+int32_t demi_dedup_compact_dev(demi_handle* h, const void* results_dev, uint64_t n, int32_t mode,
+                               void* out_records_dev, void* out_index_dev /* uint32[n], may be NULL */,
+                               void* out_count_dev, void* stream);
+/* Host convenience wrapper: records in host memory in, kept records out. */
+int32_t demi_dedup_compact(demi_handle* h, const demi_fuzz_result* results, uint64_t n, int32_t mode,
+                           demi_fuzz_result* out_records, uint32_t* out_index, uint64_t* out_count);
 
 /* ------------------------------------------------------------- statistics */
 int32_t demi_stats(const demi_handle* h, demi_perf* out);

@@ -91,4 +91,9 @@ DEMI_HD uint64_t demi_state_term(uint32_t word, uint32_t i) {
   return demi_hash6(word, i, 0x5D, 0, 0, 0);
 }
 
+/* One pending message (sender, receiver, type | payload); summed, so order-free. */
+DEMI_HD uint64_t demi_pending_term(uint32_t hdr_noflags, uint32_t p0, uint32_t p1) {
+  return demi_hash6(hdr_noflags, p0, p1, 0x50454E44u, 0, 0);
+}
+
 #endif /* DEMI_LIMITS_H */

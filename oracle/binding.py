@@ -27,7 +27,7 @@ class Config(C.Structure):
 
 class FuzzParams(C.Structure):
     _fields_ = [("seed_base", C.c_int64), ("n_prefixes", C.c_uint64), ("max_messages", C.c_int32),
-                ("invariant_check_interval", C.c_int32), ("looking_for", C.c_uint32), ("reserved", C.c_uint32)]
+                ("invariant_check_interval", C.c_int32), ("looking_for", C.c_uint32), ("flags", C.c_uint32)]
 
 
 _lib = None
@@ -43,10 +43,10 @@ def lib():
 
 
 def fuzz_batch(model, ext, seed_base, n, max_messages, interval, model_flags=0, blocked_mask=0,
-               ignore_timers=0, looking_for=0, threads=None):
+               ignore_timers=0, looking_for=0, threads=None, flags=0):
     ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
     cfg = Config(0, model, model_flags, blocked_mask, ignore_timers)
-    p = FuzzParams(seed_base, n, max_messages, interval, looking_for, 0)
+    p = FuzzParams(seed_base, n, max_messages, interval, looking_for, flags)
     out = np.empty(n, dtype=RESULT_DTYPE)
     threads = threads or (os.cpu_count() or 1)
     rc = lib().oracle_fuzz_batch(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.byref(p),

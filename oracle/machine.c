@@ -419,6 +419,11 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
     uint64_t sh = 0;
     uint32_t nw = (uint32_t)(model->n_actors * model->state_words);
     for (uint32_t i = 0; i < nw; i++) sh += demi_state_term(m->states[i], i);
+    if (p->flags & DEMI_FF_HASH_PENDING)          /* order-free: a multiset hash of what is still in flight */
+      for (uint32_t i = 0; i < m->n_pending; i++) {
+        const demi_msg* q = &m->pending[i].msg;
+        sh += demi_pending_term((uint32_t)q->src | ((uint32_t)q->dst << 8) | ((uint32_t)q->type << 16), q->p0, q->p1);
+      }
     out->state_hash = sh;
     out->trace_hash = m->trace_hash;
     out->n_nodes = (uint16_t)m->n_nodes;
