@@ -157,10 +157,12 @@ struct LaneMachine {
   // Instrumenter.aroundDispatch's cancelled-timer drop (Instrumenter.scala:1090-1096).
   // DepTracker.getMessage (DepTracker.scala:82-109): in the regime this engine
   // accepts no child is ever reused, so the Unique id is simply the next one.
-  __device__ __forceinline__ void event_produced(uint32_t hdr, uint32_t p0, uint32_t p1) {
+  // `slot_hint`: the timer slot when the caller already knows it (flush), -2 = unknown
+  __device__ __forceinline__ void event_produced(uint32_t hdr, uint32_t p0, uint32_t p1, int slot_hint) {
     if (status) return;
     uint32_t src = hdr_src(hdr), dst = hdr_dst(hdr), type = hdr_type(hdr), flags = hdr_flags(hdr);
-    int slot = MODEL::timer_slot(dst, type, p0, p1);
+    int slot = slot_hint;
+    if (slot == -2 && (cancelled || (flags & DEMI_MF_EXTERNAL))) slot = MODEL::timer_slot(dst, type, p0, p1);
     if (cancelled && slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
     if (n_nodes >= A->node_cap) { defer(); return; }
     uint32_t uniq = ++n_uniq;
@@ -203,20 +205,50 @@ struct LaneMachine {
     }
     handle_timer(slot);
   }
-  // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365)
-  __device__ __forceinline__ void send_external_messages() {
-    for (uint32_t i = 0; i < tosend.n && !status; i++) {
-      uint32_t b = tosend.get(i);
-      if (b & 0x80u) {
-        uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
-        event_produced(raw.x, raw.y, raw.z);
+  // One loop, one event_produced call site (code size): first the ops receive() left
+  // in the outbox (`n_ops`, sender `self`), in program order; then, if `do_flush`,
+  // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365).
+  __device__ __forceinline__ void drain(uint32_t n_ops, uint32_t self, bool do_flush) {
+    uint32_t* ob = smw + N * SW * BD;
+    uint32_t i = 0;
+    bool flushing = false;
+    for (;;) {
+      if (status) return;
+      if (!flushing && i >= n_ops) { if (!do_flush) return; flushing = true; i = 0; }
+      if (flushing && i >= tosend.n) { tosend.clear(); return; }
+      uint32_t hdr, p0, p1; int slot = -2;
+      if (!flushing) {
+        uint32_t w0 = ob[(i * 3) * BD]; p0 = ob[(i * 3 + 1) * BD]; p1 = ob[(i * 3 + 2) * BD];
+        uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+        i++;
+        if (kind != OP_SEND) {
+          if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
+          int s2 = MODEL::timer_slot(odst, otype, p0, p1);
+          if (s2 < 0) { defer(); return; }
+          if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
+          if (kind == OP_SCHED_REPEAT) {
+            if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); return; }
+            registry |= 1u << s2;
+          }
+          enqueue_timer((uint32_t)s2);
+          continue;
+        }
+        hdr = make_hdr(self, odst, otype, 0);
       } else {
-        uint32_t dst, type, p0, p1;
-        MODEL::slot_msg(b, dst, type, p0, p1);
-        event_produced(make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER), p0, p1);
+        uint32_t b = tosend.get(i);
+        i++;
+        if (b & 0x80u) {
+          uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
+          hdr = raw.x; p0 = raw.y; p1 = raw.z;
+        } else {
+          uint32_t dst, type;
+          MODEL::slot_msg(b, dst, type, p0, p1);
+          hdr = make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER);
+          slot = (int)b;
+        }
       }
+      event_produced(hdr, p0, p1, slot);
     }
-    tosend.clear();
   }
 
   // Cancellable.cancel(): Instrumenter.cancelTimer (Instrumenter.scala:159-168) ->
@@ -249,13 +281,14 @@ struct LaneMachine {
     while (loop && ext_idx < A->n_ext && !status) {
       uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext) + ext_idx);
       uint32_t kind = raw.x & 0xFF, a = (raw.x >> 8) & 0xFF, b = (raw.x >> 16) & 0xFF;
+      uint32_t ek = 0, es = DEMI_DEADLETTERS, ed = a;          // the EventTrace element this external leaves
       switch (kind) {
         case DEMI_EXT_START:
-          record_event(DEMI_EV_SPAWN, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
+          ek = DEMI_EV_SPAWN;
           inaccessible &= ~(1u << a); killed &= ~(1u << a);
           break;
         case DEMI_EXT_KILL:
-          record_event(DEMI_EV_KILL, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
+          ek = DEMI_EV_KILL;
           killed |= 1u << a; inaccessible |= 1u << a;
           break;
         case DEMI_EXT_SEND:
@@ -264,32 +297,38 @@ struct LaneMachine {
           ext_send_idx++;
           break;
         case DEMI_EXT_PARTITION:
-          record_event(DEMI_EV_PARTITION, a, b, 0, 0, 0, 0, 0, 0);
+          ek = DEMI_EV_PARTITION; es = a; ed = b;
           part_row(a) |= 1u << b;
           break;
         case DEMI_EXT_UNPARTITION:
-          record_event(DEMI_EV_UNPARTITION, a, b, 0, 0, 0, 0, 0, 0);
+          ek = DEMI_EV_UNPARTITION; es = a; ed = b;
           part_row(a) &= ~(1u << b);
           break;
         case DEMI_EXT_WAIT_QUIESCENCE:
-          record_event(DEMI_EV_BEGIN_WAIT_QUIESCENCE, DEMI_DEADLETTERS, DEMI_DEADLETTERS, 0, 0, 0, 0, 0, 0);
+          ek = DEMI_EV_BEGIN_WAIT_QUIESCENCE; ed = DEMI_DEADLETTERS;
           loop = false;
           break;
         default: break;
       }
+      if (ek) record_event(ek, es, ed, 0, 0, 0, 0, 0, 0);
       ext_idx++;
     }
   }
 
   // RandomScheduler.schedule_new_message (RandomScheduler.scala:352-485); blockedActors is empty here
-  __device__ __forceinline__ bool schedule_new_message(uint4& pick) {
+  // the stop conditions at the top of schedule_new_message (:354-401); they read
+  // only counters and actor states, so they are evaluated before the previous
+  // delivery's outbox is drained (drain() then flushes only if we go on)
+  __device__ __forceinline__ bool may_continue() {
     if (status | violation) return false;
     if (nsched > A->max_messages) { ext_idx = A->n_ext; return false; }
     if (A->interval > 0 && nmod == 0 && nsched != 0) {
       violation = check_invariant();
       if (violation) return false;
     }
-    send_external_messages();
+    return true;
+  }
+  __device__ __forceinline__ bool pick_next(uint4& pick) {
     if (status) return false;
     if (n_pending == 0) return false;
     pick = pending_remove_at(rng.next_int(n_pending));          // Util.scala:171-176
@@ -313,44 +352,31 @@ struct LaneMachine {
   }
 
   // Instrumenter.dispatch_new_message (Instrumenter.scala:913-1017)
-  __device__ __forceinline__ void dispatch_new_message(const uint4& pick) {
+  // returns the number of outbox ops receive() produced (applied by drain())
+  __device__ __forceinline__ uint32_t dispatch_new_message(const uint4& pick) {
     uint32_t src = hdr_src(pick.x), dst = hdr_dst(pick.x), type = hdr_type(pick.x);
     int slot = MODEL::timer_slot(dst, type, pick.y, pick.z);
     if (slot >= 0 && ((registry >> slot) & 1u)) enqueue_timer((uint32_t)slot);     // re-arm :1008-1016
-    if (status) return;
+    if (status) return 0;
     LaneOutbox<OB> ob;
     ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
     MODEL::receive(ob, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
-    if (ob.overflow) { defer(); return; }
+    if (ob.overflow) { defer(); return 0; }
     // equal sends out of one receive() would share a Unique (child reuse): defer
-    for (uint32_t i = 1; i < ob.n; i++)
+    for (uint32_t i = 1; i < ob.n; i++) {
+      const uint32_t wi = ob.base[(i * 3) * BD];
       for (uint32_t j = 0; j < i; j++)
-        if (ob.base[(i * 3) * BD] == ob.base[(j * 3) * BD] && ob.base[(i * 3 + 1) * BD] == ob.base[(j * 3 + 1) * BD] &&
-            ob.base[(i * 3 + 2) * BD] == ob.base[(j * 3 + 2) * BD] && (ob.base[(i * 3) * BD] & 0xFF) == OP_SEND) {
-          defer(); return;
+        if (wi == ob.base[(j * 3) * BD] && (wi & 0xFF) == OP_SEND &&
+            ob.base[(i * 3 + 1) * BD] == ob.base[(j * 3 + 1) * BD] && ob.base[(i * 3 + 2) * BD] == ob.base[(j * 3 + 2) * BD]) {
+          defer(); return 0;
         }
-    for (uint32_t i = 0; i < ob.n && !status; i++) {
-      uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
-      uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-      if (kind == OP_SEND) {
-        event_produced(make_hdr(dst, odst, otype, 0), q0, q1);
-      } else if (kind == OP_CANCEL) {
-        cancel_timer(odst, otype, q0, q1);
-      } else {
-        int s2 = MODEL::timer_slot(odst, otype, q0, q1);
-        if (s2 < 0) { defer(); break; }
-        if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
-        if (kind == OP_SCHED_REPEAT) {
-          if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); break; }
-          registry |= 1u << s2;
-        }
-        enqueue_timer((uint32_t)s2);
-      }
     }
+    return ob.n;
   }
 
   __device__ __forceinline__ void reset(int64_t seed) {
     rng.seed(seed);
+#pragma unroll 1
     for (uint32_t i = 0; i < N * SW; i++) smw[i * BD] = MODEL::init_word(i, A->model_flags);
     for (uint32_t a = 0; a < N; a++) part_row(a) = 0;
     n_pending = max_pending = 0;
@@ -365,11 +391,17 @@ struct LaneMachine {
 
   __device__ __forceinline__ void run(int64_t seed, demi_fuzz_result& out) {
     reset(seed);
+    uint32_t n_ops = 0, self = 0;          // outbox of the delivery that has not been drained yet
     for (;;) {
       inject_until_quiescence();
-      uint4 pick;
-      while (schedule_new_message(pick)) {
-        dispatch_new_message(pick);
+      for (;;) {
+        const bool go = may_continue();
+        drain(n_ops, self, go);            // previous receive()'s sends, then (if going on) the flush
+        n_ops = 0;
+        uint4 pick;
+        if (!go || !pick_next(pick)) break;
+        self = hdr_dst(pick.x);
+        n_ops = dispatch_new_message(pick);
         if (status) break;
       }
       if (status | violation) break;
@@ -383,8 +415,10 @@ struct LaneMachine {
     out.status = (uint16_t)status;
     if (!status) {
       uint64_t sh = 0;
+#pragma unroll 1
       for (uint32_t i = 0; i < N * SW; i++) sh += demi_state_term(smw[i * BD], i);
       if (A->fuzz_flags & DEMI_FF_HASH_PENDING)
+#pragma unroll 1
         for (uint32_t i = 0; i < n_pending; i++) {
           uint4 q = pend[i * 32];
           sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);

@@ -139,6 +139,7 @@ struct Raft5 {
         s[ROLE] = CANDIDATE;
         s[VOTED] = (uint8_t)self;
         s[VOTES] = (uint8_t)(1u << self);
+#pragma unroll 1
         for (uint32_t j = 0; j < 5; j++)
           if (j != self) out.send(j, REQUEST_VOTE, (uint32_t)s[TERM] | (last_idx << 8) | (last_term << 16), 0);
         break;
@@ -165,6 +166,7 @@ struct Raft5 {
               s[LOGVAL + s[LOGLEN]] = (uint8_t)(0x80u | self);
               s[LOGLEN]++;
             }
+#pragma unroll 1
             for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
             out.schedule_repeating(HEARTBEAT_TICK, 0, 0);
           }
@@ -172,8 +174,10 @@ struct Raft5 {
         break;
       }
       case HEARTBEAT_TICK:
-        if (s[ROLE] == LEADER)
+        if (s[ROLE] == LEADER) {
+#pragma unroll 1
           for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
+        }
         break;
       case APPEND_ENTRIES: {
         uint32_t prev = (p0 >> 8) & 0xFF, pt = (p0 >> 16) & 0xFF, lc = (p0 >> 24) & 0xFF;
@@ -240,13 +244,16 @@ struct Raft5 {
   template <class A>
   __device__ static __forceinline__ uint32_t invariant(A all, uint32_t) {
     uint32_t code = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < 5; i++)
+#pragma unroll 1
       for (uint32_t j = i + 1; j < 5; j++) {
         auto a = all.actor(i);
         auto b = all.actor(j);
         if (a[ROLE] == LEADER && b[ROLE] == LEADER && a[TERM] == b[TERM]) return 1;
         if (code) continue;
         uint32_t c = a[COMMIT] < b[COMMIT] ? a[COMMIT] : b[COMMIT];
+#pragma unroll 1
         for (uint32_t k = 0; k < c; k++)
           if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) code = 2;
       }

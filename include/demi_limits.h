@@ -60,8 +60,7 @@ static inline uint32_t demi_external_type_mask(int model) {
 
 /* ---- hashes ---------------------------------------------------------------
  * Order-sensitive and cheap on a GPU: a 64-bit SUM of per-item terms; each
- * term is two independent 32-bit multiply-xor hashes (lo | hi<<32) of the
- * item's words and its sequence number.  32-bit IMADs only. */
+ * term hashes the item's words together with its sequence number. */
 #if defined(__CUDACC__)
 #define DEMI_HD __host__ __device__ __forceinline__
 #else
@@ -72,12 +71,16 @@ DEMI_HD uint32_t demi_fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+/* Multilinear hash of six 32-bit words into 64 bits: six 32x32->64 multiply-adds
+ * (IMAD.WIDE on the GPU) and one 64-bit finaliser. */
 DEMI_HD uint64_t demi_hash6(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
-  uint32_t lo = (a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (c * 0xC2B2AE3Du) ^
-                (d * 0x27D4EB2Fu) ^ (e * 0x165667B1u) ^ (f * 0xD3A2646Du);
-  uint32_t hi = (a * 0xFD7046C5u) ^ (b * 0xB55A4F09u) ^ (c * 0x2545F491u) ^
-                (d * 0x9FB21C65u) ^ (e * 0x6C8E9CF5u) ^ (f * 0x7FEB352Du);
-  return (uint64_t)demi_fmix32(lo + 0x6A09E667u) | ((uint64_t)demi_fmix32(hi + 0xBB67AE85u) << 32);
+  uint64_t acc = (uint64_t)a * 0x9E3779B1u + (uint64_t)b * 0x85EBCA77u + (uint64_t)c * 0xC2B2AE3Du +
+                 (uint64_t)d * 0x27D4EB2Fu + (uint64_t)e * 0x165667B1u + (uint64_t)f * 0xD3A2646Du +
+                 0x6A09E667BB67AE85ull;
+  acc ^= acc >> 32;
+  acc *= 0x9E3779B97F4A7C15ull;
+  acc ^= acc >> 29;
+  return acc;
 }
 /* One EventTrace element: words as laid out in demi_event (w0 = kind | src<<8 |
  * dst<<16 | type<<24, w3 = uniq | node<<16), seq = position in the trace,
