@@ -28,6 +28,7 @@ extern "C" int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, co
   if (P.explored_slots < 2 || (P.explored_slots & (P.explored_slots - 1))) return fail(h, DEMI_ERR_INVALID, "explored_slots must be a power of two");
   if (P.max_messages < 0 || P.max_messages > 1022) return fail(h, DEMI_ERR_INVALID, "max_messages must be in [0, 1022] (setMaxMessagesToSchedule)");
   if (!P.heap_cap || !P.max_interleavings) return fail(h, DEMI_ERR_INVALID, "heap_cap / max_interleavings must be positive");
+  if (P.max_interleavings >= (1u << 20)) return fail(h, DEMI_ERR_INVALID, "max_interleavings must be below 2^20");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const DporVariant* dv = pick_dv(h->cfg.model);
   if (!dv) return fail(h, DEMI_ERR_INVALID, "no DPOR kernel for model %d", h->cfg.model);
@@ -47,7 +48,7 @@ extern "C" int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, co
   const size_t S = n_searches, NI = (size_t)P.max_interleavings + 1;
   struct Buf { void** p; size_t bytes; int fill; };
   void *d_ext = 0, *d_off = 0, *d_res = 0, *d_viol = 0, *d_hash = 0, *d_nodes = 0, *d_child = 0, *d_q = 0, *d_ex = 0, *d_heap = 0,
-       *d_tr = 0, *d_tl = 0, *d_cur = 0, *d_next = 0;
+       *d_tr = 0, *d_tl = 0, *d_cur = 0, *d_next = 0, *d_npos = 0, *d_scan = 0;
   Buf bufs[] = {
     {&d_ext, n_ext * sizeof(demi_ext_event), -1}, {&d_off, (S + 1) * sizeof(uint32_t), -1},
     {&d_res, S * sizeof(demi_dpor_result), 0}, {&d_viol, std::max<size_t>(S * cap_viol, 1) * sizeof(demi_dpor_violation), 0},
@@ -56,6 +57,7 @@ extern "C" int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, co
     {&d_q, S * dv->nq * DPOR_QCAP * sizeof(uint32_t), -1}, {&d_ex, S * P.explored_slots * sizeof(uint64_t), 0xFF},
     {&d_heap, S * P.heap_cap * sizeof(DporKey), -1}, {&d_tr, S * NI * a.T1 * sizeof(uint32_t), -1},
     {&d_tl, S * NI * sizeof(uint32_t), -1}, {&d_cur, S * a.T1 * sizeof(uint32_t), -1}, {&d_next, S * a.T1 * sizeof(uint32_t), -1},
+    {&d_npos, S * P.node_cap * sizeof(uint32_t), 0}, {&d_scan, S * a.T1 * sizeof(uint32_t), -1},
   };
   cudaError_t e = cudaSuccess;
   size_t total = 0;
@@ -73,6 +75,7 @@ extern "C" int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, co
   a.nodes = (uint4*)d_nodes; a.child_hash = (uint32_t*)d_child; a.queues = (uint32_t*)d_q; a.explored = (uint64_t*)d_ex;
   a.heap = (DporKey*)d_heap; a.traces = (uint32_t*)d_tr; a.trace_len = (uint32_t*)d_tl;
   a.cur_trace = (uint32_t*)d_cur; a.next_trace = (uint32_t*)d_next;
+  a.node_pos = (uint32_t*)d_npos; a.scan = (uint32_t*)d_scan;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dv->smem);
   if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
   if (e == cudaSuccess) {

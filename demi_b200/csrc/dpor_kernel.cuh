@@ -36,6 +36,8 @@ struct DporArgs {
   // per-search regions (index = search id)
   uint4* nodes; uint32_t* child_hash; uint32_t* queues; uint64_t* explored; DporKey* heap;
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
+  uint32_t* node_pos;           // [node_cap] (interleaving stamp << 12 | first position in the current trace)
+  uint32_t* scan;               // [T1] per trace position: parent's first position << 8 | receiver
 };
 
 template <class MODEL, int BD>
@@ -49,6 +51,7 @@ struct DporMachine {
   uint32_t* smw; const DporArgs* A;
   uint4* nodes; uint32_t* child_hash; uint32_t* queues; uint64_t* explored; DporKey* heap;
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
+  uint32_t* node_pos; uint32_t* scan;
   uint16_t qlen[NQ];            // local memory (small)
   uint32_t n_nodes, n_explored, n_heap, seq, n_traces;
   uint32_t registry, cancelled, isolated;
@@ -301,18 +304,36 @@ struct DporMachine {
         if (A->P.stop_if_found) break;                                           // test() returns Some(trace) :1236-1238
       }
       if (R.interleavings >= A->P.max_interleavings) { R.budget_exhausted = 1; break; }
-      // dpor(currentTrace) :1020-1185
+      // dpor(currentTrace) :1020-1185.  Every ancestor of a delivered event was delivered earlier in
+      // the same trace, so the dependency-tree walks of isCoEnabeled / getCommonPrefix run on trace
+      // POSITIONS: scan[i] = (first position of trace[i]'s parent) << 8 | receiver.  "First position"
+      // is what `trace.indexWhere` (:1058) returns when a Unique was delivered twice.
       const uint32_t n = cur_len;
+      const uint32_t stamp = (k + 1) << 12;
+      for (uint32_t i = 0; i < n; i++) {
+        const uint32_t id = cur_trace[i];
+        if ((node_pos[id] & 0xFFFFF000u) != stamp) node_pos[id] = stamp | i;
+      }
+      for (uint32_t i = 1; i < n; i++) {
+        const uint4 c = nodes[cur_trace[i]];
+        scan[i] = ((node_pos[c.w & 0xFFFFFu] & 0xFFFu) << 8) | hdr_dst(c.x);
+      }
+      scan[0] = 0xFF;                                                             // root: receiver "null"
       for (uint32_t li = 1; li < n && !status; li++) {
         const uint32_t later = cur_trace[li];
-        const uint32_t ldst = hdr_dst(nodes[later].x);
+        const uint32_t ldst = scan[li] & 0xFFu;
+        const uint32_t lfp = node_pos[later] & 0xFFFu;                            // first position of `later`
         for (uint32_t ei = 1; ei < li && !status; ei++) {
+          if ((scan[ei] & 0xFFu) != ldst) continue;                               // isCoEnabeled :1096
           const uint32_t earlier = cur_trace[ei];
-          if (hdr_dst(nodes[earlier].x) != ldst) continue;                        // isCoEnabeled :1096
-          if (is_ancestor(earlier, later)) continue;                              // :1104-1107
-          const uint32_t l = lca(earlier, later);
-          uint32_t branch = 0;
-          while (branch < n && cur_trace[branch] != l) branch++;                  // indexWhere :1058
+          const uint32_t efp = node_pos[earlier] & 0xFFFu;
+          uint32_t a = lfp;
+          while (a > efp) a = scan[a] >> 8;                                       // laterN.pathTo(earlierN) :1104
+          if (a == efp) continue;                                                 // later descends from earlier
+          uint32_t b = efp;                                                       // getCommonPrefix(...).last :994-1018
+          a = lfp;
+          while (a != b) { if (a > b) a = scan[a] >> 8; else b = scan[b] >> 8; }
+          const uint32_t branch = a;                                              // == trace.indexWhere(_ == lca) :1058
           explored_add(earlier, later);                                           // :1071-1073
           R.races++;
           if (explored_has(later, earlier)) continue;      // it would be skipped when popped (:1156-1160)
@@ -362,6 +383,8 @@ dpor_kernel(const __grid_constant__ DporArgs args) {
   m.trace_len = args.trace_len + (size_t)sid * (args.P.max_interleavings + 1);
   m.cur_trace = args.cur_trace + (size_t)sid * args.T1;
   m.next_trace = args.next_trace + (size_t)sid * args.T1;
+  m.node_pos = args.node_pos + (size_t)sid * args.P.node_cap;
+  m.scan = args.scan + (size_t)sid * args.T1;
   m.search(sid);
 }
 
