@@ -239,7 +239,13 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   return DEMI_OK;
 }
 
+static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_dev, void* stream, bool reset_counters);
+
 extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p, void* out_dev, void* stream) {
+  return launch_fuzz(h, p, out_dev, stream, true);
+}
+
+static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_dev, void* stream, bool reset_counters) {
   if (!h) return DEMI_ERR_INVALID;
   if (!out_dev) return fail(h, DEMI_ERR_INVALID, "demi_fuzz_batch_dev: null output");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -249,8 +255,11 @@ extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p
   if (p->n_prefixes == 0) return DEMI_OK;
   cudaStream_t s = (cudaStream_t)stream;
   plan.args.results = (demi_fuzz_result*)out_dev;
-  CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), s));
-  h->perf.kernel_launches = 0;
+  if (reset_counters) {
+    CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), s));
+    h->perf.kernel_launches = 0;
+    h->perf.prefixes = 0;
+  }
   const LaneVariant* lv = pick_lane_variant(h);
   if (lv) {
     // K1-lane handles every prefix it can prove exact; the rest are deferred to the warp engine
@@ -280,7 +289,7 @@ extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p
   plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
   CUDA_TRY(h, cudaGetLastError());
   h->perf.kernel_launches++;
-  h->perf.prefixes = p->n_prefixes;
+  h->perf.prefixes += p->n_prefixes;
   return DEMI_OK;
 }
 
@@ -292,20 +301,43 @@ extern "C" int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p, de
   const size_t bytes = (size_t)p->n_prefixes * sizeof(demi_fuzz_result);
   int32_t rc = ensure(h, (void**)&h->results_dev, &h->results_cap, std::max<size_t>(bytes, 32));
   if (rc != DEMI_OK) return rc;
+  // Pipeline: the batch is cut into chunks; chunk i's records travel to the host on the copy
+  // stream while chunk i+1 is being explored.
+  const uint64_t CHUNK = 2u << 20;
+  const uint64_t n = p->n_prefixes;
+  const uint64_t n_chunks = n <= 2 * CHUNK ? 1 : (n + CHUNK - 1) / CHUNK;
+  const uint64_t per = n_chunks ? (n + n_chunks - 1) / n_chunks : 0;
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-  rc = demi_fuzz_batch_dev(h, p, h->results_dev, h->stream);
+  if (n == 0) { rc = launch_fuzz(h, p, h->results_dev, h->stream, true); if (rc != DEMI_OK) return rc; }
+  std::vector<cudaEvent_t> evs;
+  for (uint64_t c = 0, off = 0; off < n; c++, off += per) {
+    demi_fuzz_params q = *p;
+    q.seed_base = p->seed_base + (int64_t)off;
+    q.n_prefixes = std::min<uint64_t>(per, n - off);
+    rc = launch_fuzz(h, &q, h->results_dev + off, h->stream, c == 0);
+    if (rc != DEMI_OK) break;
+    cudaEvent_t ev;
+    CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    evs.push_back(ev);
+    CUDA_TRY(h, cudaEventRecord(ev, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(out_host + off, h->results_dev + off, q.n_prefixes * sizeof(demi_fuzz_result),
+                                cudaMemcpyDeviceToHost, h->copy_stream));
+  }
+  cudaError_t e = cudaEventRecord(h->ev1, h->stream);
+  unsigned long long cnt[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, h->counters_dev, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->copy_stream);
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   if (rc != DEMI_OK) return rc;
-  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->results_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
-  unsigned long long c[2] = {0, 0};
-  CUDA_TRY(h, cudaMemcpyAsync(c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_fuzz_batch: %s", cudaGetErrorString(e));
   float ms = 0;
   CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->perf.kernel_ms = ms;
-  h->perf.deliveries = c[0];
-  h->perf.violations = c[1];
-  h->perf.d2h_bytes = bytes + sizeof(c);
+  h->perf.deliveries = cnt[0];
+  h->perf.violations = cnt[1];
+  h->perf.d2h_bytes = bytes + sizeof(cnt);
   h->perf.h2d_bytes = 0;
   return DEMI_OK;
 }
