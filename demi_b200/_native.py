@@ -21,7 +21,7 @@ EV_MSG_SEND, EV_MSG_EVENT, EV_SPAWN, EV_KILL, EV_PARTITION, EV_UNPARTITION, EV_B
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("model", C.c_int32), ("model_flags", C.c_uint32),
-                ("blocked_mask", C.c_uint32), ("ignore_timers", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("blocked_mask", C.c_uint32), ("ignore_timers", C.c_int32), ("strategy", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class FuzzParams(C.Structure):

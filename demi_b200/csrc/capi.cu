@@ -34,21 +34,21 @@ static Variant make_variant() {
 static const std::vector<Variant>& variants() {
   static const std::vector<Variant> v = {
     make_variant<PingPong3, 128, 128, false, false>(),
-    make_variant<PingPong3, 8192, 1024, true, false>(),
-    make_variant<PingPong3, 8192, 1024, true, true>(),
+    make_variant<PingPong3, 16384, 1024, true, false>(),
+    make_variant<PingPong3, 16384, 1024, true, true>(),
     make_variant<Raft5, 256, 32, false, false>(),
     make_variant<Raft5, 512, 32, false, false>(),
-    make_variant<Raft5, 8192, 1024, true, false>(),
-    make_variant<Raft5, 8192, 1024, true, true>(),
-    make_variant<Bcast32, 8192, 32, true, false>(),
-    make_variant<Bcast32, 8192, 1024, true, false>(),
-    make_variant<Bcast32, 8192, 1024, true, true>(),
+    make_variant<Raft5, 16384, 1024, true, false>(),
+    make_variant<Raft5, 16384, 1024, true, true>(),
+    make_variant<Bcast32, 16384, 32, true, false>(),
+    make_variant<Bcast32, 16384, 1024, true, false>(),
+    make_variant<Bcast32, 16384, 1024, true, true>(),
   };
   return v;
 }
-static const Variant* pick_variant(int model, uint32_t pcap, uint32_t tcap, bool record) {
+static const Variant* pick_variant(int model, uint32_t pcap, uint32_t tcap, bool record, bool need_global) {
   for (const Variant& v : variants())
-    if (v.model == model && v.record == record && v.pcap >= pcap && v.tcap >= tcap) return &v;
+    if (v.model == model && v.record == record && v.pcap >= pcap && v.tcap >= tcap && (v.pend_global || !need_global)) return &v;
   return nullptr;
 }
 
@@ -80,6 +80,8 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   *out = nullptr;
   if (cfg->model != DEMI_MODEL_PINGPONG3 && cfg->model != DEMI_MODEL_RAFT5 && cfg->model != DEMI_MODEL_BCAST32)
     return fail(nullptr, DEMI_ERR_INVALID, "demi_create: unknown model %d", cfg->model);
+  if (cfg->strategy != DEMI_RS_FULLY_RANDOM && cfg->strategy != DEMI_RS_SRC_DST_FIFO)
+    return fail(nullptr, DEMI_ERR_INVALID, "demi_create: unknown randomization strategy %d", cfg->strategy);
   int n = demi_device_count();
   if (n <= 0) return fail(nullptr, DEMI_ERR_NO_DEVICE, "demi_create: no CUDA device (this engine has no CPU fallback)");
   if (cfg->device < 0 || cfg->device >= n)
@@ -110,7 +112,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
   cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
-  cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count);
+  cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count); cudaFree(h->fifo_scratch);
   demi_replay_free(h);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -172,8 +174,9 @@ static const LaneVariant* pick_lane_variant(const demi_handle* h) {
   static const std::vector<LaneVariant> v = {
     make_lane_variant<Raft5, 256, 96>(),
     make_lane_variant<PingPong3, 256, 128>(),
+    make_lane_variant<Bcast32, 128, 8192>(),
   };
-  if (!h->use_lane_engine || h->cfg.blocked_mask || !h->ext_sends_distinct) return nullptr;
+  if (!h->use_lane_engine || h->cfg.blocked_mask || !h->ext_sends_distinct || h->cfg.strategy != DEMI_RS_FULLY_RANDOM) return nullptr;
   for (const LaneVariant& lv : v) if (lv.model == h->cfg.model) return &lv;
   return nullptr;
 }
@@ -195,7 +198,8 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   if (p->n_prefixes > 0xFFFFFFFFull) return fail(h, DEMI_ERR_INVALID, "n_prefixes > 2^32-1 per call");
   const uint32_t pcap = demi_pending_cap(h->cfg.model, p->max_messages, h->n_ext_sends);
   const uint32_t tcap = demi_tosend_cap(h->n_ext_sends);
-  const Variant* v = pick_variant(h->cfg.model, pcap, tcap, record);
+  const bool fifo = h->cfg.strategy == DEMI_RS_SRC_DST_FIFO;          // SrcDstFIFO lives in the HBM-pending variants
+  const Variant* v = pick_variant(h->cfg.model, pcap, tcap, record, fifo);
   if (!v) return fail(h, DEMI_ERR_CAPACITY, "no kernel variant for pending_cap=%u tosend_cap=%u", pcap, tcap);
   const size_t smem = v->smem_per_warp * WARPS;
   CUDA_TRY(h, cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -226,6 +230,12 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   a.seed_base = p->seed_base;
   a.n_prefixes = p->n_prefixes;
   a.fuzz_flags = p->flags;
+  a.strategy = h->cfg.strategy;
+  if (fifo) {
+    if ((rc = ensure(h, (void**)&h->fifo_scratch, &h->fifo_scratch_bytes,
+                     total_warps * (uint64_t)(v->pcap / 2 + 3 * FIFO_PAIRS) * sizeof(uint16_t))) != DEMI_OK) return rc;
+    a.fifo_scratch = h->fifo_scratch;
+  }
   a.ext = h->ext_dev;
   a.n_ext = (uint32_t)h->ext_host.size();
   a.node_cap = node_cap;

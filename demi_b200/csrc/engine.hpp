@@ -37,6 +37,7 @@ struct demi_handle {
   uint4* lane_pend = nullptr; size_t lane_pend_bytes = 0;
   uint32_t* ovf_list = nullptr; size_t ovf_list_bytes = 0;
   uint32_t* ovf_count = nullptr;
+  uint16_t* fifo_scratch = nullptr; size_t fifo_scratch_bytes = 0;
   int use_lane_engine = 1;
   uint32_t* rec_counts_dev = nullptr;
   // pinned staging for host transfers

@@ -23,6 +23,12 @@ fuzz_kernel(const __grid_constant__ KernelArgs args) {
   m.lane = lane;
   m.nodes_g = args.node_scratch + gw * args.node_cap;
   m.pend_g = PEND_GLOBAL ? (args.pend_scratch + gw * (uint64_t)PCAP) : nullptr;
+  if (PEND_GLOBAL && args.fifo_scratch) {
+    uint16_t* f = args.fifo_scratch + gw * (uint64_t)(M::HALF + 3 * FIFO_PAIRS);
+    m.f_next = f; m.f_head = f + M::HALF; m.f_tail = m.f_head + FIFO_PAIRS; m.f_pairs = m.f_tail + FIFO_PAIRS;
+  } else {
+    m.f_next = m.f_head = m.f_tail = m.f_pairs = nullptr;
+  }
 
   const uint64_t count = args.index_list ? (uint64_t)(*args.index_count) : args.n_prefixes;
   unsigned long long my_steps = 0, my_viol = 0;

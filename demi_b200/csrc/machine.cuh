@@ -26,6 +26,8 @@
 namespace demi {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr uint32_t FIFO_PAIRS = 1056;      // (32 actors + deadLetters... pair code = src*32+dst) rounded up
+constexpr uint32_t FIFO_NIL = 0xFFFFu;
 constexpr int OUTBOX_CAP = 40;
 
 enum OutOp : uint32_t { OP_SEND = 0, OP_SCHED_ONCE = 1, OP_SCHED_REPEAT = 2, OP_CANCEL = 3 };
@@ -127,6 +129,8 @@ struct KernelArgs {
   int64_t  seed_base;
   uint64_t n_prefixes;
   uint32_t fuzz_flags;        // DEMI_FF_*
+  int32_t  strategy;          // DEMI_RS_* (SrcDstFIFO needs a PEND_GLOBAL variant)
+  uint16_t* fifo_scratch;     // [total_warps][PCAP/2 + 3*FIFO_PAIRS] u16: next[], head[], tail[], pairs[]
   // external-event program
   const demi_ext_event* ext;
   uint32_t n_ext;
@@ -189,6 +193,16 @@ struct Machine {
   uint32_t violation, status;
   uint32_t inaccessible, killed;
   uint64_t thash;
+  // ---- SrcDstFIFO (RandomScheduler.scala:702-909); only in PEND_GLOBAL variants.  The lower half of the
+  // pending array is timersAndExternals (:712), the upper half the entry pool of the per-pair FIFO lists
+  // srcDstToMessages (:706); srcDsts (:704) is `f_pairs`.
+  static constexpr uint32_t HALF = PCAP / 2;
+  JRandom rng_pairs;
+  uint32_t n_pairs, n_queued, fifo_free;
+  uint16_t *f_next, *f_head, *f_tail, *f_pairs;
+  __device__ __forceinline__ bool fifo_mode() const { return PEND_GLOBAL && A->strategy == DEMI_RS_SRC_DST_FIFO; }
+  __device__ __forceinline__ uint32_t ld16(const uint16_t* p) const { return (uint32_t)__ldcg(p); }
+
   // ---- lane-distributed registers
   LaneSet just, resend, registry, cancelled;
   uint32_t part_row;        // lane a: EventOrchestrator.partitioned row of actor a
@@ -219,7 +233,35 @@ struct Machine {
   }
 
   // RandomizedHashSet.insert: append (schedulers/Util.scala:126-136)
+  // SrcDstFIFO.+= (RandomScheduler.scala:786-805)
+  __device__ __forceinline__ void fifo_insert(uint4 e) {
+    if (n_pending + n_queued >= A->pending_cap) { status = DEMI_PS_PENDING_OVF; return; }
+    if (hdr_src(e.x) == DEMI_DEADLETTERS) {
+      if (n_pending >= HALF) { status = DEMI_PS_PENDING_OVF; return; }
+      if (lane == 0) pend_store(n_pending, e);
+      n_pending++;
+    } else {
+      if (n_queued >= HALF) { status = DEMI_PS_PENDING_OVF; return; }
+      const uint32_t pair = hdr_src(e.x) * 32u + hdr_dst(e.x);
+      const uint32_t slot = fifo_free;
+      fifo_free = ld16(f_next + slot);
+      const uint32_t head = ld16(f_head + pair), tail = ld16(f_tail + pair);
+      __syncwarp();
+      if (lane == 0) {
+        pend_store(HALF + slot, e);
+        __stcg(f_next + slot, (uint16_t)FIFO_NIL);
+        if (head == FIFO_NIL) { __stcg(f_pairs + n_pairs, (uint16_t)pair); __stcg(f_head + pair, (uint16_t)slot); }
+        else __stcg(f_next + tail, (uint16_t)slot);
+        __stcg(f_tail + pair, (uint16_t)slot);
+      }
+      if (head == FIFO_NIL) n_pairs++;
+      n_queued++;
+      __syncwarp();
+    }
+    if (n_pending + n_queued > max_pending) max_pending = n_pending + n_queued;
+  }
   __device__ __forceinline__ void pending_insert(uint4 e) {
+    if (fifo_mode()) { fifo_insert(e); return; }
     if (n_pending >= A->pending_cap) { status = DEMI_PS_PENDING_OVF; return; }
     if (lane == 0) pend_store(n_pending, e);
     n_pending++;
@@ -453,12 +495,13 @@ struct Machine {
     if (n_pending == 0) return false;
     __syncwarp();
     const uint32_t blocked_mask = A->blocked_mask;
+    const uint32_t TOP = fifo_mode() ? HALF : (uint32_t)PCAP;      // the stash lives at the top of the array in use
     uint32_t nb = 0;
     uint32_t idx = rng.next_int(n_pending);
     uint4 e = pending_remove_at(idx);
     bool got = true;
     while ((blocked_mask >> (hdr_dst(e.x) & 31)) & 1u) {
-      if (lane == 0) pend_store(PCAP - 1 - nb, e);
+      if (lane == 0) pend_store(TOP - 1 - nb, e);
       nb++;
       __syncwarp();
       if (n_pending == 0) { got = false; break; }
@@ -467,13 +510,13 @@ struct Machine {
     }
     if (nb) {
       // reverse the stash in place, then slide it down behind the live entries
-      uint32_t lo = PCAP - nb;
+      uint32_t lo = TOP - nb;
       for (uint32_t base = 0; base < nb / 2; base += 32) {
         uint32_t i = base + lane;
         uint4 x = make_uint4(0, 0, 0, 0), y = x;
-        if (i < nb / 2) { x = pend_load(lo + i); y = pend_load(PCAP - 1 - i); }
+        if (i < nb / 2) { x = pend_load(lo + i); y = pend_load(TOP - 1 - i); }
         __syncwarp();
-        if (i < nb / 2) { pend_store(lo + i, y); pend_store(PCAP - 1 - i, x); }
+        if (i < nb / 2) { pend_store(lo + i, y); pend_store(TOP - 1 - i, x); }
         __syncwarp();
       }
       if (lo != n_pending) {
@@ -492,6 +535,44 @@ struct Machine {
     return got;
   }
 
+  // SrcDstFIFO.getNonBlockedMessage (RandomScheduler.scala:716-756) + dequeue (:758-768)
+  __device__ __forceinline__ bool fifo_get_non_blocked(uint4& out) {
+    const uint32_t blocked_mask = A->blocked_mask;
+    bool any = false;
+    __syncwarp();
+    for (uint32_t base = 0; base < n_pairs && !any; base += 32) {
+      uint32_t i = base + lane;
+      bool ok = i < n_pairs && !((blocked_mask >> (ld16(f_pairs + i) & 31u)) & 1u);
+      any = __any_sync(FULL_MASK, ok);
+    }
+    if (!any) return find_non_blocked(out);                                     // only timers left :717-728
+    if (rng_pairs.next_int(n_pending + n_queued) < n_pending)                    // :732
+      if (find_non_blocked(out)) return true;
+    uint32_t idx = rng_pairs.next_int(n_pairs);                                  // :750-753
+    while ((blocked_mask >> (ld16(f_pairs + idx) & 31u)) & 1u) idx = rng_pairs.next_int(n_pairs);
+    const uint32_t pair = ld16(f_pairs + idx);
+    const uint32_t slot = ld16(f_head + pair);
+    out = pend_load(HALF + slot);
+    const uint32_t nxt = ld16(f_next + slot);
+    __syncwarp();
+    if (lane == 0) { __stcg(f_head + pair, (uint16_t)nxt); __stcg(f_next + slot, (uint16_t)fifo_free); }
+    fifo_free = slot;
+    if (nxt == FIFO_NIL) {                                                       // srcDsts.remove(idx): order preserving
+      for (uint32_t base = idx; base + 1 < n_pairs; base += 32) {
+        uint32_t i = base + lane;
+        uint32_t v = 0;
+        if (i + 1 < n_pairs) v = ld16(f_pairs + i + 1);
+        __syncwarp();
+        if (i + 1 < n_pairs) __stcg(f_pairs + i, (uint16_t)v);
+        __syncwarp();
+      }
+      n_pairs--;
+    }
+    n_queued--;
+    __syncwarp();
+    return true;
+  }
+
   // RandomScheduler.schedule_new_message (RandomScheduler.scala:352-485)
   __device__ __forceinline__ bool schedule_new_message(uint4& pick) {
     if (status | violation) return false;                        // :354-360
@@ -502,7 +583,8 @@ struct Machine {
     }
     send_external_messages();                                    // :424
     if (status) return false;
-    if (!find_non_blocked(pick)) return false;                   // :451-457
+    if (fifo_mode()) { if (!fifo_get_non_blocked(pick)) return false; }   // :446-449
+    else if (!find_non_blocked(pick)) return false;              // :451-457
     nsched++;                                                    // :462
     if (nsched == 0x7FFFFFFF) nsched = 1;
     if (++nmod == A->interval) nmod = 0;
@@ -590,6 +672,12 @@ struct Machine {
     just.clear(); resend.clear(); registry.clear(); cancelled.clear();
     part_row = 0; delivered_bits = 0;
     r_hdr = r_p0 = r_p1 = r_parent = 0;
+    n_pairs = n_queued = fifo_free = 0;
+    if (fifo_mode()) {
+      rng_pairs.seed(seed);                                       // SrcDstFIFO.rand (:705), see demi_b200.h
+      for (uint32_t i = lane; i < FIFO_PAIRS; i += 32) { __stcg(f_head + i, (uint16_t)FIFO_NIL); __stcg(f_tail + i, (uint16_t)FIFO_NIL); }
+      for (uint32_t i = lane; i < HALF; i += 32) __stcg(f_next + i, (uint16_t)(i + 1 < HALF ? i + 1 : FIFO_NIL));
+    }
     if (lane == 0) __stcg(&nodes_g[0], make_uint4(0, 0, 0, 0));   // DepTracker.root (DepTracker.scala:15-17)
     __syncwarp();
   }
@@ -629,6 +717,12 @@ struct Machine {
           uint4 q = pend_load(i);
           sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);
         }
+      if ((A->fuzz_flags & DEMI_FF_HASH_PENDING) && fifo_mode())
+        for (uint32_t pi = 0; pi < n_pairs; pi++)
+          for (uint32_t sl = ld16(f_head + ld16(f_pairs + pi)); sl != FIFO_NIL; sl = ld16(f_next + sl)) {
+            uint4 q = pend_load(HALF + sl);
+            if (lane == 0) sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);
+          }
       for (int o = 16; o > 0; o >>= 1) sh += __shfl_xor_sync(FULL_MASK, sh, o);
       out.violation = violation; out.steps = (uint32_t)nsched;
       out.state_hash = sh; out.trace_hash = thash;

@@ -280,6 +280,7 @@ struct Bcast32 {
       for (uint32_t j = 0; j < 32; j++) if (j != self) out.send(j, FLOOD, p0 - 1, 0);
   }
   static constexpr int REPLAY_OUTBOX = 32;
+  static constexpr int LANE_OUTBOX = 32;
   template <class A>
   __device__ static __forceinline__ uint32_t invariant(A all, uint32_t flags) {
     if (!flags) return 0;

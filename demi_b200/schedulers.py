@@ -27,9 +27,10 @@ class SchedulerConfig(object):
     `model`/`model_flags` stand in for the application under test; `invariant_check`
     is the violation code looked for by the model's built-in invariant (None = any)."""
 
-    def __init__(self, model, model_flags=0, device=0, ignoreTimers=False, blocked_mask=0):
+    def __init__(self, model, model_flags=0, device=0, ignoreTimers=False, blocked_mask=0, strategy=0):
         self.model, self.model_flags, self.device = model, model_flags, device
         self.ignoreTimers, self.blocked_mask = ignoreTimers, blocked_mask
+        self.strategy = strategy       # 0 = FullyRandom, 1 = SrcDstFIFO (RandomizationStrategy, RandomScheduler.scala:624-631)
 
 
 class Engine(object):
@@ -39,7 +40,7 @@ class Engine(object):
         self.cfg = schedulerConfig
         self._h = C.c_void_p()
         c = N.Config(schedulerConfig.device, schedulerConfig.model, schedulerConfig.model_flags,
-                     schedulerConfig.blocked_mask, 1 if schedulerConfig.ignoreTimers else 0)
+                     schedulerConfig.blocked_mask, 1 if schedulerConfig.ignoreTimers else 0, schedulerConfig.strategy)
         rc = N.lib().demi_create(C.byref(c), C.byref(self._h))
         if rc != N.OK:
             raise DemiError(rc, N.lib().demi_last_error(None).decode())

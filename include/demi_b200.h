@@ -115,8 +115,15 @@ typedef struct demi_config {
   uint32_t model_flags;       /* model-defined (raft5: seeded-bug bits)        */
   uint32_t blocked_mask;      /* Instrumenter.blockedActors as a bitmask       */
   int32_t  ignore_timers;     /* SchedulerConfig.ignoreTimers                  */
-  int32_t  reserved[3];
+  int32_t  strategy;          /* RandomizationStrategy of RandomScheduler: DEMI_RS_FULLY_RANDOM / DEMI_RS_SRC_DST_FIFO */
+  int32_t  reserved[2];
 } demi_config;
+/* FullyRandom (RandomScheduler.scala:635-697) */
+#define DEMI_RS_FULLY_RANDOM 0
+/* SrcDstFIFO (RandomScheduler.scala:702-909): a random (src,dst) pair, FIFO within the pair; timers and
+ * externals in random order.  The reference seeds both of its generators from the wall clock (:705, :712);
+ * here both are seeded with the prefix seed (what two constructions in the same millisecond give). */
+#define DEMI_RS_SRC_DST_FIFO 1
 
 /* Per-prefix result of one RandomScheduler execution. 32 bytes. */
 typedef struct demi_fuzz_result {

@@ -22,7 +22,7 @@ RESULT_DTYPE = np.dtype([("violation", "<u4"), ("steps", "<u4"), ("state_hash", 
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("model", C.c_int32), ("model_flags", C.c_uint32),
-                ("blocked_mask", C.c_uint32), ("ignore_timers", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("blocked_mask", C.c_uint32), ("ignore_timers", C.c_int32), ("strategy", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class FuzzParams(C.Structure):
@@ -43,9 +43,9 @@ def lib():
 
 
 def fuzz_batch(model, ext, seed_base, n, max_messages, interval, model_flags=0, blocked_mask=0,
-               ignore_timers=0, looking_for=0, threads=None, flags=0):
+               ignore_timers=0, looking_for=0, threads=None, flags=0, strategy=0):
     ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
-    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers)
+    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers, strategy)
     p = FuzzParams(seed_base, n, max_messages, interval, looking_for, flags)
     out = np.empty(n, dtype=RESULT_DTYPE)
     threads = threads or (os.cpu_count() or 1)
@@ -57,9 +57,9 @@ def fuzz_batch(model, ext, seed_base, n, max_messages, interval, model_flags=0, 
 
 
 def fuzz_trace(model, ext, seed, max_messages, interval, model_flags=0, blocked_mask=0, ignore_timers=0,
-               looking_for=0, cap_events=65536, cap_nodes=65536):
+               looking_for=0, cap_events=65536, cap_nodes=65536, strategy=0):
     ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
-    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers)
+    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers, strategy)
     p = FuzzParams(seed, 1, max_messages, interval, looking_for, 0)
     ev = np.zeros(cap_events, dtype=EVENT_DTYPE)
     par = np.zeros(cap_nodes, dtype=np.uint16)

@@ -48,8 +48,31 @@ static void record_event(om_machine* m, uint8_t kind, uint8_t src, uint8_t dst, 
 }
 
 /* ------------------------------------------------- RandomizedHashSet (a1) */
+#define FIFO_NIL 0xFFFFu
+/* SrcDstFIFO.+= (RandomScheduler.scala:786-805) */
+static void fifo_insert(om_machine* m, const om_pending* e) {
+  if (m->n_pending + m->n_queued >= m->pending_cap) { m->status = DEMI_PS_PENDING_OVF; return; }
+  if (e->msg.src == DEMI_DEADLETTERS) {
+    m->pending[m->n_pending++] = *e;                       /* timersAndExternals += */
+  } else {
+    uint32_t pair = (uint32_t)e->msg.src * 32u + e->msg.dst;
+    uint16_t slot = m->fifo_free;
+    m->fifo_free = m->fifo_next[slot];
+    m->fifo_pool[slot] = *e; m->fifo_next[slot] = FIFO_NIL;
+    if (m->fifo_head[pair] == FIFO_NIL) {                  /* no queue yet: srcDsts.add */
+      m->pairs[m->n_pairs++] = (uint16_t)pair;
+      m->fifo_head[pair] = m->fifo_tail[pair] = slot;
+    } else {
+      m->fifo_next[m->fifo_tail[pair]] = slot;
+      m->fifo_tail[pair] = slot;
+    }
+    m->n_queued++;
+  }
+  if (m->n_pending + m->n_queued > m->max_pending) m->max_pending = m->n_pending + m->n_queued;
+}
 /* RandomizedHashSet.insert: append (schedulers/Util.scala:126-136) */
 void om_pending_insert(om_machine* m, const om_pending* e) {
+  if (m->strategy == DEMI_RS_SRC_DST_FIFO) { fifo_insert(m, e); return; }
   if (m->n_pending >= m->pending_cap) { m->status = DEMI_PS_PENDING_OVF; return; }
   m->pending[m->n_pending++] = *e;
   if (m->n_pending > m->max_pending) m->max_pending = m->n_pending;
@@ -78,13 +101,35 @@ int om_find_non_blocked(om_machine* m, om_pending* out) {
   while (e.msg.dst < 32 && ((m->blocked_mask >> e.msg.dst) & 1u)) {
     blocked[nb++] = e;
     if (m->n_pending == 0) {
-      for (uint32_t i = 0; i < nb; i++) om_pending_insert(m, &blocked[i]);
+      for (uint32_t i = 0; i < nb; i++) m->pending[m->n_pending++] = blocked[i];
       return 0;
     }
     e = om_pending_remove_random(m);
   }
-  for (uint32_t i = 0; i < nb; i++) om_pending_insert(m, &blocked[i]);
+  for (uint32_t i = 0; i < nb; i++) m->pending[m->n_pending++] = blocked[i];
   *out = e;
+  return 1;
+}
+
+/* SrcDstFIFO.getNonBlockedMessage (RandomScheduler.scala:716-756) + dequeue (:758-768) */
+static int fifo_get_non_blocked(om_machine* m, om_pending* out) {
+  int any = 0;
+  for (uint32_t i = 0; i < m->n_pairs; i++) if (!((m->blocked_mask >> (m->pairs[i] & 31u)) & 1u)) { any = 1; break; }
+  if (!any) return om_find_non_blocked(m, out);                            /* only timers left :717-728 */
+  if ((uint32_t)jr_next_int_bound(&m->rng_pairs, (int32_t)(m->n_pending + m->n_queued)) < m->n_pending)   /* :732 */
+    if (om_find_non_blocked(m, out)) return 1;
+  int32_t idx = jr_next_int_bound(&m->rng_pairs, (int32_t)m->n_pairs);      /* :750-753 */
+  while ((m->blocked_mask >> (m->pairs[idx] & 31u)) & 1u) idx = jr_next_int_bound(&m->rng_pairs, (int32_t)m->n_pairs);
+  uint32_t pair = m->pairs[idx];
+  uint16_t slot = m->fifo_head[pair];
+  *out = m->fifo_pool[slot];
+  m->fifo_head[pair] = m->fifo_next[slot];
+  m->fifo_next[slot] = m->fifo_free; m->fifo_free = slot;
+  if (m->fifo_head[pair] == FIFO_NIL) {                                    /* srcDsts.remove(idx): order preserving */
+    for (uint32_t j = (uint32_t)idx; j + 1 < m->n_pairs; j++) m->pairs[j] = m->pairs[j + 1];
+    m->n_pairs--;
+  }
+  m->n_queued--;
   return 1;
 }
 
@@ -308,7 +353,9 @@ static int schedule_new_message(om_machine* m, om_pending* out) {
   if (m->status) return 0;
   /* :426-439 pendingSystemMessages: always empty here (no FD / checkpoint actors) */
   om_pending pick;
-  if (!om_find_non_blocked(m, &pick)) return 0;                 /* :451-457 */
+  if (m->strategy == DEMI_RS_SRC_DST_FIFO) {                    /* :446-449 */
+    if (!fifo_get_non_blocked(m, &pick)) return 0;
+  } else if (!om_find_non_blocked(m, &pick)) return 0;          /* :451-457 */
   if (m->status) return 0;
   m->nsched++;                                                  /* :462 */
   if (m->nsched == INT_MAX) m->nsched = 1;
@@ -368,6 +415,14 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
   m->node_cap = demi_node_cap(m->pending_cap);
   m->event_cap = cap_events;
   jr_seed(&m->rng, seed);
+  m->strategy = cfg->strategy;
+  jr_seed(&m->rng_pairs, seed);
+  m->n_pairs = 0; m->n_queued = 0;
+  if (m->strategy == DEMI_RS_SRC_DST_FIFO) {
+    memset(m->fifo_head, 0xFF, sizeof(m->fifo_head)); memset(m->fifo_tail, 0xFF, sizeof(m->fifo_tail));
+    for (uint32_t i = 0; i < OM_MAX_PENDING; i++) m->fifo_next[i] = (uint16_t)(i + 1 < OM_MAX_PENDING ? i + 1 : 0xFFFFu);
+    m->fifo_free = 0;
+  }
   memset(m->states, 0, sizeof(m->states));
   model->init(m->states, cfg->model_flags);
   /* populateActorSystem: every actor is created and isolated until its Start
@@ -420,10 +475,17 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
     uint32_t nw = (uint32_t)(model->n_actors * model->state_words);
     for (uint32_t i = 0; i < nw; i++) sh += demi_state_term(m->states[i], i);
     if (p->flags & DEMI_FF_HASH_PENDING)          /* order-free: a multiset hash of what is still in flight */
+    {
       for (uint32_t i = 0; i < m->n_pending; i++) {
         const demi_msg* q = &m->pending[i].msg;
         sh += demi_pending_term((uint32_t)q->src | ((uint32_t)q->dst << 8) | ((uint32_t)q->type << 16), q->p0, q->p1);
       }
+      for (uint32_t pi = 0; pi < m->n_pairs; pi++)
+        for (uint16_t sl = m->fifo_head[m->pairs[pi]]; sl != 0xFFFFu; sl = m->fifo_next[sl]) {
+          const demi_msg* q = &m->fifo_pool[sl].msg;
+          sh += demi_pending_term((uint32_t)q->src | ((uint32_t)q->dst << 8) | ((uint32_t)q->type << 16), q->p0, q->p1);
+        }
+    }
     out->state_hash = sh;
     out->trace_hash = m->trace_hash;
     out->n_nodes = (uint16_t)m->n_nodes;

@@ -67,6 +67,13 @@ struct om_machine {
   /* RandomizedHashSet.arr (Util.scala:112) */
   om_pending pending[OM_MAX_PENDING];
   uint32_t n_pending, max_pending;
+  /* SrcDstFIFO (RandomScheduler.scala:702-909): `pending` then holds timersAndExternals (:712);
+   * srcDsts (:704) is `pairs`, srcDstToMessages (:706) the per-pair FIFO lists below */
+  int strategy;
+  jrandom rng_pairs;                        /* SrcDstFIFO.rand (:705) */
+  uint16_t pairs[1056]; uint32_t n_pairs;   /* pair code = src * 32 + dst */
+  om_pending fifo_pool[OM_MAX_PENDING]; uint16_t fifo_next[OM_MAX_PENDING];
+  uint16_t fifo_head[1056], fifo_tail[1056]; uint16_t fifo_free; uint32_t n_queued;
   /* ExternalEventInjector.messagesToSend (ExternalEventInjector.scala:109) */
   demi_msg tosend[OM_MAX_TOSEND];
   uint32_t n_tosend;
