@@ -4,4 +4,5 @@ from . import _native  # noqa: F401
 from .events import (Start, Kill, Send, WaitQuiescence, Partition, UnPartition,  # noqa: F401
                      pack_externals, unpack_externals, raft5_program, pingpong3_program, bcast32_program)
 from .schedulers import (DemiError, SchedulerConfig, Engine, RandomScheduler, STSScheduler, ReplayScheduler,  # noqa: F401
-                         DDMin, MinimizationStats, DPORwHeuristics, mask_of, events_of)
+                         DDMin, MinimizationStats, DPORwHeuristics, STSSchedMinimizer, LeftToRightOneAtATime,
+                         mask_of, events_of)

@@ -54,6 +54,12 @@ class DDMinOut(C.Structure):
                 ("reserved", C.c_uint32 * 2)]
 
 
+class IntMinOut(C.Structure):
+    _fields_ = [("n_events", C.c_uint32), ("deliveries_before", C.c_uint32), ("deliveries_after", C.c_uint32),
+                ("total_replays", C.c_uint32), ("n_internal_sizes", C.c_uint32), ("unignorable", C.c_uint32),
+                ("replays_executed", C.c_uint32), ("batches", C.c_uint32)]
+
+
 class DporParams(C.Structure):
     _fields_ = [("max_messages", C.c_int32), ("depth_bound", C.c_int32), ("max_interleavings", C.c_uint32),
                 ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32), ("node_cap", C.c_uint32),
@@ -75,6 +81,7 @@ EXPORTS = [
     "demi_fuzz_trace", "demi_stats",
     "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin", "demi_dpor_batch",
     "demi_dedup_compact_dev", "demi_dedup_compact",
+    "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
 ]
 
 _lib = None
@@ -123,6 +130,13 @@ def lib():
     L.demi_dedup_compact_dev.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp, vp, vp, vp]
     L.demi_dedup_compact.restype = C.c_int32
     L.demi_dedup_compact.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp, vp, C.POINTER(C.c_uint64)]
+    L.demi_replay_batch_ex.restype = C.c_int32
+    L.demi_replay_batch_ex.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.demi_replay_trace.restype = C.c_int32
+    L.demi_replay_trace.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32,
+                                    C.POINTER(C.c_uint32), vp]
+    L.demi_internal_minimize.restype = C.c_int32
+    L.demi_internal_minimize.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(IntMinOut)]
     L.demi_dpor_batch.restype = C.c_int32
     L.demi_dpor_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), vp, vp, C.c_uint32, vp, C.c_uint32]
     L.demi_stats.restype = C.c_int32

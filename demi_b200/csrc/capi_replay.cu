@@ -16,11 +16,12 @@
 using namespace demi;
 
 typedef void (*replay_fn)(const ReplayArgs);
-struct ReplayVariant { int model; int bd; replay_fn fn; size_t smem; int n_actors; };
+struct ReplayVariant { int model; int bd; replay_fn fn; replay_fn fn_rec; size_t smem; int n_actors; };
 template <class MODEL, int BD>
 static ReplayVariant make_rv() {
   using M = ReplayMachine<MODEL, BD>;
-  return ReplayVariant{MODEL::ID, BD, replay_lane_kernel<MODEL, BD>, (size_t)M::WORDS * BD * sizeof(uint32_t), MODEL::N_ACTORS};
+  return ReplayVariant{MODEL::ID, BD, replay_lane_kernel<MODEL, BD, false>, replay_lane_kernel<MODEL, BD, true>,
+                       (size_t)M::WORDS * BD * sizeof(uint32_t), MODEL::N_ACTORS};
 }
 static const ReplayVariant* pick_rv(int model) {
   static const std::vector<ReplayVariant> v = {
@@ -91,13 +92,26 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
   return DEMI_OK;
 }
 
+static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* skips_dev, uint32_t n_masks, uint32_t mask_words,
+                             uint32_t looking_for, uint32_t flags, void* out_dev, void* stream,
+                             demi_event* rec_dev, uint32_t rec_cap, uint32_t* rec_count_dev);
+
 extern "C" int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, uint32_t n_masks, uint32_t mask_words,
                                          uint32_t looking_for, uint32_t flags, void* out_dev, void* stream) {
   if (!h) return DEMI_ERR_INVALID;
+  if (!masks_dev) return fail(h, DEMI_ERR_INVALID, "demi_replay_batch_dev: null buffer");
+  return launch_replay(h, masks_dev, nullptr, n_masks, mask_words, looking_for, flags, out_dev, stream, nullptr, 0, nullptr);
+}
+
+static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* skips_dev, uint32_t n_masks, uint32_t mask_words,
+                             uint32_t looking_for, uint32_t flags, void* out_dev, void* stream,
+                             demi_event* rec_dev, uint32_t rec_cap, uint32_t* rec_count_dev) {
+  if (!h) return DEMI_ERR_INVALID;
   if (h->trace_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
-  if (!masks_dev || !out_dev) return fail(h, DEMI_ERR_INVALID, "demi_replay_batch_dev: null buffer");
+  if (!out_dev) return fail(h, DEMI_ERR_INVALID, "replay: null output buffer");
+  const bool record = rec_dev != nullptr;
   const uint32_t n_ext = (uint32_t)h->trace_ext_host.size();
-  if (mask_words * 64 < n_ext) return fail(h, DEMI_ERR_INVALID, "mask_words %u too small for %u externals", mask_words, n_ext);
+  if (masks_dev && mask_words * 64 < n_ext) return fail(h, DEMI_ERR_INVALID, "mask_words %u too small for %u externals", mask_words, n_ext);
   if (n_masks == 0) return DEMI_OK;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const ReplayVariant* rv = pick_rv(h->cfg.model);
@@ -121,6 +135,8 @@ extern "C" int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, 
   a.external_type_mask = demi_external_type_mask(h->cfg.model);
   a.n_uniq_words = (h->trace_n_uniq + 31) / 32;
   a.masks = (const uint64_t*)masks_dev; a.n_masks = n_masks; a.mask_words = mask_words;
+  a.skips = (const uint32_t*)skips_dev;
+  a.rec_events = rec_dev; a.rec_cap = rec_cap; a.rec_count = rec_count_dev;
   a.results = (demi_replay_result*)out_dev;
   a.pending_cap = demi_replay_pending_cap(h->trace_n_send_events);
   a.tosend_cap = demi_tosend_cap(h->trace_n_ext_sends);
@@ -140,10 +156,72 @@ extern "C" int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, 
   a.table = (uint4*)h->rp_table; a.tosend = (uint32_t*)h->rp_tosend;
   a.pruned = (flags & DEMI_RF_FILTER_KNOWN_ABSENTS) ? (uint32_t*)h->rp_pruned : nullptr;
   a.counters = h->rp_counters;
-  rv->fn<<<grid, rv->bd, rv->smem, s>>>(a);
+  if (record) {
+    CUDA_TRY(h, cudaFuncSetAttribute(rv->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv->smem));
+    rv->fn_rec<<<1, rv->bd, rv->smem, s>>>(a);
+  } else {
+    rv->fn<<<grid, rv->bd, rv->smem, s>>>(a);
+  }
   CUDA_TRY(h, cudaGetLastError());
   h->perf.kernel_launches = 1;
   h->perf.prefixes = n_masks;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_replay_batch_ex(demi_handle* h, const uint64_t* masks, const uint32_t* skip_events, uint32_t n_tests,
+                                        uint32_t mask_words, uint32_t looking_for, uint32_t flags, demi_replay_result* out_host) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!out_host) return fail(h, DEMI_ERR_INVALID, "demi_replay_batch_ex: null output");
+  if (n_tests == 0) return DEMI_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int32_t rc;
+  const size_t mbytes = masks ? (size_t)n_tests * mask_words * sizeof(uint64_t) : 0, rbytes = (size_t)n_tests * sizeof(demi_replay_result);
+  const size_t sbytes = skip_events ? (size_t)n_tests * sizeof(uint32_t) : 0;
+  if ((rc = ensure_bytes(h, &h->rp_masks, &h->rp_masks_bytes, std::max<size_t>(mbytes + sbytes, 8))) != DEMI_OK) return rc;
+  if ((rc = ensure_bytes(h, &h->rp_results, &h->rp_results_bytes, rbytes)) != DEMI_OK) return rc;
+  char* base = (char*)h->rp_masks;
+  if (masks) CUDA_TRY(h, cudaMemcpyAsync(base, masks, mbytes, cudaMemcpyHostToDevice, h->stream));
+  if (skip_events) CUDA_TRY(h, cudaMemcpyAsync(base + mbytes, skip_events, sbytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  rc = launch_replay(h, masks ? base : nullptr, skip_events ? base + mbytes : nullptr, n_tests, mask_words, looking_for, flags,
+                     h->rp_results, h->stream, nullptr, 0, nullptr);
+  if (rc != DEMI_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->rp_results, rbytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->perf.kernel_ms = ms; h->perf.h2d_bytes = mbytes + sbytes; h->perf.d2h_bytes = rbytes;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_replay_trace(demi_handle* h, const uint64_t* mask, uint32_t mask_words, uint32_t skip_event,
+                                     uint32_t looking_for, uint32_t flags,
+                                     demi_event* events, uint32_t cap_events, uint32_t* n_events, demi_replay_result* result) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!events || !cap_events || !result) return fail(h, DEMI_ERR_INVALID, "demi_replay_trace: null buffer");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  void *d_mask = 0, *d_skip = 0, *d_rec = 0, *d_cnt = 0, *d_res = 0;
+  cudaError_t e = cudaMalloc(&d_rec, (size_t)cap_events * sizeof(demi_event));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cnt, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_res, sizeof(demi_replay_result));
+  if (e == cudaSuccess) e = cudaMalloc(&d_skip, 4);
+  if (e == cudaSuccess && mask) e = cudaMalloc(&d_mask, (size_t)mask_words * 8);
+  if (e == cudaSuccess && mask) e = cudaMemcpyAsync(d_mask, mask, (size_t)mask_words * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_skip, &skip_event, 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, 4, h->stream);
+  int32_t rc = DEMI_OK;
+  if (e == cudaSuccess) rc = launch_replay(h, d_mask, d_skip, 1, mask_words, looking_for, flags, d_res, h->stream,
+                                           (demi_event*)d_rec, cap_events, (uint32_t*)d_cnt);
+  uint32_t cnt = 0;
+  if (e == cudaSuccess && rc == DEMI_OK) e = cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == DEMI_OK) e = cudaMemcpyAsync(result, d_res, sizeof(demi_replay_result), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && rc == DEMI_OK) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && rc == DEMI_OK && cnt) e = cudaMemcpy(events, d_rec, (size_t)std::min(cnt, cap_events) * sizeof(demi_event), cudaMemcpyDeviceToHost);
+  cudaFree(d_mask); cudaFree(d_skip); cudaFree(d_rec); cudaFree(d_cnt); cudaFree(d_res);
+  if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_replay_trace: %s", cudaGetErrorString(e));
+  if (rc != DEMI_OK) return rc;
+  if (n_events) *n_events = cnt;
   return DEMI_OK;
 }
 

@@ -35,8 +35,11 @@ struct ReplayArgs {
   uint32_t external_type_mask;
   uint32_t n_uniq_words;                         // words of the per-test pruned-send bitset
   // tests
-  const uint64_t* masks; uint32_t n_masks, mask_words;
+  const uint64_t* masks; uint32_t n_masks, mask_words;   // masks == nullptr: every test uses the full subsequence
+  const uint32_t* skips;                                   // optional: test i also drops trace event skips[i]
   demi_replay_result* results;
+  // recording (single-test launches of the REC variant): the EventTrace STSScheduler.test returns
+  demi_event* rec_events; uint32_t rec_cap; uint32_t* rec_count;
   // capacities
   uint32_t pending_cap, tosend_cap, table_slots; // table_slots: power of two >= 2*pending_cap
   // per-warp scratch in HBM
@@ -46,7 +49,7 @@ struct ReplayArgs {
   unsigned long long* counters;   // [0] reproduced, [1] delivered
 };
 
-template <class MODEL, int BD>
+template <class MODEL, int BD, bool REC = false>
 struct ReplayMachine {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
@@ -71,7 +74,16 @@ struct ReplayMachine {
 
   __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OB * 3 + a) * BD]; }
   __device__ __forceinline__ LaneState actor(uint32_t a) { return LaneState{smw + a * SW * BD, BD}; }
-  __device__ __forceinline__ bool in_mask(uint32_t i) const { return (mask[i >> 6] >> (i & 63)) & 1ull; }
+  __device__ __forceinline__ bool in_mask(uint32_t i) const { return !mask || ((mask[i >> 6] >> (i & 63)) & 1ull); }
+  // ---- recording (REC): trace + Uniq ids; the pending set becomes an insertion-ordered list so that
+  // equal messages leave oldest-first (Queue.dequeue, STSScheduler.scala:729) and Uniq ids pair up
+  uint32_t n_rec, n_uniq, n_list;
+  __device__ __forceinline__ void rec_push(uint32_t kind, uint32_t src, uint32_t dst, uint32_t type,
+                                           uint32_t p0, uint32_t p1, uint32_t uniq) {
+    if (!REC) return;
+    if (n_rec >= A->rec_cap) { status = DEMI_PS_EVENT_OVF; return; }
+    reinterpret_cast<uint4*>(A->rec_events)[n_rec++] = make_uint4(kind | (src << 8) | (dst << 16) | (type << 24), p0, p1, uniq);
+  }
 
   // ---- pending multiset
   __device__ __forceinline__ uint32_t hash_key(uint32_t hdr, uint32_t p0, uint32_t p1) const {
@@ -88,15 +100,33 @@ struct ReplayMachine {
       s = (s + 1) & (A->table_slots - 1);
     }
   }
-  __device__ __forceinline__ void pending_add(uint32_t hdr, uint32_t p0, uint32_t p1) {
+  __device__ __forceinline__ void pending_add(uint32_t hdr, uint32_t p0, uint32_t p1, uint32_t uniq = 0) {
     if (n_pending >= A->pending_cap) { status = DEMI_PS_PENDING_OVF; return; }
+    if (REC) {
+      if (n_list >= A->table_slots) { status = DEMI_RS_UNSUPPORTED; return; }
+      table[(size_t)n_list * 32] = make_uint4(hdr, p0, p1, uniq | 0x80000000u);
+      n_list++; n_pending++;
+      return;
+    }
     bool found; uint32_t count;
     uint32_t s = probe(hdr, p0, p1, found, count);
     if (status) return;
     table[(size_t)s * 32] = make_uint4(hdr, p0, p1, (gen << 16) | (count + 1));
     n_pending++;
   }
-  __device__ __forceinline__ bool pending_take(uint32_t hdr, uint32_t p0, uint32_t p1) {
+  __device__ __forceinline__ bool pending_take(uint32_t hdr, uint32_t p0, uint32_t p1, uint32_t* uniq_out = nullptr) {
+    if (REC) {
+      for (uint32_t i = 0; i < n_list; i++) {
+        uint4 q = table[(size_t)i * 32];
+        if ((q.w & 0x80000000u) && q.x == hdr && q.y == p0 && q.z == p1) {
+          table[(size_t)i * 32] = make_uint4(q.x, q.y, q.z, q.w & 0x7FFFFFFFu);
+          if (uniq_out) *uniq_out = q.w & 0xFFFFu;
+          n_pending--;
+          return true;
+        }
+      }
+      return false;
+    }
     bool found; uint32_t count;
     uint32_t s = probe(hdr, p0, p1, found, count);
     if (!found || count == 0) return false;
@@ -129,8 +159,13 @@ struct ReplayMachine {
     if (status) return;
     int slot = MODEL::timer_slot(dst, type, p0, p1);
     if (cancelled && slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
+    uint32_t uniq = 0;
+    if (REC) {
+      uniq = ++n_uniq;                                              // Uniq(...) :570; appendMsgSend :620-622
+      rec_push(DEMI_EV_MSG_SEND, (!external && src == DEMI_DEADLETTERS) ? DEMI_TIMER_SND : src, dst, type, p0, p1, uniq);
+    }
     if (!external && crosses_partition(src, dst)) return;
-    pending_add(make_hdr(src, dst, type, 0), p0, p1);
+    pending_add(make_hdr(src, dst, type, 0), p0, p1, uniq);
   }
   __device__ __forceinline__ void tosend_push(uint32_t code) {
     if (n_tosend >= A->tosend_cap) { status = DEMI_PS_QUEUE_OVF; return; }
@@ -207,7 +242,9 @@ struct ReplayMachine {
   }
 
   __device__ __forceinline__ void run(uint32_t test_idx, uint32_t generation, demi_replay_result& out) {
-    mask = A->masks + (size_t)test_idx * A->mask_words;
+    mask = A->masks ? A->masks + (size_t)test_idx * A->mask_words : nullptr;
+    const uint32_t skip = A->skips ? A->skips[test_idx] : 0xFFFFFFFFu;
+    n_rec = n_uniq = n_list = 0;
     gen = generation;
     for (uint32_t i = 0; i < N * SW; i++) smw[i * BD] = MODEL::init_word(i, A->model_flags);
     for (uint32_t a = 0; a < N; a++) part_row(a) = 0;
@@ -270,13 +307,14 @@ struct ReplayMachine {
         else if (kind == DEMI_EV_PARTITION) PF_ROW(src) &= ~(1u << dst);
         else if (kind == DEMI_EV_UNPARTITION) PF_ROW(src) |= 1u << dst;
       }
-      if (!k) continue;
+      if (!k || i == skip) continue;
       // ---- STSSched: advanceReplay (:405-559)
       switch (kind) {
-        case DEMI_EV_SPAWN: inaccessible &= ~(1u << dst); killed &= ~(1u << dst); break;
-        case DEMI_EV_KILL: killed |= 1u << dst; inaccessible |= 1u << dst; break;
-        case DEMI_EV_PARTITION: part_row(src) |= 1u << dst; break;
-        case DEMI_EV_UNPARTITION: part_row(src) &= ~(1u << dst); break;
+        case DEMI_EV_SPAWN: rec_push(kind, src, dst, 0, 0, 0, 0); inaccessible &= ~(1u << dst); killed &= ~(1u << dst); break;
+        case DEMI_EV_KILL: rec_push(kind, src, dst, 0, 0, 0, 0); killed |= 1u << dst; inaccessible |= 1u << dst; break;
+        case DEMI_EV_PARTITION: rec_push(kind, src, dst, 0, 0, 0, 0); part_row(src) |= 1u << dst; break;
+        case DEMI_EV_UNPARTITION: rec_push(kind, src, dst, 0, 0, 0, 0); part_row(src) &= ~(1u << dst); break;
+        case DEMI_EV_QUIESCENCE: case DEMI_EV_BEGIN_WAIT_QUIESCENCE: rec_push(kind, src, dst, 0, 0, 0, 0); break;
         case DEMI_EV_MSG_SEND:
           if ((A->external_type_mask >> (type & 31)) & 1u) tosend_push(0x80000000u | i);   // enqueue_message :469-470
           break;
@@ -284,8 +322,9 @@ struct ReplayMachine {
           flush();                                                   // messagePending :381-403
           if (status) break;
           uint32_t hdr = make_hdr(src, dst, type, 0);
-          bool enabled = !((A->blocked_mask >> (dst & 31)) & 1u) && pending_take(hdr, e.y, e.z);
-          if (enabled) deliver(src, dst, type, e.y, e.z);           // schedule_new_message :696-772
+          uint32_t duniq = 0;
+          bool enabled = !((A->blocked_mask >> (dst & 31)) & 1u) && pending_take(hdr, e.y, e.z, &duniq);
+          if (enabled) { rec_push(DEMI_EV_MSG_EVENT, src, dst, type, e.y, e.z, duniq); deliver(src, dst, type, e.y, e.z); }   // :696-772
           else if (strict) diverged = true;                          // ReplayScheduler: ReplayException
           else ignored++;                                            // "Ignoring message" :528-529
           break;
@@ -296,6 +335,7 @@ struct ReplayMachine {
 #undef PF_ROW
     if (!status && !diverged) flush();                               // :682 before trace_finished
     out.violation = 0; out.delivered = 0; out.ignored = 0; out.state_hash = 0;
+    if (REC && A->rec_count) *A->rec_count = n_rec;
     if (status) { out.status = (uint16_t)status; return; }
     if (diverged) { out.status = DEMI_RS_DIVERGED; out.delivered = (uint16_t)delivered; return; }
     uint32_t v = MODEL::invariant(LaneAll<SW>{smw, BD}, A->model_flags);      // :283-289
@@ -308,10 +348,10 @@ struct ReplayMachine {
   }
 };
 
-template <class MODEL, int BD>
+template <class MODEL, int BD, bool REC = false>
 __global__ void __launch_bounds__(BD)
 replay_lane_kernel(const __grid_constant__ ReplayArgs args) {
-  using M = ReplayMachine<MODEL, BD>;
+  using M = ReplayMachine<MODEL, BD, REC>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
   const uint32_t tid = threadIdx.x;
   const uint64_t gthread = (uint64_t)blockIdx.x * BD + tid;

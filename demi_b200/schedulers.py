@@ -117,6 +117,37 @@ class Engine(object):
         self._check(N.lib().demi_replay_batch_dev(self._h, C.c_void_p(masks_ptr), n_masks, self.mask_words(),
                                                   looking_for or 0, flags, C.c_void_p(out_ptr), C.c_void_p(stream)))
 
+    def replay_batch_ex(self, masks=None, skip_events=None, looking_for=0, flags=0):
+        mw = self.mask_words()
+        n = len(skip_events) if skip_events is not None else len(masks)
+        m = None if masks is None else np.ascontiguousarray(masks, dtype=np.uint64).reshape(-1, mw)
+        sk = None if skip_events is None else np.ascontiguousarray(skip_events, dtype=np.uint32)
+        out = np.empty(n, dtype=N.REPLAY_DTYPE)
+        self._check(N.lib().demi_replay_batch_ex(self._h, None if m is None else m.ctypes.data,
+                                                 None if sk is None else sk.ctypes.data, n, mw, looking_for or 0, flags,
+                                                 out.ctypes.data))
+        return out
+
+    def replay_trace(self, mask=None, skip_event=0xFFFFFFFF, looking_for=0, flags=0, cap_events=65536):
+        """The EventTrace STSScheduler.test returns (recording mode)."""
+        mw = self.mask_words()
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint64)
+        ev = np.zeros(cap_events, dtype=N.EVENT_DTYPE)
+        n = C.c_uint32()
+        res = np.zeros(1, dtype=N.REPLAY_DTYPE)
+        self._check(N.lib().demi_replay_trace(self._h, None if m is None else m.ctypes.data, mw, skip_event,
+                                              looking_for or 0, flags, ev.ctypes.data, cap_events, C.byref(n),
+                                              res.ctypes.data))
+        return res[0], ev[:n.value].copy()
+
+    def internal_minimize(self, looking_for, flags=0, cap_events=65536):
+        ev = np.zeros(cap_events, dtype=N.EVENT_DTYPE)
+        sizes = np.zeros(cap_events, dtype=np.uint32)
+        out = N.IntMinOut()
+        self._check(N.lib().demi_internal_minimize(self._h, looking_for or 0, flags, ev.ctypes.data, cap_events,
+                                                   sizes.ctypes.data, cap_events, C.byref(out)))
+        return ev[:out.n_events].copy(), sizes[:out.n_internal_sizes].copy(), out
+
     def ddmin(self, looking_for, flags=0, check_unmodified=True, cap_iterations=1 << 16):
         mw = self.mask_words()
         mcs = np.zeros(mw, dtype=np.uint64)
@@ -367,3 +398,31 @@ class DPORwHeuristics(object):
         if res[0]["status"]:
             raise DemiError(N.ERR_CAPACITY, "DPOR search status %d" % res[0]["status"])
         return viol[0][0] if res[0]["violations"] else None
+
+
+class LeftToRightOneAtATime(object):
+    """RemovalStrategy that ignores deliveries one at a time, left to right
+    (minification/internal_minimization/OneAtATimeRemoval.scala:131-137)."""
+    pass
+
+
+class STSSchedMinimizer(object):
+    """STSSchedMinimizer(mcs, verified_mcs, violation, removalStrategy, schedulerConfig, ...) —
+    minification/internal_minimization/ScheduleCheckers.scala:19-107; minimize() returns
+    (MinimizationStats, minimized EventTrace) like RunnerUtils.minimizeInternals (RunnerUtils.scala:980-1003)."""
+
+    def __init__(self, mcs, verified_mcs, violation, removalStrategy, schedulerConfig, stats=None, engine=None):
+        if not isinstance(removalStrategy, LeftToRightOneAtATime):
+            raise NotImplementedError("only LeftToRightOneAtATime is accelerated")
+        self.mcs, self.verified_mcs, self.violation = list(mcs), verified_mcs, violation
+        self.engine = engine or Engine(schedulerConfig)
+        self._stats = stats or MinimizationStats()
+        self.last = None
+
+    def minimize(self):
+        self.engine.set_trace(self.verified_mcs, pack_externals(self.mcs))
+        trace, sizes, out = self.engine.internal_minimize(self.violation)
+        self._stats.total_replays += out.total_replays
+        self._stats.internal_sizes = [int(x) for x in sizes]
+        self.last = out
+        return self._stats, trace

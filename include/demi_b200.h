@@ -229,6 +229,33 @@ int32_t demi_replay_batch(demi_handle* h, const uint64_t* masks, uint32_t n_mask
 int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, uint32_t n_masks, uint32_t mask_words,
                               uint32_t looking_for, uint32_t flags, void* out_dev, void* stream);
 
+/* Same as demi_replay_batch with two extensions used by the internal-event minimizers: `masks` may be NULL
+ * (every test replays the full external sequence) and `skip_events[i]` (may be NULL; 0xFFFFFFFF = none) names
+ * one event of the trace — normally a delivery — that test i leaves out, i.e. the EventTrace that
+ * OneAtATimeStrategy.getNextTrace builds (internal_minimization/OneAtATimeRemoval.scala:57-124). */
+int32_t demi_replay_batch_ex(demi_handle* h, const uint64_t* masks, const uint32_t* skip_events, uint32_t n_tests,
+                             uint32_t mask_words, uint32_t looking_for, uint32_t flags, demi_replay_result* out_host);
+/* One STSScheduler.test in recording mode: returns the EventTrace of the replayed execution
+ * (`Some(event_orchestrator.events)`, STSScheduler.scala:292-297) with per-execution Uniq ids (node = 0). */
+int32_t demi_replay_trace(demi_handle* h, const uint64_t* mask, uint32_t mask_words, uint32_t skip_event,
+                          uint32_t looking_for, uint32_t flags,
+                          demi_event* events, uint32_t cap_events, uint32_t* n_events, demi_replay_result* result);
+/* STSSchedMinimizer + LeftToRightOneAtATime over the trace given to demi_set_trace (which must be a verified
+ * MCS trace; its externals are the MCS): RunnerUtils.minimizeInternals (RunnerUtils.scala:980-1003;
+ * internal_minimization/ScheduleCheckers.scala:19-107).  Decisions and counters are the sequential ones;
+ * candidate removals are evaluated speculatively in batches.  On return the handle's trace is the minimized one. */
+typedef struct demi_intmin_out {
+  uint32_t n_events;            /* length of the minimized EventTrace                       */
+  uint32_t deliveries_before, deliveries_after;
+  uint32_t total_replays;       /* tests the sequential algorithm issued                    */
+  uint32_t n_internal_sizes;    /* record_internal_size entries written                     */
+  uint32_t unignorable;         /* RemovalStrategy.unignorable                              */
+  uint32_t replays_executed, batches;
+} demi_intmin_out;
+int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, uint32_t flags,
+                               demi_event* out_trace, uint32_t cap_events,
+                               uint32_t* internal_sizes, uint32_t cap_sizes, demi_intmin_out* out);
+
 /* DDMin.minimize over the trace's externals with STSSched as the TestOracle
  * (RunnerUtils.stsSchedDDMin, RunnerUtils.scala:642-707; DeltaDebugging.scala:27-109).
  * WaitQuiescence externals are dropped first (RunnerUtils.scala:678-684).  The

@@ -215,3 +215,32 @@ def dpor_search(model, ext, max_messages, max_interleavings, looking_for=0, stop
                                   C.c_void_p(hashes.ctypes.data), C.c_uint32(len(hashes)))
     r = res[0]
     return rc, r, viol[:min(int(r["violations"]), cap_viol)].copy(), hashes[:int(r["interleavings"])].copy()
+
+
+# ------------------------------------------------ recorded STS replay / internal minimization
+def replay_trace(model, events, ext, mask, looking_for=0, flags=0, model_flags=0, skip_event=0xFFFFFFFF, cap=65536):
+    ri = make_replay_input(model, events, ext)
+    cfg = Config(0, model, model_flags, 0, 0, 0)
+    mask = np.ascontiguousarray(mask, dtype=np.uint64)
+    out = np.zeros(1, dtype=REPLAY_DTYPE)
+    rec = np.zeros(cap, dtype=EVENT_DTYPE)
+    n = C.c_uint32()
+    lib().oracle_sts_replay_trace(C.byref(cfg), C.byref(ri), C.c_void_p(mask.ctypes.data), C.c_uint32(looking_for),
+                                  C.c_uint32(flags), C.c_uint32(skip_event), C.c_void_p(out.ctypes.data),
+                                  C.c_void_p(rec.ctypes.data), C.c_uint32(cap), C.byref(n))
+    return out[0], rec[:n.value].copy()
+
+
+def internal_minimize(model, verified, mcs_ext, looking_for, flags=0, model_flags=0, cap=65536):
+    verified = np.ascontiguousarray(verified, dtype=EVENT_DTYPE)
+    mcs_ext = np.ascontiguousarray(mcs_ext, dtype=EXT_DTYPE)
+    cfg = Config(0, model, model_flags, 0, 0, 0)
+    out = np.zeros(cap, dtype=EVENT_DTYPE)
+    sizes = np.zeros(cap, dtype=np.uint32)
+    n_out, total, n_sizes, unig = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib().oracle_internal_minimize(C.byref(cfg), C.c_void_p(verified.ctypes.data), C.c_uint32(len(verified)),
+                                        C.c_void_p(mcs_ext.ctypes.data), C.c_uint32(len(mcs_ext)), C.c_uint32(looking_for),
+                                        C.c_uint32(flags), C.c_void_p(out.ctypes.data), C.c_uint32(cap), C.byref(n_out),
+                                        C.byref(total), C.c_void_p(sizes.ctypes.data), C.c_uint32(cap), C.byref(n_sizes),
+                                        C.byref(unig))
+    return rc, out[:n_out.value].copy(), total.value, sizes[:n_sizes.value].copy(), unig.value

@@ -118,6 +118,22 @@ int oracle_sts_project(const demi_replay_input* in, const uint64_t* mask, int fi
  * STSScheduler.scala:112-114). */
 typedef struct { om_machine m; uint32_t delivered, ignored; uint64_t rhash; } sts_machine;
 
+/* Recording (the EventTrace STSScheduler.test returns, STSScheduler.scala:292-297): trigger_start/kill/
+ * partition add their events (EventOrchestrator.scala:219-332), Quiescence markers are copied (:530-534),
+ * every event_produced appends a MsgSend with a fresh Uniq (:570, :622) and every delivery a MsgEvent (:749).
+ * With recording on, equal pending messages are dequeued oldest-first (Queue.dequeue, :729) so that the Uniq
+ * ids pair up exactly as in the reference. */
+static __thread demi_event* g_rec = 0;
+static __thread uint32_t g_rec_cap = 0, g_rec_n = 0, g_rec_uniq = 0;
+static __thread int g_rec_ovf = 0;
+static void rec_push(uint8_t kind, uint8_t src, uint8_t dst, uint8_t type, uint32_t p0, uint32_t p1, uint16_t uniq) {
+  if (!g_rec) return;
+  if (g_rec_n >= g_rec_cap) { g_rec_ovf = 1; return; }
+  demi_event* e = &g_rec[g_rec_n++];
+  e->kind = kind; e->src = src; e->dst = dst; e->type = type; e->p0 = p0; e->p1 = p1; e->uniq = uniq; e->node = 0;
+}
+
+
 static int sts_find(const om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
   for (uint32_t i = 0; i < m->n_pending; i++) {
     const demi_msg* q = &m->pending[i].msg;
@@ -126,6 +142,11 @@ static int sts_find(const om_machine* m, int src, int dst, uint8_t type, uint32_
   return -1;
 }
 static void sts_remove_at(om_machine* m, uint32_t i) {
+  if (g_rec) {                       /* keep insertion order: sts_find then returns the oldest equal entry */
+    for (uint32_t j = i; j + 1 < m->n_pending; j++) m->pending[j] = m->pending[j + 1];
+    m->n_pending--;
+    return;
+  }
   m->pending[i] = m->pending[m->n_pending - 1];
   m->n_pending--;
 }
@@ -158,10 +179,13 @@ static void sts_event_produced(om_machine* m, const demi_msg* msg) {
   if (m->status) return;
   int ci = key_find(m->cancelled, m->n_cancelled, msg->dst, msg->type, msg->p0, msg->p1);
   if (ci >= 0) { key_remove(m->cancelled, &m->n_cancelled, ci); return; }
+  uint16_t uniq = (uint16_t)(++g_rec_uniq);                                /* Uniq(...) :570 */
+  int is_timer = !(msg->flags & DEMI_MF_EXTERNAL) && msg->src == DEMI_DEADLETTERS;
+  rec_push(DEMI_EV_MSG_SEND, is_timer ? DEMI_TIMER_SND : msg->src, msg->dst, msg->type, msg->p0, msg->p1, uniq);   /* :620-622 */
   if (!(msg->flags & DEMI_MF_EXTERNAL) && sts_crosses(m, msg->src, msg->dst)) return;
   if (m->n_pending >= m->pending_cap) { m->status = DEMI_PS_PENDING_OVF; return; }
   m->pending[m->n_pending].msg = *msg;
-  m->pending[m->n_pending].uniq = 0; m->pending[m->n_pending].node = 0;
+  m->pending[m->n_pending].uniq = uniq; m->pending[m->n_pending].node = 0;
   m->n_pending++;
   if (m->n_pending > m->max_pending) m->max_pending = m->n_pending;
 }
@@ -215,7 +239,14 @@ void sts_om_cancel(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t 
 
 void oracle_sts_replay(const demi_config* cfg, const demi_replay_input* in, const uint64_t* mask,
                        uint32_t looking_for, uint32_t flags, demi_replay_result* out, void* scratch) {
+  oracle_sts_replay_ex(cfg, in, mask, looking_for, flags, 0xFFFFFFFFu, out, 0, 0, 0, scratch);
+}
+
+void oracle_sts_replay_ex(const demi_config* cfg, const demi_replay_input* in, const uint64_t* mask,
+                          uint32_t looking_for, uint32_t flags, uint32_t skip_event, demi_replay_result* out,
+                          demi_event* rec, uint32_t cap_rec, uint32_t* n_rec, void* scratch) {
   sts_machine* S = scratch ? (sts_machine*)scratch : (sts_machine*)malloc(sizeof(sts_machine));
+  g_rec = rec; g_rec_cap = cap_rec; g_rec_n = 0; g_rec_uniq = 0; g_rec_ovf = 0;
   om_machine* m = &S->m;
   const oracle_model* model = oracle_get_model(cfg->model);
   memset(out, 0, sizeof(*out));
@@ -245,14 +276,18 @@ void oracle_sts_replay(const demi_config* cfg, const demi_replay_input* in, cons
     int found = 0;
     while (idx < n && !m->status) {
       const demi_event* e = &in->events[idx];
-      if (keep[idx]) {
+      if (keep[idx] && idx != skip_event) {
         switch (e->kind) {
           case DEMI_EV_SPAWN:                                       /* trigger_start */
+            rec_push(DEMI_EV_SPAWN, e->src, e->dst, 0, 0, 0, 0);
             m->inaccessible &= ~(1u << e->dst); m->killed &= ~(1u << e->dst); break;
           case DEMI_EV_KILL:
+            rec_push(DEMI_EV_KILL, e->src, e->dst, 0, 0, 0, 0);
             m->killed |= 1u << e->dst; m->inaccessible |= 1u << e->dst; break;
-          case DEMI_EV_PARTITION: m->partitioned[e->src] |= 1u << e->dst; break;
-          case DEMI_EV_UNPARTITION: m->partitioned[e->src] &= ~(1u << e->dst); break;
+          case DEMI_EV_PARTITION: rec_push(DEMI_EV_PARTITION, e->src, e->dst, 0, 0, 0, 0); m->partitioned[e->src] |= 1u << e->dst; break;
+          case DEMI_EV_UNPARTITION: rec_push(DEMI_EV_UNPARTITION, e->src, e->dst, 0, 0, 0, 0); m->partitioned[e->src] &= ~(1u << e->dst); break;
+          case DEMI_EV_QUIESCENCE: case DEMI_EV_BEGIN_WAIT_QUIESCENCE:
+            rec_push(e->kind, e->src, e->dst, 0, 0, 0, 0); break;
           case DEMI_EV_MSG_SEND:
             if ((in->external_type_mask >> (e->type & 31)) & 1u) {  /* :469-470 enqueue_message */
               demi_msg s; s.src = DEMI_DEADLETTERS; s.dst = e->dst; s.type = e->type; s.flags = DEMI_MF_EXTERNAL;
@@ -281,6 +316,7 @@ void oracle_sts_replay(const demi_config* cfg, const demi_replay_input* in, cons
     /* deliver the expected message (:696-772) */
     const demi_event* e = &in->events[idx];
     int pi = sts_find(m, e->src, e->dst, e->type, e->p0, e->p1);
+    rec_push(DEMI_EV_MSG_EVENT, e->src, e->dst, e->type, e->p0, e->p1, m->pending[pi].uniq);   /* appendMsgEvent :749 */
     sts_remove_at(m, (uint32_t)pi);
     idx++;
     S->rhash += demi_event_term((uint32_t)e->src | ((uint32_t)e->dst << 8) | ((uint32_t)e->type << 16),
@@ -308,6 +344,9 @@ void oracle_sts_replay(const demi_config* cfg, const demi_replay_input* in, cons
     for (uint32_t i = 0; i < nw; i++) sh += demi_state_term(m->states[i], i);
     out->state_hash = sh + S->rhash;
   }
+  if (n_rec) *n_rec = g_rec_n;
+  if (g_rec_ovf && !out->status) out->status = DEMI_PS_EVENT_OVF;
+  g_rec = 0;
   free(keep);
   if (!scratch) free(S);
 }

@@ -15,6 +15,9 @@ typedef struct demi_replay_input {
 int  oracle_sts_project(const demi_replay_input* in, const uint64_t* mask, int filter_known_absents, uint8_t* keep);
 void oracle_sts_replay(const demi_config* cfg, const demi_replay_input* in, const uint64_t* mask,
                        uint32_t looking_for, uint32_t flags, demi_replay_result* out, void* scratch);
+void oracle_sts_replay_ex(const demi_config* cfg, const demi_replay_input* in, const uint64_t* mask,
+                          uint32_t looking_for, uint32_t flags, uint32_t skip_event, demi_replay_result* out,
+                          demi_event* rec, uint32_t cap_rec, uint32_t* n_rec, void* scratch);
 size_t oracle_sts_scratch_size(void);
 int  oracle_in_sts_mode(void);
 
