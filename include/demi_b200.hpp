@@ -1,0 +1,282 @@
+// demi_b200.hpp — C++ host-side mirror of DEMi's scheduler plugin surface over the C ABI
+// (include/demi_b200.h).  Header-only; link with -ldemi_b200.
+//
+// The reference's host is Scala; this image has no JVM toolchain, so the compiled-language host
+// layer that sits above the C ABI is C++ here (the JNI/Scala binding a DEMi maintainer would add is
+// in jni/).  Class and method names, argument meaning and error behaviour follow the reference:
+//
+//   SchedulerConfig      src/main/scala/verification/SchedulerConfig.scala:9-37
+//   RandomScheduler      schedulers/RandomScheduler.scala:41 (explore :234, test :597, setMaxMessages :55,
+//                        setInvariant :521)
+//   STSScheduler         schedulers/STSScheduler.scala:84 (test :199)
+//   ReplayScheduler      schedulers/ReplayScheduler.scala:71 (replay; ReplayException :128-130)
+//   DDMin                minification/DeltaDebugging.scala:7 (minimize :27, verify_mcs :64)
+//   STSSchedMinimizer    minification/internal_minimization/ScheduleCheckers.scala:19 (minimize :34)
+//   DPORwHeuristics      schedulers/DPORwHeuristics.scala:77 (test :1193, setMaxMessagesToSchedule :123,
+//                        setDepthBound :116)
+//   MinimizationStats    minification/Minimizer.scala:30-237 (the counters DDMin / the minimizers drive)
+//
+// Reference exceptions map to C++ ones: IllegalArgumentException -> std::invalid_argument,
+// IllegalStateException -> std::logic_error, ReplayException -> demi::ReplayException, anything the
+// engine reports -> demi::Error (code + demi_last_error text).  There is no CPU fallback: without a
+// CUDA device the constructors throw demi::Error(DEMI_ERR_NO_DEVICE).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "demi_b200.h"
+
+namespace demi {
+
+struct Error : std::runtime_error {
+  int32_t code;
+  Error(int32_t c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+struct ReplayException : std::runtime_error { using std::runtime_error::runtime_error; };
+
+typedef uint32_t ViolationFingerprint;          // the model's violation code; 0 = "any" where optional
+typedef std::vector<demi_ext_event> ExternalEvents;
+typedef std::vector<demi_event> EventTrace;
+
+// ---- external events (ExternalEvents.scala:62-91) with stable ids (UniqueExternalEvent._id)
+inline uint32_t next_external_id() { static uint32_t id = 0; return ++id; }            // IDGenerator
+inline demi_ext_event Start(uint8_t name) { return {DEMI_EXT_START, name, 0, 0, 0, 0, next_external_id()}; }
+inline demi_ext_event Kill(uint8_t name) { return {DEMI_EXT_KILL, name, 0, 0, 0, 0, next_external_id()}; }
+inline demi_ext_event Send(uint8_t name, uint8_t type, uint32_t p0 = 0, uint32_t p1 = 0) {
+  return {DEMI_EXT_SEND, name, 0, type, p0, p1, next_external_id()};
+}
+inline demi_ext_event WaitQuiescence() { return {DEMI_EXT_WAIT_QUIESCENCE, 0, 0, 0, 0, 0, next_external_id()}; }
+inline demi_ext_event Partition(uint8_t a, uint8_t b) { return {DEMI_EXT_PARTITION, a, b, 0, 0, 0, next_external_id()}; }
+inline demi_ext_event UnPartition(uint8_t a, uint8_t b) { return {DEMI_EXT_UNPARTITION, a, b, 0, 0, 0, next_external_id()}; }
+
+struct SchedulerConfig {
+  int32_t model = DEMI_MODEL_RAFT5;
+  uint32_t model_flags = 0;
+  int32_t device = 0;
+  bool ignoreTimers = false;
+  bool filterKnownAbsents = false;
+  uint32_t blocked_mask = 0;
+  int32_t strategy = DEMI_RS_FULLY_RANDOM;      // RandomizationStrategy: FullyRandom | SrcDstFIFO
+};
+
+struct MinimizationStats {
+  uint32_t total_replays = 0;
+  std::vector<uint32_t> iteration_size, internal_size;
+  void increment_replays(uint32_t n = 1) { total_replays += n; }
+};
+
+// One demi_handle.
+class Engine {
+ public:
+  explicit Engine(const SchedulerConfig& c) : cfg(c) {
+    demi_config dc{};
+    dc.device = c.device; dc.model = c.model; dc.model_flags = c.model_flags; dc.blocked_mask = c.blocked_mask;
+    dc.ignore_timers = c.ignoreTimers ? 1 : 0; dc.strategy = c.strategy;
+    int32_t rc = demi_create(&dc, &h);
+    if (rc != DEMI_OK) throw Error(rc, demi_last_error(nullptr));
+  }
+  ~Engine() { demi_destroy(h); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  void check(int32_t rc) const {
+    if (rc == DEMI_OK) return;
+    std::string msg = demi_last_error(h);
+    if (rc == DEMI_ERR_INVALID) throw std::invalid_argument(msg);
+    if (rc == DEMI_ERR_STATE) throw std::logic_error(msg);
+    throw Error(rc, msg);
+  }
+  demi_handle* handle() const { return h; }
+  const SchedulerConfig cfg;
+ private:
+  demi_handle* h = nullptr;
+};
+
+inline std::vector<uint64_t> mask_of(const ExternalEvents& all, const ExternalEvents& subseq) {
+  std::vector<uint64_t> m((all.size() + 63) / 64 ? (all.size() + 63) / 64 : 1, 0);
+  for (const demi_ext_event& s : subseq)
+    for (size_t i = 0; i < all.size(); i++)
+      if (all[i].id == s.id) { m[i >> 6] |= 1ull << (i & 63); break; }
+  return m;
+}
+inline ExternalEvents events_of(const ExternalEvents& all, const std::vector<uint64_t>& mask) {
+  ExternalEvents out;
+  for (size_t i = 0; i < all.size(); i++) if ((mask[i >> 6] >> (i & 63)) & 1ull) out.push_back(all[i]);
+  return out;
+}
+
+class RandomScheduler {
+ public:
+  RandomScheduler(const SchedulerConfig& cfg, uint32_t max_executions = 1, int32_t invariant_check_interval = 0,
+                  int64_t seed = 0, std::shared_ptr<Engine> e = nullptr)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), max_executions(max_executions),
+        invariant_check_interval(invariant_check_interval), seed(seed) {}
+  std::string getName() const { return "RandomScheduler"; }
+  void setMaxMessages(int32_t n) { maxMessages = n; }
+  void setInvariant(bool have) { have_invariant = have; }          // models carry their invariant
+  // Some((trace, fingerprint)) of the first violating execution, else nullopt (RandomScheduler.scala:234-272)
+  std::optional<std::pair<EventTrace, ViolationFingerprint>> explore(const ExternalEvents& trace,
+                                                                     ViolationFingerprint lookingFor = 0) {
+    if (!have_invariant) throw std::invalid_argument("Must invoke setInvariant before test()");   // :244-246
+    engine->check(demi_set_externals(engine->handle(), trace.data(), (uint32_t)trace.size()));
+    demi_fuzz_params p{seed, max_executions, maxMessages, invariant_check_interval, lookingFor, 0};
+    results.assign(max_executions, demi_fuzz_result{});
+    engine->check(demi_fuzz_batch(engine->handle(), &p, results.data()));
+    if (stats) stats->increment_replays(max_executions);
+    for (uint32_t i = 0; i < max_executions; i++) {
+      if (results[i].status) throw Error(DEMI_ERR_CAPACITY, "a prefix overflowed an engine structure");
+      if (!results[i].violation) continue;
+      EventTrace ev(65536);
+      uint32_t n_ev = 0, n_nodes = 0;
+      demi_fuzz_result r{};
+      engine->check(demi_fuzz_trace(engine->handle(), &p, seed + i, ev.data(), (uint32_t)ev.size(), &n_ev, nullptr, 0, &n_nodes, &r));
+      ev.resize(n_ev);
+      return std::make_pair(ev, r.violation);
+    }
+    return std::nullopt;
+  }
+  // TestOracle.test: Some(trace) iff the violation was reproduced (RandomScheduler.scala:597-612)
+  std::optional<EventTrace> test(const ExternalEvents& events, ViolationFingerprint fp, MinimizationStats* s = nullptr) {
+    stats = s;
+    auto r = explore(events, fp);
+    if (!r) return std::nullopt;
+    return r->first;
+  }
+  std::shared_ptr<Engine> engine;
+  std::vector<demi_fuzz_result> results;
+ private:
+  uint32_t max_executions; int32_t invariant_check_interval; int64_t seed;
+  int32_t maxMessages = -1;                                           // Int.MaxValue (:54)
+  bool have_invariant = true;
+  MinimizationStats* stats = nullptr;
+};
+
+class STSScheduler {
+ public:
+  STSScheduler(const SchedulerConfig& cfg, const EventTrace& original_trace, const ExternalEvents& original_externals,
+               bool allowPeek = false, std::shared_ptr<Engine> e = nullptr)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), original_trace(original_trace), original_externals(original_externals),
+        flags(cfg.filterKnownAbsents ? DEMI_RF_FILTER_KNOWN_ABSENTS : 0) {
+    if (allowPeek) throw std::invalid_argument("STSSched with Peek is outside the accelerated path");
+    if (original_trace.empty()) throw std::invalid_argument("original_trace must not be empty");     // assume(:203)
+    engine->check(demi_set_trace(engine->handle(), original_trace.data(), (uint32_t)original_trace.size(),
+                                 original_externals.data(), (uint32_t)original_externals.size()));
+  }
+  std::string getName() const { return "STSSchedNoPeek"; }
+  uint32_t mask_words() const { return (uint32_t)((original_externals.size() + 63) / 64 ? (original_externals.size() + 63) / 64 : 1); }
+  // Some(recorded trace) iff the violation was reproduced (STSScheduler.scala:199-310)
+  std::optional<EventTrace> test(const ExternalEvents& subseq, ViolationFingerprint fp, MinimizationStats* stats = nullptr) {
+    if (stats) stats->increment_replays();
+    std::vector<uint64_t> m = mask_of(original_externals, subseq);
+    EventTrace ev(65536);
+    uint32_t n = 0; demi_replay_result r{};
+    engine->check(demi_replay_trace(engine->handle(), m.data(), mask_words(), 0xFFFFFFFFu, fp, flags, ev.data(),
+                                    (uint32_t)ev.size(), &n, &r));
+    if (r.status) throw Error(DEMI_ERR_CAPACITY, "replay reported a capacity status");
+    if (!r.violation) return std::nullopt;
+    ev.resize(n);
+    return ev;
+  }
+  std::vector<demi_replay_result> test_batch(const std::vector<std::vector<uint64_t>>& masks, ViolationFingerprint fp) {
+    std::vector<uint64_t> flat;
+    for (auto& m : masks) flat.insert(flat.end(), m.begin(), m.end());
+    std::vector<demi_replay_result> out(masks.size());
+    engine->check(demi_replay_batch(engine->handle(), flat.data(), (uint32_t)masks.size(), mask_words(), fp, flags, out.data()));
+    return out;
+  }
+  std::shared_ptr<Engine> engine;
+  const EventTrace original_trace;
+  const ExternalEvents original_externals;
+  const uint32_t flags;
+};
+
+class ReplayScheduler : public STSScheduler {
+ public:
+  using STSScheduler::STSScheduler;
+  // strict replay of the recorded trace; throws ReplayException on divergence (ReplayScheduler.scala:71-140)
+  demi_replay_result replay(ViolationFingerprint fp = 0) {
+    std::vector<uint64_t> m = mask_of(original_externals, original_externals);
+    demi_replay_result r{};
+    engine->check(demi_replay_batch(engine->handle(), m.data(), 1, mask_words(), fp, flags | DEMI_RF_STRICT, &r));
+    if (r.status == DEMI_RS_DIVERGED) throw ReplayException("Expected event not pending after " + std::to_string(r.delivered) + " deliveries");
+    if (r.status) throw Error(DEMI_ERR_CAPACITY, "replay reported a capacity status");
+    return r;
+  }
+};
+
+class DDMin {
+ public:
+  DDMin(STSScheduler& oracle, bool checkUnmodifed = false, MinimizationStats* stats = nullptr)
+      : oracle(oracle), checkUnmodifed(checkUnmodifed), _stats(stats ? stats : &own) {}
+  // the MCS (WaitQuiescence dropped, RunnerUtils.scala:678-684); throws std::invalid_argument
+  // ("Unmodified trace does not trigger violation") like DeltaDebugging.scala:41-47
+  ExternalEvents minimize(ViolationFingerprint fp) {
+    std::vector<uint64_t> mcs(oracle.mask_words(), 0);
+    std::vector<uint32_t> iters(1 << 16);
+    oracle.engine->check(demi_ddmin(oracle.engine->handle(), fp, oracle.flags, checkUnmodifed ? 1 : 0, mcs.data(),
+                                    oracle.mask_words(), iters.data(), (uint32_t)iters.size(), &last));
+    _stats->total_replays = last.total_replays;
+    _stats->iteration_size.assign(iters.begin(), iters.begin() + last.n_iterations);
+    return events_of(oracle.original_externals, mcs);
+  }
+  std::optional<EventTrace> verify_mcs(const ExternalEvents& mcs, ViolationFingerprint fp) { return oracle.test(mcs, fp); }
+  demi_ddmin_out last{};
+  MinimizationStats* _stats;
+ private:
+  STSScheduler& oracle; bool checkUnmodifed; MinimizationStats own;
+};
+
+struct LeftToRightOneAtATime {};       // RemovalStrategy (OneAtATimeRemoval.scala:131-137)
+
+class STSSchedMinimizer {
+ public:
+  STSSchedMinimizer(const ExternalEvents& mcs, const EventTrace& verified_mcs, ViolationFingerprint violation,
+                    LeftToRightOneAtATime, const SchedulerConfig& cfg, std::shared_ptr<Engine> e = nullptr)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), mcs(mcs), verified_mcs(verified_mcs), violation(violation),
+        flags(cfg.filterKnownAbsents ? DEMI_RF_FILTER_KNOWN_ABSENTS : 0) {}
+  std::pair<MinimizationStats, EventTrace> minimize() {
+    engine->check(demi_set_trace(engine->handle(), verified_mcs.data(), (uint32_t)verified_mcs.size(), mcs.data(), (uint32_t)mcs.size()));
+    EventTrace out(65536); std::vector<uint32_t> sizes(65536);
+    engine->check(demi_internal_minimize(engine->handle(), violation, flags, out.data(), (uint32_t)out.size(), sizes.data(),
+                                         (uint32_t)sizes.size(), &last));
+    out.resize(last.n_events);
+    MinimizationStats s;
+    s.total_replays = last.total_replays;
+    s.internal_size.assign(sizes.begin(), sizes.begin() + last.n_internal_sizes);
+    return {s, out};
+  }
+  demi_intmin_out last{};
+ private:
+  std::shared_ptr<Engine> engine; ExternalEvents mcs; EventTrace verified_mcs; ViolationFingerprint violation; uint32_t flags;
+};
+
+class DPORwHeuristics {
+ public:
+  DPORwHeuristics(const SchedulerConfig& cfg, int32_t depth_bound = -1, bool stopIfViolationFound = true,
+                  uint32_t max_interleavings = 1000, std::shared_ptr<Engine> e = nullptr)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), depth_bound(depth_bound), stop(stopIfViolationFound), budget(max_interleavings) {}
+  std::string getName() const { return "DPORwHeuristics"; }
+  void setMaxMessagesToSchedule(int32_t n) { max_messages = n; }
+  void setDepthBound(int32_t d) { depth_bound = d; }
+  // the first violating interleaving, or nullopt (DPORwHeuristics.scala:1193-1242)
+  std::optional<demi_dpor_violation> test(const ExternalEvents& events, ViolationFingerprint fp, MinimizationStats* stats = nullptr) {
+    if (max_messages < 0) throw std::invalid_argument("setMaxMessagesToSchedule is required");
+    ExternalEvents prog;                                              // convertToDPORTrace (:1279-1303)
+    for (const demi_ext_event& e : events) if (e.kind == DEMI_EXT_START || e.kind == DEMI_EXT_SEND) prog.push_back(e);
+    uint32_t offs[2] = {0, (uint32_t)prog.size()};
+    demi_dpor_params P{max_messages, depth_bound, budget, fp, stop ? 1u : 0u, 4096, 1u << 16, 1u << 15};
+    demi_dpor_violation v[8]{};
+    engine->check(demi_dpor_batch(engine->handle(), prog.data(), offs, 1, &P, &last, v, 8, nullptr, 0));
+    if (stats) stats->increment_replays(last.interleavings);
+    if (last.status) throw Error(DEMI_ERR_CAPACITY, "DPOR search reported a capacity status");
+    if (!last.violations) return std::nullopt;
+    return v[0];
+  }
+  demi_dpor_result last{};
+ private:
+  std::shared_ptr<Engine> engine; int32_t depth_bound; bool stop; uint32_t budget; int32_t max_messages = -1;
+};
+
+}  // namespace demi

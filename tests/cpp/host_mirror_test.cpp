@@ -1,0 +1,71 @@
+// C++ host mirror (include/demi_b200.hpp) end to end.  With a CUDA device: fuzz -> DDMin -> verify ->
+// internal minimization -> strict replay -> DPOR.  Without: the no-CPU-fallback contract.
+#include <cstdio>
+#include <cstdlib>
+#include "demi_b200.hpp"
+
+using namespace demi;
+
+#define CHECK(c) do { if (!(c)) { std::printf("CHECK failed: %s (line %d)\n", #c, __LINE__); return 1; } } while (0)
+
+int main() {
+  SchedulerConfig cfg;
+  cfg.model = DEMI_MODEL_RAFT5;
+  cfg.model_flags = 1;
+  if (demi_device_count() == 0) {
+    try { RandomScheduler r(cfg); std::printf("expected an exception\n"); return 1; }
+    catch (const Error& e) { CHECK(e.code == DEMI_ERR_NO_DEVICE); std::printf("no device: %s\nOK (no-fallback contract)\n", e.what()); return 0; }
+  }
+  ExternalEvents prog;
+  for (int a = 0; a < 5; a++) prog.push_back(Start((uint8_t)a));
+  for (int a = 0; a < 5; a++) prog.push_back(Send((uint8_t)a, 1, 0x1F));
+  for (int k = 0; k < 6; k++) prog.push_back(Send((uint8_t)(k % 5), 2, 1 + k));
+  prog.push_back(WaitQuiescence());
+
+  RandomScheduler sched(cfg, /*max_executions=*/4000, /*invariant_check_interval=*/5, /*seed=*/1);
+  sched.setMaxMessages(50);
+  auto found = sched.explore(prog);
+  CHECK(found.has_value());
+  EventTrace trace = found->first;
+  ViolationFingerprint fp = found->second;
+  std::printf("violation %u, trace of %zu events\n", fp, trace.size());
+  CHECK(!sched.test(prog, 99).has_value());                       // a fingerprint that never occurs
+
+  ReplayScheduler replayer(cfg, trace, prog);
+  demi_replay_result rr = replayer.replay(fp);                     // validate_replay (RunnerUtils.scala:101-128)
+  CHECK(rr.violation == fp && rr.ignored == 0);
+
+  STSScheduler sts(cfg, trace, prog);
+  MinimizationStats stats;
+  DDMin ddmin(sts, /*checkUnmodifed=*/true, &stats);
+  ExternalEvents mcs = ddmin.minimize(fp);
+  std::printf("DDMin: %zu -> %zu externals in %u sequential tests (%u executed)\n", prog.size() - 1, mcs.size(),
+              stats.total_replays, ddmin.last.replays_executed);
+  CHECK(mcs.size() < prog.size());
+  auto verified = ddmin.verify_mcs(mcs, fp);
+  if (!verified) { mcs.assign(prog.begin(), prog.end() - 1); verified = sts.test(mcs, fp); }
+  CHECK(verified.has_value());
+  bool threw = false;
+  try { DDMin(sts, true).minimize(77); } catch (const std::invalid_argument&) { threw = true; }   // "Unmodified trace does not trigger violation"
+  CHECK(threw);
+
+  STSSchedMinimizer im(mcs, *verified, fp, LeftToRightOneAtATime(), cfg);
+  auto res = im.minimize();
+  std::printf("internal minimization: %u -> %u deliveries in %u replays\n", im.last.deliveries_before,
+              im.last.deliveries_after, res.first.total_replays);
+  CHECK(im.last.deliveries_after <= im.last.deliveries_before);
+  ReplayScheduler final_check(cfg, res.second, mcs);
+  CHECK(final_check.replay(fp).violation == fp);
+
+  SchedulerConfig pp; pp.model = DEMI_MODEL_PINGPONG3; pp.model_flags = 1 | (2 << 8);
+  DPORwHeuristics dpor(pp, -1, true, 300);
+  threw = false;
+  try { dpor.test({Start(0)}, 7); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  dpor.setMaxMessagesToSchedule(40);
+  ExternalEvents pprog = {Start(0), Start(1), Start(2), Send(2, 1, 0), Send(2, 1, 1), Send(2, 1, 2)};
+  auto hit = dpor.test(pprog, 7);
+  CHECK(hit.has_value() && hit->code == 7);
+  std::printf("DPOR: violation after %u interleavings\nOK\n", dpor.last.interleavings);
+  return 0;
+}

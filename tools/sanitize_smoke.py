@@ -1,0 +1,49 @@
+"""Small invocation of every kernel, meant to run under compute-sanitizer (memcheck / racecheck)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import demi_b200 as D
+from demi_b200 import _native as N
+from oracle import binding as O
+
+for strategy in (0, 1):
+    for model, prog, flags, maxm, iv in ((2, D.raft5_program(client_cmds=2), 1, 50, 5), (1, D.pingpong3_program(20), 0, -1, 0),
+                                         (3, D.bcast32_program(2), 0, 60, 0)):
+        ext = D.pack_externals(prog)
+        for lane in (True, False):
+            if lane:
+                os.environ.pop("DEMI_DISABLE_LANE_ENGINE", None)
+            else:
+                os.environ["DEMI_DISABLE_LANE_ENGINE"] = "1"
+            eng = D.Engine(D.SchedulerConfig(model, model_flags=flags, strategy=strategy))
+            eng.set_externals(ext)
+            g = eng.fuzz_batch(1, 300, maxm, iv, flags=1)
+            c = O.fuzz_batch(model, ext, 1, 300, maxm, iv, model_flags=flags, flags=1, strategy=strategy)
+            assert (g == c).all(), (model, strategy, lane)
+            eng.fuzz_trace(3, maxm, iv)
+            eng.close()
+os.environ.pop("DEMI_DISABLE_LANE_ENGINE", None)
+prog = D.raft5_program(client_cmds=4)
+ext = D.pack_externals(prog)
+res = O.fuzz_batch(2, ext, 1, 3000, 50, 5, model_flags=1)
+seed = 1 + int(np.nonzero(res["violation"])[0][0])
+ev, par, r = O.fuzz_trace(2, ext, seed, 50, 5, model_flags=1)
+code = int(r["violation"])
+eng = D.Engine(D.SchedulerConfig(2, model_flags=1))
+eng.set_trace(ev, ext)
+rng = np.random.default_rng(0)
+masks = (rng.integers(0, 2 ** len(ext), size=400, dtype=np.uint64) & O.full_mask(ext)[0]).reshape(-1, 1)
+for fl in (0, 1, 2):
+    assert (eng.replay_batch(masks, code, fl) == O.replay_batch(2, ev, ext, masks, looking_for=code, flags=fl, model_flags=1)).all()
+mcs, iters, dd = eng.ddmin(code)
+rr, vtrace = eng.replay_trace(O.full_mask(ext), looking_for=code)
+mext = D.pack_externals([e for e in prog if not isinstance(e, D.WaitQuiescence)])
+eng.set_trace(vtrace, mext)
+eng.internal_minimize(code)
+progs = [[D.Start(a) for a in range(5)] + [D.Send(a, 1, 0x1F) for a in range(k)] for k in (2, 3, 5)] * 4
+eng.dpor_batch(progs, 30, 40)
+u, i = eng.dedup_compact(eng.fuzz_batch(1, 5000, 6, 5, flags=1) if eng.set_externals(ext) is None else None, 0)
+print("sanitize smoke ok", len(u))
