@@ -95,7 +95,7 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaMalloc(&h->counters_dev, 2 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 2 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 4 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ovf_count, sizeof(uint32_t));
   if (getenv("DEMI_DISABLE_LANE_ENGINE")) h->use_lane_engine = 0;
   if (e != cudaSuccess) {
@@ -209,7 +209,6 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   uint64_t want = (p->n_prefixes + WARPS - 1) / WARPS;
   uint64_t full = (uint64_t)h->sm_count * (uint64_t)blocks_per_sm;
   int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, full));
-  if (record) grid = 1;
   const uint64_t total_warps = (uint64_t)grid * WARPS;
   const uint32_t node_cap = demi_node_cap(pcap);
 
@@ -392,7 +391,7 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
   CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), h->stream));
   plan.v->fn<<<1, WARPS * 32, plan.smem, h->stream>>>(plan.args);
   cudaError_t e = cudaGetLastError();
-  demi_fuzz_result r{}; uint32_t counts[2] = {0, 0};
+  demi_fuzz_result r{}; uint32_t counts[4] = {0, 0, 0, 0};
   if (e == cudaSuccess) e = cudaMemcpyAsync(&r, res_dev, sizeof(r), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(counts, h->rec_counts_dev, sizeof(counts), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

@@ -140,7 +140,7 @@ static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* 
   a.results = (demi_replay_result*)out_dev;
   a.pending_cap = demi_replay_pending_cap(h->trace_n_send_events);
   a.tosend_cap = demi_tosend_cap(h->trace_n_ext_sends);
-  a.table_slots = demi_pow2_at_least(4 * a.pending_cap, 256, 1u << 16);
+  a.table_slots = demi_pow2_at_least(2 * a.pending_cap, 256, 1u << 16);
   int32_t rc;
   const size_t table_bytes = warps * a.table_slots * 32 * sizeof(uint4);
   const bool fresh_table = h->rp_table_bytes < table_bytes;
@@ -149,9 +149,17 @@ static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* 
   if (flags & DEMI_RF_FILTER_KNOWN_ABSENTS)
     if ((rc = ensure_bytes(h, &h->rp_pruned, &h->rp_pruned_bytes,
                            warps * (a.n_uniq_words + rv->n_actors) * 32 * sizeof(uint32_t))) != DEMI_OK) return rc;
-  (void)fresh_table;
-  // generations restart at 1 every launch: clear the stamps
-  CUDA_TRY(h, cudaMemsetAsync(h->rp_table, 0, table_bytes, s));
+  // Generation stamps: each launch gets a fresh range [gen_base, gen_base + tests per thread]; the table is
+  // cleared only when it was (re)allocated, its geometry changed, or the 16-bit range is exhausted.
+  const uint32_t per_thread = (uint32_t)(((uint64_t)n_masks + (uint64_t)grid * rv->bd - 1) / ((uint64_t)grid * rv->bd)) + 1;
+  const uint64_t geometry = ((uint64_t)a.table_slots << 32) ^ warps;
+  if (fresh_table || h->rp_gen_next == 0 || h->rp_table_geometry != geometry || h->rp_gen_next + per_thread >= 0xFFF0u || record) {
+    CUDA_TRY(h, cudaMemsetAsync(h->rp_table, 0, table_bytes, s));
+    h->rp_gen_next = 1;
+    h->rp_table_geometry = geometry;
+  }
+  a.gen_base = h->rp_gen_next;
+  h->rp_gen_next = record ? 0 : h->rp_gen_next + per_thread;   // the recording variant leaves list entries behind: clear next time
   CUDA_TRY(h, cudaMemsetAsync(h->rp_counters, 0, 2 * sizeof(unsigned long long), s));
   a.table = (uint4*)h->rp_table; a.tosend = (uint32_t*)h->rp_tosend;
   a.pruned = (flags & DEMI_RF_FILTER_KNOWN_ABSENTS) ? (uint32_t*)h->rp_pruned : nullptr;

@@ -29,7 +29,12 @@ dedup_insert_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, unsign
     uint64_t s = dd_slot(key, slots);
     for (;;) {
       unsigned long long prev = atomicCAS(&keys[s], (unsigned long long)DD_EMPTY, (unsigned long long)key);
-      if (prev == DD_EMPTY || prev == key) { atomicMin(&vals[s], (uint32_t)i); break; }
+      if (prev == DD_EMPTY || prev == key) {
+        // the value only ever decreases: a plain (possibly stale, hence larger) read that already shows a
+        // smaller index means this record cannot win, and the second atomic is skipped
+        if (__ldcg(&vals[s]) > (uint32_t)i) atomicMin(&vals[s], (uint32_t)i);
+        break;
+      }
       s = (s + 1) & (slots - 1);
     }
   }

@@ -22,7 +22,18 @@ namespace demi {
 
 constexpr int DPOR_QCAP = 256;
 
-struct DporKey { uint32_t branch, seq, e1, e2, trace_ref, later_i; };
+// One backtrack point = 8 bytes.  Points are enqueued in increasing (interleaving k, later position li,
+// earlier position ei) order, so that triple IS the FIFO sequence number; both racing events are
+// traces[k][li] and traces[k][ei].  Packed so that the larger word leaves the heap first:
+//   branch:12 | ~k:20 | ~li:12 | ~ei:12   (deeper branch first, then oldest first)
+typedef uint64_t DporKey;
+__host__ __device__ __forceinline__ DporKey dpor_key(uint32_t branch, uint32_t k, uint32_t li, uint32_t ei) {
+  return ((uint64_t)branch << 44) | ((uint64_t)(0xFFFFFu - k) << 24) | ((uint64_t)(0xFFFu - li) << 12) | (uint64_t)(0xFFFu - ei);
+}
+__host__ __device__ __forceinline__ uint32_t dpor_key_branch(DporKey q) { return (uint32_t)(q >> 44); }
+__host__ __device__ __forceinline__ uint32_t dpor_key_trace(DporKey q) { return 0xFFFFFu - (uint32_t)((q >> 24) & 0xFFFFFu); }
+__host__ __device__ __forceinline__ uint32_t dpor_key_later(DporKey q) { return 0xFFFu - (uint32_t)((q >> 12) & 0xFFFu); }
+__host__ __device__ __forceinline__ uint32_t dpor_key_earlier(DporKey q) { return 0xFFFu - (uint32_t)(q & 0xFFFu); }
 
 struct DporArgs {
   uint32_t model_flags, blocked_mask; int32_t ignore_timers;
@@ -53,7 +64,7 @@ struct DporMachine {
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
   uint32_t* node_pos; uint32_t* scan;
   uint16_t qlen[NQ];            // local memory (small)
-  uint32_t n_nodes, n_explored, n_heap, seq, n_traces;
+  uint32_t n_nodes, n_explored, n_heap, n_traces;
   uint32_t registry, cancelled, isolated;
   uint32_t parent_event, current_depth, cur_len, next_len, next_pos;
   int32_t nsched;
@@ -140,7 +151,7 @@ struct DporMachine {
 
   // backtrack heap: deeper branch first (DefaultBacktrackOrdering), FIFO among ties
   __device__ __forceinline__ static bool before(const DporKey& a, const DporKey& b) {
-    return a.branch != b.branch ? a.branch > b.branch : a.seq < b.seq;
+    return a > b;
   }
   __device__ __forceinline__ void heap_push(DporKey k) {
     if (n_heap >= A->P.heap_cap) { status = DEMI_DS_HEAP_OVF; return; }
@@ -274,7 +285,7 @@ struct DporMachine {
     const uint32_t ext_lo = A->ext_offsets[sid], ext_hi = A->ext_offsets[sid + 1];
     demi_dpor_result R; memset(&R, 0, sizeof(R));
     n_nodes = 1; nodes[0] = make_uint4(0, 0, 0, 0);
-    n_explored = n_heap = seq = n_traces = 0; status = 0;
+    n_explored = n_heap = n_traces = 0; status = 0;
     next_len = next_pos = 0;
     uint32_t n_viol = 0;
     for (uint32_t i = ext_lo; i < ext_hi; i++) {
@@ -337,26 +348,28 @@ struct DporMachine {
           explored_add(earlier, later);                                           // :1071-1073
           R.races++;
           if (explored_has(later, earlier)) continue;      // it would be skipped when popped (:1156-1160)
-          heap_push(DporKey{branch, seq++, later, earlier, k, li});               // :1134
+          heap_push(dpor_key(branch, k, li, ei));                                 // :1134
         }
       }
       if (status) break;
-      bool have = false; DporKey key;
+      bool have = false; uint32_t kb = 0, kl = 0, e1 = 0, e2 = 0; const uint32_t* kt = nullptr;
       while (n_heap) {                                                            // getNext :1142-1162
-        key = heap_pop();
-        if (explored_has(key.e1, key.e2)) continue;
+        const DporKey key = heap_pop();
+        kt = traces + (size_t)dpor_key_trace(key) * A->T1;
+        kb = dpor_key_branch(key); kl = dpor_key_later(key);
+        e1 = kt[kl]; e2 = kt[dpor_key_earlier(key)];
+        if (explored_has(e1, e2)) continue;
         have = true; break;
       }
       if (!have) { R.exhausted = 1; break; }
-      explored_add(key.e1, key.e2);                                               // :1169-1171
+      explored_add(e1, e2);                                                       // :1169-1171
       if (status) break;
       // nextTrace = trace.take(maxIndex+1) ++ replayThis (:1180, :1060-1063)
       next_len = 0; next_pos = 0;
-      for (uint32_t i = 0; i <= key.branch && i < n; i++) next_trace[next_len++] = cur_trace[i];
-      const uint32_t* kt = traces + (size_t)key.trace_ref * A->T1;
-      for (uint32_t i = key.branch + 1; i <= key.later_i; i++) {
+      for (uint32_t i = 0; i <= kb && i < n; i++) next_trace[next_len++] = cur_trace[i];
+      for (uint32_t i = kb + 1; i <= kl; i++) {
         uint32_t id = kt[i];
-        if (id != key.e2) next_trace[next_len++] = id;
+        if (id != e2) next_trace[next_len++] = id;
       }
     }
     R.violations = n_viol; R.n_nodes = n_nodes; R.n_explored = n_explored; R.heap_left = n_heap; R.status = status;

@@ -52,7 +52,7 @@ struct demi_handle {
   void* trace_dev = nullptr; void* trace_ext_dev = nullptr;
   uint16_t* ev_ordinal_dev = nullptr; uint16_t* send_ext_index_dev = nullptr;
   uint32_t trace_n_uniq = 0, trace_n_send_events = 0, trace_n_ext_sends = 0;
-  void* rp_table = nullptr; size_t rp_table_bytes = 0;
+  void* rp_table = nullptr; size_t rp_table_bytes = 0; uint32_t rp_gen_next = 0; uint64_t rp_table_geometry = 0;
   void* rp_tosend = nullptr; size_t rp_tosend_bytes = 0;
   void* rp_pruned = nullptr; size_t rp_pruned_bytes = 0;
   void* rp_masks = nullptr; size_t rp_masks_bytes = 0;

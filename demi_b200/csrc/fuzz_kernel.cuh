@@ -36,13 +36,15 @@ fuzz_kernel(const __grid_constant__ KernelArgs args) {
   for (uint64_t it = gw; it < count; it += total_warps) {
     const uint64_t idx = args.index_list ? (uint64_t)args.index_list[it] : it;
     demi_fuzz_result r;
+    if (RECORD) m.rec_ev = args.rec_events + it * (uint64_t)args.rec_cap;
     m.run(args.seed_base + (int64_t)idx, r);
     const bool retry = args.ovf_list && (r.status == DEMI_PS_PENDING_OVF || r.status == DEMI_PS_NODE_OVF);
     if (retry) {
       if (lane == 0) { uint32_t pos = atomicAdd(args.ovf_count, 1u); args.ovf_list[pos] = (uint32_t)idx; }
     } else {
       if (lane == 0) {
-        uint4* dst = reinterpret_cast<uint4*>(args.results + idx);
+        // recording launches number their outputs by work-list position, batches by prefix index
+        uint4* dst = reinterpret_cast<uint4*>(args.results + (RECORD ? it : idx));
         dst[0] = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
         dst[1] = make_uint4((uint32_t)r.trace_hash, (uint32_t)(r.trace_hash >> 32),
                             (uint32_t)r.n_nodes | ((uint32_t)r.n_events << 16),
@@ -54,10 +56,15 @@ fuzz_kernel(const __grid_constant__ KernelArgs args) {
     if (RECORD) {
       // single-prefix launch: export counts and the DepTracker tree (DepTracker.scala:111-116)
       __syncwarp();
-      if (lane == 0) { args.rec_counts[0] = m.n_events; args.rec_counts[1] = m.n_nodes; }
+      if (lane == 0) {
+        uint32_t* c = args.rec_counts + it * 4;
+        c[0] = m.n_events; c[1] = m.n_nodes; c[3] = r.violation;
+        // ViolationFingerprint.affectedNodes of the violation the execution stopped on
+        c[2] = (r.status == 0 && r.violation) ? MODEL::affected(m.sm->states, args.model_flags, r.violation) : 0u;
+      }
       if (args.rec_parent)
         for (uint32_t i = lane; i < m.n_nodes && i < args.rec_parent_cap; i += 32)
-          args.rec_parent[i] = (uint16_t)__ldcg(&m.nodes_g[i]).w;
+          args.rec_parent[it * (uint64_t)args.rec_parent_cap + i] = (uint16_t)__ldcg(&m.nodes_g[i]).w;
     }
   }
   if (lane == 0 && args.sum_steps && (my_steps | my_viol)) {

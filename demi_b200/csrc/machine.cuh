@@ -149,7 +149,8 @@ struct KernelArgs {
   // scratch
   uint4*    node_scratch;     // [total_warps][node_cap]
   uint4*    pend_scratch;     // [total_warps][pending_cap] when the pending set lives in HBM
-  // recording (single-prefix launches)
+  // recording launches: slot `it` (the position in the launch's work list) owns rec_events[it*rec_cap ..),
+  // rec_counts[it*4 ..) = {n_events, n_nodes, affectedNodes, violation} and rec_parent[it*rec_parent_cap ..)
   demi_event* rec_events; uint32_t rec_cap; uint32_t* rec_counts; uint16_t* rec_parent; uint32_t rec_parent_cap;
   // summary counters
   unsigned long long* sum_steps; unsigned long long* n_violations;
@@ -179,6 +180,7 @@ struct Machine {
   Smem* sm;
   uint4* pend_g;            // PEND_GLOBAL
   uint4* nodes_g;           // dep-tree node table {hdr,p0,p1,parent}
+  demi_event* rec_ev;       // RECORD: this execution's EventTrace slot
   const KernelArgs* A;
   uint32_t lane;
 
@@ -227,7 +229,7 @@ struct Machine {
     thash += demi_event_term(w0, p0, p1, w3, n_events, parent);
     if (RECORD) {
       if (n_events >= A->rec_cap) { status = DEMI_PS_EVENT_OVF; return; }
-      if (lane == 0) reinterpret_cast<uint4*>(A->rec_events)[n_events] = make_uint4(w0, p0, p1, w3);
+      if (lane == 0) reinterpret_cast<uint4*>(rec_ev)[n_events] = make_uint4(w0, p0, p1, w3);
     }
     n_events++;
   }

@@ -61,6 +61,8 @@ struct PingPong3 {
     if (lane == 0 && (flags & 1u) && states[1] >= (flags >> 8)) return 7;
     return 0;
   }
+  // ViolationFingerprint.affectedNodes (TestOracle.scala:9-18) as an actor bitmask
+  __device__ static uint32_t affected(const uint32_t*, uint32_t, uint32_t code) { return code == 7 ? 1u : 0u; }
 };
 
 // -------------------------------------------------------------------- raft5
@@ -241,6 +243,21 @@ struct Raft5 {
       if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) return 2;
     return 0;
   }
+  // affectedNodes: the first pair, in (i, j) order, that witnesses `code`
+  __device__ static uint32_t affected(const uint32_t* states, uint32_t, uint32_t code) {
+    for (uint32_t i = 0; i < 5; i++)
+      for (uint32_t j = i + 1; j < 5; j++) {
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(states + i * STATE_WORDS);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(states + j * STATE_WORDS);
+        if (code == 1 && a[ROLE] == LEADER && b[ROLE] == LEADER && a[TERM] == b[TERM]) return (1u << i) | (1u << j);
+        if (code == 2) {
+          uint32_t c = a[COMMIT] < b[COMMIT] ? a[COMMIT] : b[COMMIT];
+          for (uint32_t k = 0; k < c; k++)
+            if (a[LOGTERM + k] != b[LOGTERM + k] || a[LOGVAL + k] != b[LOGVAL + k]) return (1u << i) | (1u << j);
+        }
+      }
+    return 0;
+  }
   template <class A>
   __device__ static __forceinline__ uint32_t invariant(A all, uint32_t) {
     uint32_t code = 0;
@@ -295,6 +312,11 @@ struct Bcast32 {
   __device__ static __forceinline__ uint32_t invariant_lane(const uint32_t* states, uint32_t flags, uint32_t lane) {
     if (!flags) return 0;
     return states[lane * 2] >= flags ? 3u : 0u;
+  }
+  __device__ static uint32_t affected(const uint32_t* states, uint32_t flags, uint32_t code) {
+    if (code != 3 || !flags) return 0;
+    for (uint32_t a = 0; a < 32; a++) if (states[a * 2] >= flags) return 1u << a;
+    return 0;
   }
 };
 

@@ -42,6 +42,7 @@ struct ReplayArgs {
   demi_event* rec_events; uint32_t rec_cap; uint32_t* rec_count;
   // capacities
   uint32_t pending_cap, tosend_cap, table_slots; // table_slots: power of two >= 2*pending_cap
+  uint32_t gen_base;                             // first hash-table generation this launch may use (1..0xFFFE)
   // per-warp scratch in HBM
   uint4*    table;      // [warps][table_slots][32]
   uint32_t* tosend;     // [warps][tosend_cap][32]
@@ -367,10 +368,12 @@ replay_lane_kernel(const __grid_constant__ ReplayArgs args) {
   m.pruned = args.pruned ? args.pruned + gwarp * (uint64_t)(args.n_uniq_words + M::N) * 32 + lane : nullptr;
 
   unsigned long long my_repro = 0, my_deliv = 0;
-  uint32_t generation = 0;
+  // generations continue across launches (the host hands out disjoint ranges), so the table needs no
+  // clearing between launches; on wrap-around this thread clears its own slots
+  uint32_t generation = args.gen_base - 1;
   for (uint64_t idx = gthread; idx < args.n_masks; idx += total) {
     generation++;
-    if (generation == 0xFFFFu) {       // generation wrap: clear this thread's table
+    if (generation >= 0xFFFFu) {
       for (uint32_t s = 0; s < args.table_slots; s++) m.table[(size_t)s * 32] = make_uint4(0, 0, 0, 0);
       generation = 1;
     }

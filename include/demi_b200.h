@@ -338,6 +338,39 @@ int32_t demi_dedup_compact_dev(demi_handle* h, const void* results_dev, uint64_t
 int32_t demi_dedup_compact(demi_handle* h, const demi_fuzz_result* results, uint64_t n, int32_t mode,
                            demi_fuzz_result* out_records, uint32_t* out_index, uint64_t* out_count);
 
+/* ------------------------------------------------------ provenance pruning */
+/* ProvenanceTracker.pruneConcurrentEvents (schedulers/Util.scala:267-376; called from RunnerUtils.fuzz,
+ * RunnerUtils.scala:138-163): drop the deliveries that are not in the happens-before past of the violation.
+ * `initialTrace` is DepTracker.initialTrace (DepTracker.scala:63, :126-129): position 0 is the root event,
+ * position t >= 1 the t-th delivered Unique.  Bit t of the keep mask says position t stays in the filtered
+ * queue.  happens-before is the reflexive-transitive closure of "earlier delivery on the same receiver" and
+ * "delivery -> message created by it" (Util.scala:289-304); position t stays iff it happens before the last
+ * delivery on some affected node and that delivery does not happen before it (Util.scala:367-374, as
+ * written: a last delivery itself only stays if it precedes another one). 32 bytes. */
+typedef struct demi_provenance_out {
+  uint32_t status;          /* DEMI_PV_*                                                        */
+  uint32_t violation;       /* the violation code of the execution (demi_fuzz_provenance only)  */
+  uint32_t affected_mask;   /* ViolationFingerprint.affectedNodes (TestOracle.scala:9-18)       */
+  uint32_t n_trace;         /* initialTrace length, root included                               */
+  uint32_t n_kept;          /* length of the filtered queue                                     */
+  uint32_t reserved[3];
+} demi_provenance_out;
+#define DEMI_PV_OK 0
+#define DEMI_PV_CYCLE 1          /* the relation is cyclic: Util.topologicalSort's sys.error (Util.scala:506) */
+#define DEMI_PV_OVERFLOW 2       /* trace longer than the mask, or a node id outside the tree                */
+#define DEMI_PV_PREFIX_FAILED 3  /* the execution itself ended with a DEMI_PS_* capacity status             */
+/* One recorded execution (events + DepTracker tree as returned by demi_fuzz_trace) and the violation's
+ * affected actors. keep_mask: mask_words uint64 words, mask_words*64 >= initialTrace length. */
+int32_t demi_provenance(demi_handle* h, const demi_event* events, uint32_t n_events,
+                        const uint16_t* dep_parent, uint32_t n_nodes, uint32_t affected_mask,
+                        uint64_t* keep_mask, uint32_t mask_words, demi_provenance_out* out);
+/* The post-fuzz step on a whole batch: re-execute prefixes seed_base + prefix_index[i] (the violating ones a
+ * fuzz batch reported) in recording mode, take affectedNodes from the model's invariant on the final states
+ * and prune.  keep_masks: n x mask_words uint64, out: n records; results (may be NULL): the n result records. */
+int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* p, const uint32_t* prefix_index, uint32_t n,
+                             uint64_t* keep_masks, uint32_t mask_words, demi_provenance_out* out,
+                             demi_fuzz_result* results);
+
 /* ------------------------------------------------------------- statistics */
 int32_t demi_stats(const demi_handle* h, demi_perf* out);
 

@@ -40,6 +40,8 @@ typedef struct oracle_model {
   void (*receive)(om_machine* m, int self, uint32_t* st, const demi_msg* msg);
   /* TestOracle.Invariant (minification/TestOracle.scala:27) on actor states */
   uint32_t (*invariant)(const uint32_t* states, uint32_t flags);
+  /* ViolationFingerprint.affectedNodes (TestOracle.scala:9-18) as an actor bitmask */
+  uint32_t (*affected)(const uint32_t* states, uint32_t flags, uint32_t code);
 } oracle_model;
 
 const oracle_model* oracle_get_model(int id);

@@ -34,6 +34,12 @@ static uint32_t pp_invariant(const uint32_t* st, uint32_t flags) {
   return 0;
 }
 
+/* ViolationFingerprint.affectedNodes (TestOracle.scala:9-18): the actors the violation was observed on */
+static uint32_t pp_affected(const uint32_t* st, uint32_t flags, uint32_t code) {
+  (void)st; (void)flags;
+  return code == 7 ? 1u : 0u;
+}
+
 /* ================================================================= raft5 */
 /* 5-node Raft (Ongaro & Ousterhout, "In Search of an Understandable Consensus
  * Algorithm", Figure 2), tick-driven timers, log capacity 8, one entry per
@@ -214,6 +220,24 @@ static uint32_t raft_invariant(const uint32_t* st, uint32_t flags) {
   return 0;
 }
 
+/* the first pair, in (i, j) order, that witnesses `code` */
+static uint32_t raft_affected(const uint32_t* st, uint32_t flags, uint32_t code) {
+  (void)flags;
+  for (int i = 0; i < RAFT_N; i++)
+    for (int j = i + 1; j < RAFT_N; j++) {
+      const uint8_t* a = (const uint8_t*)&st[i * 10];
+      const uint8_t* b = (const uint8_t*)&st[j * 10];
+      if (code == 1 && a[R_ROLE] == ROLE_LEADER && b[R_ROLE] == ROLE_LEADER && a[R_TERM] == b[R_TERM])
+        return (1u << i) | (1u << j);
+      if (code == 2) {
+        uint32_t c = a[R_COMMIT] < b[R_COMMIT] ? a[R_COMMIT] : b[R_COMMIT];
+        for (uint32_t k = 0; k < c; k++)
+          if (a[R_LOGTERM + k] != b[R_LOGTERM + k] || a[R_LOGVAL + k] != b[R_LOGVAL + k]) return (1u << i) | (1u << j);
+      }
+    }
+  return 0;
+}
+
 /* =============================================================== bcast32 */
 /* BASELINE.json configs[4]: 32-actor broadcast storm.  Flood(ttl) => count++,
  * remember the largest ttl seen, re-broadcast Flood(ttl-1) to all 31 peers
@@ -235,10 +259,16 @@ static uint32_t bc_invariant(const uint32_t* st, uint32_t flags) {
   return 0;
 }
 
+static uint32_t bc_affected(const uint32_t* st, uint32_t flags, uint32_t code) {
+  if (code != 3 || !flags) return 0;
+  for (int a = 0; a < 32; a++) if (st[a * 2] >= flags) return 1u << a;
+  return 0;
+}
+
 static const oracle_model MODELS[] = {
-  { DEMI_MODEL_PINGPONG3, 3, 2, pp_init, pp_receive, pp_invariant },
-  { DEMI_MODEL_RAFT5, 5, 10, raft_init, raft_receive, raft_invariant },
-  { DEMI_MODEL_BCAST32, 32, 2, bc_init, bc_receive, bc_invariant },
+  { DEMI_MODEL_PINGPONG3, 3, 2, pp_init, pp_receive, pp_invariant, pp_affected },
+  { DEMI_MODEL_RAFT5, 5, 10, raft_init, raft_receive, raft_invariant, raft_affected },
+  { DEMI_MODEL_BCAST32, 32, 2, bc_init, bc_receive, bc_invariant, bc_affected },
 };
 const oracle_model* oracle_get_model(int id) {
   for (unsigned i = 0; i < sizeof(MODELS) / sizeof(MODELS[0]); i++)

@@ -102,7 +102,7 @@ def config3_dpor():
     """Independent DPORwHeuristics searches (depth 100), one per external subsequence."""
     rng = np.random.default_rng(7)
     progs = []
-    for _ in range(4096):
+    for _ in range(int(os.environ.get("DEMI_C3_SEARCHES", "32768"))):
         ev = [D.Start(int(a)) for a in rng.permutation(5)]
         ev += [D.Send(int(a), 1, 0x1F) for a in rng.permutation(5)[:int(rng.integers(3, 6))]]
         ev += [D.Send(int(rng.integers(0, 5)), 2, int(rng.integers(1, 50))) for _ in range(int(rng.integers(0, 3)))]
