@@ -75,6 +75,10 @@ assert REPLAY_DTYPE.itemsize == 16
 assert EXT_DTYPE.itemsize == 16 and EVENT_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 32
 
 # every symbol include/demi_b200.h declares
+PROVENANCE_DTYPE = np.dtype([("status", "<u4"), ("violation", "<u4"), ("affected_mask", "<u4"), ("n_trace", "<u4"),
+                             ("n_kept", "<u4"), ("reserved", "<u4", (3,))])
+PV_OK, PV_CYCLE, PV_OVERFLOW, PV_PREFIX_FAILED = 0, 1, 2, 3
+
 EXPORTS = [
     "demi_version", "demi_last_error", "demi_device_count", "demi_create", "demi_destroy",
     "demi_set_externals", "demi_fuzz_batch", "demi_fuzz_batch_dev", "demi_fuzz_summary_dev",
@@ -82,6 +86,7 @@ EXPORTS = [
     "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin", "demi_dpor_batch",
     "demi_dedup_compact_dev", "demi_dedup_compact",
     "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
+    "demi_provenance", "demi_fuzz_provenance",
 ]
 
 _lib = None
@@ -137,6 +142,10 @@ def lib():
                                     C.POINTER(C.c_uint32), vp]
     L.demi_internal_minimize.restype = C.c_int32
     L.demi_internal_minimize.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(IntMinOut)]
+    L.demi_provenance.restype = C.c_int32
+    L.demi_provenance.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp]
+    L.demi_fuzz_provenance.restype = C.c_int32
+    L.demi_fuzz_provenance.argtypes = [vp, C.POINTER(FuzzParams), vp, C.c_uint32, vp, C.c_uint32, vp, vp]
     L.demi_dpor_batch.restype = C.c_int32
     L.demi_dpor_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), vp, vp, C.c_uint32, vp, C.c_uint32]
     L.demi_stats.restype = C.c_int32

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "fuzz_kernel.cuh"
+#include "provenance_kernel.cuh"
 #include "lane_kernel.cuh"
 
 using namespace demi;
@@ -111,7 +112,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
-  cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev);
+  cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev); cudaFree(h->prov_scratch);
   cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count); cudaFree(h->fifo_scratch);
   demi_replay_free(h);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
@@ -406,6 +407,128 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
   if (n_nodes) *n_nodes = counts[1];
   if (result) *result = r;
   if (r.status) return fail(h, DEMI_ERR_CAPACITY, "demi_fuzz_trace: prefix status %u", (unsigned)r.status);
+  return DEMI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Provenance pruning (ProvenanceTracker, schedulers/Util.scala:267-376)
+static int32_t launch_provenance(demi_handle* h, ProvArgs a, cudaStream_t s) {
+  constexpr int PW = 4;
+  const uint64_t want = ((uint64_t)a.n + PW - 1) / PW;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * 8));
+  a.t_cap = a.mask_words * 64;
+  a.scratch_stride = a.t_cap + 3 * a.par_stride;
+  int32_t rc = ensure(h, (void**)&h->prov_scratch, &h->prov_scratch_bytes,
+                      (uint64_t)grid * PW * a.scratch_stride * sizeof(uint32_t));
+  if (rc != DEMI_OK) return rc;
+  a.scratch = (uint32_t*)h->prov_scratch;
+  provenance_kernel<PW><<<grid, PW * 32, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->perf.kernel_launches++;
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_provenance(demi_handle* h, const demi_event* events, uint32_t n_events,
+                                   const uint16_t* dep_parent, uint32_t n_nodes, uint32_t affected_mask,
+                                   uint64_t* keep_mask, uint32_t mask_words, demi_provenance_out* out) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!events || !dep_parent || !keep_mask || !out || !mask_words || !n_nodes)
+    return fail(h, DEMI_ERR_INVALID, "demi_provenance: events, dep_parent, keep_mask and out are required");
+  if (n_nodes > 65536) return fail(h, DEMI_ERR_INVALID, "demi_provenance: node ids are 16-bit");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t ev_b = (size_t)std::max(n_events, 1u) * sizeof(demi_event), par_b = (size_t)n_nodes * 2;
+  const size_t keep_b = (size_t)mask_words * 8;
+  unsigned char* buf = nullptr;                      // events | parents | counts | keep | out
+  const size_t o_par = (ev_b + 15) & ~(size_t)15, o_cnt = (o_par + par_b + 15) & ~(size_t)15, o_keep = o_cnt + 16,
+               o_out = o_keep + ((keep_b + 15) & ~(size_t)15), total = o_out + sizeof(demi_provenance_out);
+  CUDA_TRY(h, cudaMalloc(&buf, total));
+  const uint32_t counts[4] = {n_events, n_nodes, affected_mask, 0};
+  cudaError_t e = cudaMemcpyAsync(buf, events, (size_t)n_events * sizeof(demi_event), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_par, dep_parent, par_b, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + o_cnt, counts, sizeof(counts), cudaMemcpyHostToDevice, h->stream);
+  int32_t rc = DEMI_OK;
+  if (e == cudaSuccess) {
+    ProvArgs a{};
+    a.events = (const demi_event*)buf; a.ev_stride = std::max(n_events, 1u);
+    a.parent = (const uint16_t*)(buf + o_par); a.par_stride = n_nodes;
+    a.counts = (const uint32_t*)(buf + o_cnt); a.results = nullptr;
+    a.keep = (uint64_t*)(buf + o_keep); a.mask_words = mask_words;
+    a.out = (demi_provenance_out*)(buf + o_out); a.n = 1;
+    rc = launch_provenance(h, a, h->stream);
+  }
+  if (rc == DEMI_OK && e == cudaSuccess) e = cudaMemcpyAsync(keep_mask, buf + o_keep, keep_b, cudaMemcpyDeviceToHost, h->stream);
+  if (rc == DEMI_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, buf + o_out, sizeof(*out), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (rc != DEMI_OK) return rc;
+  if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_provenance: %s", cudaGetErrorString(e));
+  return DEMI_OK;
+}
+
+extern "C" int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* p, const uint32_t* prefix_index, uint32_t n,
+                                        uint64_t* keep_masks, uint32_t mask_words, demi_provenance_out* out,
+                                        demi_fuzz_result* results) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (!p) return fail(h, DEMI_ERR_INVALID, "null params");
+  if (!n) return DEMI_OK;
+  if (!prefix_index || !keep_masks || !out || !mask_words)
+    return fail(h, DEMI_ERR_INVALID, "demi_fuzz_provenance: prefix_index, keep_masks and out are required");
+  if (p->max_messages < 0 || (uint64_t)p->max_messages + 2 > (uint64_t)mask_words * 64)
+    return fail(h, DEMI_ERR_INVALID, "demi_fuzz_provenance: mask_words*64 must cover max_messages + 2 positions");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  demi_fuzz_params q = *p;
+  q.n_prefixes = n;
+  LaunchPlan plan;
+  int32_t rc = plan_launch(h, &q, true, &plan);
+  if (rc != DEMI_OK) return rc;
+  // an execution records at most one MsgSend + one MsgEvent per message, plus the external markers
+  const uint32_t node_cap = plan.args.node_cap;
+  const uint32_t ev_cap = 2 * node_cap + 2 * plan.args.n_ext + 16;
+  const size_t b_ev = (size_t)n * ev_cap * sizeof(demi_event), b_par = (((size_t)n * node_cap * 2) + 15) & ~(size_t)15,
+               b_cnt = (size_t)n * 16, b_res = (size_t)n * sizeof(demi_fuzz_result), b_idx = (((size_t)n * 4) + 15) & ~(size_t)15,
+               b_keep = (size_t)n * mask_words * 8, b_out = (size_t)n * sizeof(demi_provenance_out);
+  unsigned char* buf = nullptr;
+  CUDA_TRY(h, cudaMalloc(&buf, b_ev + b_par + b_cnt + b_res + b_idx + 16 + b_keep + b_out));
+  unsigned char* d_par = buf + b_ev; unsigned char* d_cnt = d_par + b_par; unsigned char* d_res = d_cnt + b_cnt;
+  unsigned char* d_idx = d_res + b_res; unsigned char* d_n = d_idx + b_idx; unsigned char* d_keep = d_n + 16;
+  unsigned char* d_out = d_keep + b_keep;
+  cudaStream_t s = h->stream;
+  cudaError_t e = cudaMemcpyAsync(d_idx, prefix_index, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, b_cnt, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0xFF, b_res, s);
+  if (e == cudaSuccess) {
+    plan.args.results = (demi_fuzz_result*)d_res;
+    plan.args.index_list = (const uint32_t*)d_idx; plan.args.index_count = (const uint32_t*)d_n;
+    plan.args.rec_events = (demi_event*)buf; plan.args.rec_cap = ev_cap;
+    plan.args.rec_counts = (uint32_t*)d_cnt;
+    plan.args.rec_parent = (uint16_t*)d_par; plan.args.rec_parent_cap = node_cap;
+    plan.args.sum_steps = nullptr; plan.args.n_violations = nullptr;
+    cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, s);
+    plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
+    e = cudaGetLastError();
+    h->perf.kernel_launches++;
+    if (e == cudaSuccess) {
+      ProvArgs a{};
+      a.events = (const demi_event*)buf; a.ev_stride = ev_cap;
+      a.parent = (const uint16_t*)d_par; a.par_stride = node_cap;
+      a.counts = (const uint32_t*)d_cnt; a.results = (const demi_fuzz_result*)d_res;
+      a.keep = (uint64_t*)d_keep; a.mask_words = mask_words; a.out = (demi_provenance_out*)d_out; a.n = n;
+      rc = launch_provenance(h, a, s);
+    }
+    cudaEventRecord(t1, s);
+    if (rc == DEMI_OK && e == cudaSuccess) e = cudaMemcpyAsync(keep_masks, d_keep, b_keep, cudaMemcpyDeviceToHost, s);
+    if (rc == DEMI_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, s);
+    if (rc == DEMI_OK && e == cudaSuccess && results) e = cudaMemcpyAsync(results, d_res, b_res, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) h->perf.kernel_ms = ms;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+  }
+  cudaFree(buf);
+  if (rc != DEMI_OK) return rc;
+  if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_fuzz_provenance: %s", cudaGetErrorString(e));
   return DEMI_OK;
 }
 

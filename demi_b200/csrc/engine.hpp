@@ -40,6 +40,7 @@ struct demi_handle {
   uint16_t* fifo_scratch = nullptr; size_t fifo_scratch_bytes = 0;
   int use_lane_engine = 1;
   uint32_t* rec_counts_dev = nullptr;
+  void* prov_scratch = nullptr; size_t prov_scratch_bytes = 0;
   // pinned staging for host transfers
   void* pinned = nullptr; size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;

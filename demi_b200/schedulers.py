@@ -93,6 +93,32 @@ class Engine(object):
                                             par.ctypes.data, cap_nodes, C.byref(nn), res.ctypes.data))
         return ev[:ne.value].copy(), par[:nn.value].copy(), res[0]
 
+    # ---- provenance pruning (ProvenanceTracker, schedulers/Util.scala:267-376)
+    def provenance(self, events, dep_parent, affected_mask, mask_words=None):
+        """pruneConcurrentEvents on one recorded execution: (keep mask over initialTrace positions, out record)."""
+        ev = np.ascontiguousarray(events, dtype=N.EVENT_DTYPE)
+        par = np.ascontiguousarray(dep_parent, dtype=np.uint16)
+        if mask_words is None:
+            mask_words = max(1, (int((ev["kind"] == N.EV_MSG_EVENT).sum()) + 1 + 63) // 64)
+        keep = np.zeros(mask_words, dtype=np.uint64)
+        out = np.zeros(1, dtype=N.PROVENANCE_DTYPE)
+        self._check(N.lib().demi_provenance(self._h, ev.ctypes.data, len(ev), par.ctypes.data, len(par),
+                                            int(affected_mask), keep.ctypes.data, mask_words, out.ctypes.data))
+        return keep, out[0]
+
+    def fuzz_provenance(self, seed_base, prefix_index, max_messages, interval, looking_for=0, mask_words=None):
+        """The post-fuzz pruning step on prefixes seed_base + prefix_index[i] (RunnerUtils.scala:138-163)."""
+        idx = np.ascontiguousarray(prefix_index, dtype=np.uint32)
+        if mask_words is None:
+            mask_words = max(1, (max_messages + 2 + 63) // 64)
+        p = N.FuzzParams(seed_base, len(idx), max_messages, interval, looking_for or 0, 0)
+        keep = np.zeros((len(idx), mask_words), dtype=np.uint64)
+        out = np.zeros(len(idx), dtype=N.PROVENANCE_DTYPE)
+        res = np.zeros(len(idx), dtype=N.RESULT_DTYPE)
+        self._check(N.lib().demi_fuzz_provenance(self._h, C.byref(p), idx.ctypes.data, len(idx), keep.ctypes.data,
+                                                 mask_words, out.ctypes.data, res.ctypes.data))
+        return keep, out, res
+
     # ---- STSSched replay / DDMin
     def set_trace(self, events, externals):
         ev = np.ascontiguousarray(events, dtype=N.EVENT_DTYPE)
@@ -358,6 +384,28 @@ class DDMin(object):
 
     def verify_mcs(self, mcs, violation_fingerprint):
         return self.oracle.test(mcs, violation_fingerprint)
+
+
+class ProvenanceTracker:
+    """ProvenanceTracker(trace, depGraph) (schedulers/Util.scala:267-376).  `trace` / `dep_parent` are the recorded
+    EventTrace and DepTracker tree of one execution (Engine.fuzz_trace)."""
+
+    def __init__(self, engine, trace, dep_parent):
+        self.engine, self.trace, self.dep_parent = engine, np.asarray(trace, dtype=N.EVENT_DTYPE), dep_parent
+        self.last = None
+
+    def prune_concurrent_events(self, affected_nodes):
+        """pruneConcurrentEvents(violation): indices into `trace` of the deliveries that stay.  The root event is
+        dropped here, as EventTrace.intersection does afterwards (EventTrace.scala:127-131)."""
+        delivery_index = np.nonzero(self.trace["kind"] == N.EV_MSG_EVENT)[0]
+        keep, out = self.engine.provenance(self.trace, self.dep_parent, affected_nodes)
+        self.last = out
+        if out["status"] == N.PV_CYCLE:
+            raise RuntimeError("happens-before relation is cyclic")            # Util.topologicalSort, Util.scala:506
+        if out["status"]:
+            raise RuntimeError("provenance: trace does not fit (status %d)" % out["status"])
+        bits = np.unpackbits(keep.view(np.uint8), bitorder="little")[1:len(delivery_index) + 1].astype(bool)
+        return delivery_index[bits]
 
 
 class DPORwHeuristics(object):

@@ -131,8 +131,16 @@ class RandomScheduler {
       EventTrace ev(65536);
       uint32_t n_ev = 0, n_nodes = 0;
       demi_fuzz_result r{};
-      engine->check(demi_fuzz_trace(engine->handle(), &p, seed + i, ev.data(), (uint32_t)ev.size(), &n_ev, nullptr, 0, &n_nodes, &r));
-      ev.resize(n_ev);
+      depGraph.assign(65536, 0);
+      engine->check(demi_fuzz_trace(engine->handle(), &p, seed + i, ev.data(), (uint32_t)ev.size(), &n_ev,
+                                    depGraph.data(), (uint32_t)depGraph.size(), &n_nodes, &r));
+      ev.resize(n_ev); depGraph.resize(n_nodes);
+      // ViolationFingerprint.affectedNodes of the execution found (TestOracle.scala:9-18)
+      uint32_t which = i; uint64_t keep[32]; demi_provenance_out po{};
+      if (maxMessages >= 0 && maxMessages + 2 <= 32 * 64) {
+        engine->check(demi_fuzz_provenance(engine->handle(), &p, &which, 1, keep, 32, &po, nullptr));
+        affectedNodes = po.affected_mask;
+      }
       return std::make_pair(ev, r.violation);
     }
     return std::nullopt;
@@ -146,6 +154,8 @@ class RandomScheduler {
   }
   std::shared_ptr<Engine> engine;
   std::vector<demi_fuzz_result> results;
+  std::vector<uint16_t> depGraph;      // depTracker.getGraph of the violating execution, as parent pointers
+  uint32_t affectedNodes = 0;          // ... and its fingerprint's affectedNodes
  private:
   uint32_t max_executions; int32_t invariant_check_interval; int64_t seed;
   int32_t maxMessages = -1;                                           // Int.MaxValue (:54)
@@ -250,6 +260,35 @@ class STSSchedMinimizer {
   demi_intmin_out last{};
  private:
   std::shared_ptr<Engine> engine; ExternalEvents mcs; EventTrace verified_mcs; ViolationFingerprint violation; uint32_t flags;
+};
+
+// ProvenanceTracker(trace, depGraph) (schedulers/Util.scala:267-376): `trace` is the recorded EventTrace of an
+// execution, `dep_parent` its DepTracker tree, both as returned by demi_fuzz_trace.
+class ProvenanceTracker {
+ public:
+  ProvenanceTracker(std::shared_ptr<Engine> e, EventTrace trace, std::vector<uint16_t> dep_parent)
+      : engine(std::move(e)), trace(std::move(trace)), dep_parent(std::move(dep_parent)) {}
+  // pruneConcurrentEvents(violation): the deliveries of `trace` (by index into it) that stay; the root event,
+  // which the reference filters out afterwards (EventTrace.intersection, EventTrace.scala:127-131), is not listed
+  std::vector<uint32_t> pruneConcurrentEvents(uint32_t affectedNodes) {
+    std::vector<uint32_t> delivery_index;
+    for (uint32_t i = 0; i < trace.size(); i++) if (trace[i].kind == DEMI_EV_MSG_EVENT) delivery_index.push_back(i);
+    const uint32_t words = (uint32_t)((delivery_index.size() + 1 + 63) / 64);
+    std::vector<uint64_t> keep(words, 0);
+    engine->check(demi_provenance(engine->handle(), trace.data(), (uint32_t)trace.size(), dep_parent.data(),
+                                  (uint32_t)dep_parent.size(), affectedNodes, keep.data(), words, &last));
+    if (last.status == DEMI_PV_CYCLE) throw std::runtime_error("happens-before relation is cyclic");   // Util.scala:506
+    if (last.status) throw Error(DEMI_ERR_CAPACITY, "provenance: trace does not fit");
+    std::vector<uint32_t> kept;
+    for (uint32_t t = 1; t <= delivery_index.size(); t++)
+      if ((keep[t >> 6] >> (t & 63)) & 1ull) kept.push_back(delivery_index[t - 1]);
+    return kept;
+  }
+  demi_provenance_out last{};
+ private:
+  std::shared_ptr<Engine> engine;
+  EventTrace trace;
+  std::vector<uint16_t> dep_parent;
 };
 
 class DPORwHeuristics {

@@ -244,3 +244,31 @@ def internal_minimize(model, verified, mcs_ext, looking_for, flags=0, model_flag
                                         C.byref(total), C.c_void_p(sizes.ctypes.data), C.c_uint32(cap), C.byref(n_sizes),
                                         C.byref(unig))
     return rc, out[:n_out.value].copy(), total.value, sizes[:n_sizes.value].copy(), unig.value
+
+
+PROVENANCE_DTYPE = np.dtype([("status", "<u4"), ("violation", "<u4"), ("affected_mask", "<u4"), ("n_trace", "<u4"),
+                             ("n_kept", "<u4"), ("reserved", "<u4", (3,))])
+
+
+def provenance(events, dep_parent, affected_mask, mask_words):
+    """ProvenanceTracker.pruneConcurrentEvents, literal restatement (oracle/provenance.c)."""
+    ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    par = np.ascontiguousarray(dep_parent, dtype=np.uint16)
+    keep = np.zeros(mask_words, dtype=np.uint64)
+    out = np.zeros(1, dtype=PROVENANCE_DTYPE)
+    lib().oracle_provenance(C.c_void_p(ev.ctypes.data), C.c_uint32(len(ev)), C.c_void_p(par.ctypes.data),
+                            C.c_uint32(len(par)), C.c_uint32(affected_mask), C.c_void_p(keep.ctypes.data),
+                            C.c_uint32(mask_words), C.c_void_p(out.ctypes.data))
+    return keep, out[0]
+
+
+def fuzz_provenance(model, ext, seed, max_messages, interval, mask_words, model_flags=0, looking_for=0, strategy=0):
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    cfg = Config(0, model, model_flags, 0, 0, strategy)
+    p = FuzzParams(seed, 1, max_messages, interval, looking_for, 0)
+    keep = np.zeros(mask_words, dtype=np.uint64)
+    out = np.zeros(1, dtype=PROVENANCE_DTYPE)
+    lib().oracle_fuzz_provenance(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.byref(p),
+                                 C.c_int64(seed), C.c_void_p(keep.ctypes.data), C.c_uint32(mask_words),
+                                 C.c_void_p(out.ctypes.data))
+    return keep, out[0]

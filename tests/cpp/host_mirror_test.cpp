@@ -31,6 +31,15 @@ int main() {
   std::printf("violation %u, trace of %zu events\n", fp, trace.size());
   CHECK(!sched.test(prog, 99).has_value());                       // a fingerprint that never occurs
 
+  // RunnerUtils.pruneConcurrentEvents (RunnerUtils.scala:149-163)
+  CHECK(sched.affectedNodes != 0);
+  ProvenanceTracker prov(sched.engine, trace, sched.depGraph);
+  std::vector<uint32_t> kept = prov.pruneConcurrentEvents(sched.affectedNodes);
+  std::printf("provenance: %u of %u deliveries precede the violation on nodes %#x\n", (unsigned)kept.size(),
+              prov.last.n_trace - 1, sched.affectedNodes);
+  CHECK(!kept.empty() && kept.size() + 1 == prov.last.n_kept && prov.last.n_kept < prov.last.n_trace);
+  for (uint32_t i : kept) CHECK(trace[i].kind == DEMI_EV_MSG_EVENT);
+
   ReplayScheduler replayer(cfg, trace, prog);
   demi_replay_result rr = replayer.replay(fp);                     // validate_replay (RunnerUtils.scala:101-128)
   CHECK(rr.violation == fp && rr.ignored == 0);

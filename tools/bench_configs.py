@@ -132,6 +132,32 @@ def config3_dpor():
                                        % (nc, cores(), cil / cdt * cores())}}
 
 
+def provenance():
+    """§8(f) rank 4: provenance pruning of every violating prefix a fuzz batch found."""
+    eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    ext = D.pack_externals(D.raft5_program())
+    eng.set_externals(ext)
+    n = 2_000_000
+    res = eng.fuzz_batch(1, n, 50, 5)
+    viol = np.nonzero(res["violation"])[0].astype(np.uint32)
+    eng.fuzz_provenance(1, viol[:64], 50, 5)
+    t0 = time.perf_counter()
+    keep, out, _ = eng.fuzz_provenance(1, viol, 50, 5)
+    dt = time.perf_counter() - t0
+    kms = eng.stats().kernel_ms
+    nc = min(len(viol), 2000)
+    t0 = time.perf_counter()
+    for i in viol[:nc]:
+        O.fuzz_provenance(N.MODEL_RAFT5, ext, 1 + int(i), 50, 5, keep.shape[1], model_flags=1)
+    cdt = time.perf_counter() - t0
+    return {"config": "provenance pruning of the %d violating prefixes among %d raft5 depth-50 prefixes" % (len(viol), n),
+            "metric": "executions pruned/s", "value": len(viol) / (kms * 1e-3), "e2e_value": len(viol) / dt, "kernel_ms": kms,
+            "status_ok": bool((out["status"] == 0).all()),
+            "deliveries": int(out["n_trace"].sum() - len(out)), "deliveries_kept": int(out["n_kept"].sum() - len(out)),
+            "cpu_baseline": {"value": nc / cdt, "cores": 1, "kind": "port",
+                             "sample": "%d executions, literal pair-set closure, one core" % nc}}
+
+
 def config5_bcast():
     """bcast32 depth-200 fuzz with state-hash dedup + compaction."""
     eng = D.Engine(D.SchedulerConfig(N.MODEL_BCAST32))
@@ -188,5 +214,5 @@ def config5_bcast():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c4", "c3", "c5"]
     for w in which:
-        fn = {"c4": config4_ddmin, "c3": config3_dpor, "c5": config5_bcast}[w]
+        fn = {"c4": config4_ddmin, "c3": config3_dpor, "c5": config5_bcast, "prov": provenance}[w]
         print(json.dumps(fn()), flush=True)
