@@ -66,6 +66,21 @@ class DporParams(C.Structure):
                 ("explored_slots", C.c_uint32), ("heap_cap", C.c_uint32)]
 
 
+class DporSeed(C.Structure):
+    _fields_ = [("events", C.c_void_p), ("n_events", C.c_uint32), ("dep_parent", C.c_void_p), ("n_nodes", C.c_uint32)]
+
+
+class DporEx(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("seed", C.POINTER(DporSeed)), ("caps", C.c_void_p), ("cap_offsets", C.c_void_p)]
+
+
+class IncDDMinOut(C.Structure):
+    _fields_ = [("mcs_size", C.c_uint32), ("total_replays", C.c_uint32), ("rounds", C.c_uint32), ("instances", C.c_uint32),
+                ("tests_executed", C.c_uint32), ("batches", C.c_uint32), ("interleavings_executed", C.c_uint64)]
+
+
+DF_ARVIND_ORDERING, DF_PRIORITIZE_PENDING = 1, 2
+
 DPOR_RESULT_DTYPE = np.dtype([("interleavings", "<u4"), ("violations", "<u4"), ("deliveries", "<u8"), ("races", "<u8"),
                               ("n_nodes", "<u4"), ("n_explored", "<u4"), ("heap_left", "<u4"), ("exhausted", "<u4"),
                               ("budget_exhausted", "<u4"), ("status", "<u4")])
@@ -86,7 +101,7 @@ EXPORTS = [
     "demi_set_trace", "demi_replay_batch", "demi_replay_batch_dev", "demi_ddmin", "demi_dpor_batch",
     "demi_dedup_compact_dev", "demi_dedup_compact",
     "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
-    "demi_provenance", "demi_fuzz_provenance",
+    "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
 ]
 
 _lib = None
@@ -148,6 +163,12 @@ def lib():
     L.demi_fuzz_provenance.argtypes = [vp, C.POINTER(FuzzParams), vp, C.c_uint32, vp, C.c_uint32, vp, vp]
     L.demi_dpor_batch.restype = C.c_int32
     L.demi_dpor_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), vp, vp, C.c_uint32, vp, C.c_uint32]
+    L.demi_dpor_batch_ex.restype = C.c_int32
+    L.demi_dpor_batch_ex.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(DporParams), C.POINTER(DporEx), vp, vp, C.c_uint32,
+                                     vp, C.c_uint32]
+    L.demi_incremental_ddmin.restype = C.c_int32
+    L.demi_incremental_ddmin.argtypes = [vp, vp, C.c_uint32, C.POINTER(DporParams), C.c_uint32, C.POINTER(DporSeed),
+                                         C.c_int32, C.c_uint32, vp, C.c_uint32, C.POINTER(IncDDMinOut)]
     L.demi_stats.restype = C.c_int32
     L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
     _lib = L

@@ -260,150 +260,22 @@ extern "C" int32_t demi_replay_batch(demi_handle* h, const uint64_t* masks, uint
 }
 
 // ---------------------------------------------------------------------- DDMin
+#include "ddmin_driver.hpp"
 namespace {
 
-typedef std::vector<uint64_t> Mask;
-
-struct Atom { uint32_t first, second; };
-
-struct DDMinDriver {
-  demi_handle* h;
-  uint32_t looking_for, flags, mw, n_ext;
-  const demi_ext_event* ext;
-  std::map<Mask, bool> memo;           // mask -> violation reproduced?
-  uint32_t original_num_events = 0, total_inputs_pruned = 0, total_replays = 0;
-  std::vector<uint32_t> iteration_sizes;
-  uint32_t replays_executed = 0, batches = 0;
-  int32_t error = DEMI_OK;
-  bool malformed = false;
-  // interference siblings waiting on the recursion stack: (dag, remainder)
-  std::vector<std::pair<Mask, Mask>> pending_siblings;
-  static constexpr size_t BATCH_TARGET = 4096;
-
-  static bool bit(const Mask& m, uint32_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
-  static void setbit(Mask& m, uint32_t i) { m[i >> 6] |= 1ull << (i & 63); }
-  static uint32_t popcount(const Mask& m) { uint32_t c = 0; for (uint64_t w : m) c += (uint32_t)__builtin_popcountll(w); return c; }
-  static Mask unite(const Mask& a, const Mask& b) { Mask r(a.size()); for (size_t i = 0; i < a.size(); i++) r[i] = a[i] | b[i]; return r; }
-
-  // UnmodifiedEventDag.get_atomic_events (minification/Util.scala:197-265)
-  bool atomic_events(const Mask& dag, std::vector<Atom>& atoms) const {
-    std::vector<int32_t> last_start(DEMI_MAX_ACTORS, -1);
-    std::map<std::pair<int, int>, int32_t> last_part;
-    atoms.clear();
-    for (uint32_t i = 0; i < n_ext; i++) {
-      if (!bit(dag, i)) continue;
-      const demi_ext_event& e = ext[i];
-      switch (e.kind) {
-        case DEMI_EXT_KILL:
-          if (last_start[e.a] < 0) return false;                  // "Kill without preceding Start"
-          atoms.push_back({(uint32_t)last_start[e.a], i}); last_start[e.a] = -1; break;
-        case DEMI_EXT_START: last_start[e.a] = (int32_t)i; break;
-        case DEMI_EXT_PARTITION: last_part[{e.a, e.b}] = (int32_t)i; break;
-        case DEMI_EXT_UNPARTITION: {
-          auto it = last_part.find({e.a, e.b});
-          if (it == last_part.end() || it->second < 0) return false;   // "UnPartition without preceding Partition"
-          atoms.push_back({(uint32_t)it->second, i}); it->second = -1; break;
-        }
-        default: atoms.push_back({i, 0xFFFFFFFFu}); break;
-      }
-    }
-    for (int a = 0; a < DEMI_MAX_ACTORS; a++) if (last_start[a] >= 0) atoms.push_back({(uint32_t)last_start[a], 0xFFFFFFFFu});
-    for (auto& kv : last_part) if (kv.second >= 0) atoms.push_back({(uint32_t)kv.second, 0xFFFFFFFFu});
-    std::stable_sort(atoms.begin(), atoms.end(), [](const Atom& x, const Atom& y) { return x.first < y.first; });
-    return true;
-  }
-  // MinificationUtil.split_list(atoms, 2) (minification/Util.scala:9-37) + remove_events:
-  // halves[0] = events of the first chunk, halves[1] = events of the second.
-  bool halves(const Mask& dag, Mask out[2], size_t& n_atoms) const {
-    std::vector<Atom> atoms;
-    if (!atomic_events(dag, atoms)) return false;
-    n_atoms = atoms.size();
-    size_t n0 = atoms.size() / 2 + (atoms.size() % 2 ? 1 : 0);
-    out[0].assign(mw, 0); out[1].assign(mw, 0);
-    for (size_t i = 0; i < atoms.size(); i++) {
-      Mask& s = out[i < n0 ? 0 : 1];
-      setbit(s, atoms[i].first);
-      if (atoms[i].second != 0xFFFFFFFFu) setbit(s, atoms[i].second);
-    }
-    return true;
-  }
-
-  // speculative closure of the tests ddmin2(dag, rem) may issue, `depth` levels deep
-  void expand(const Mask& dag, const Mask& rem, int depth, std::vector<Mask>& want) {
-    if (want.size() >= 4 * BATCH_TARGET) return;
-    Mask hv[2]; size_t na;
-    if (!halves(dag, hv, na) || na <= 1) return;
-    for (int k = 0; k < 2; k++) {
-      Mask t = unite(hv[k], rem);
-      if (!memo.count(t)) want.push_back(t);
-    }
-    if (depth <= 0) return;
-    expand(hv[0], rem, depth - 1, want);                       // left half violates
-    expand(hv[1], rem, depth - 1, want);                       // right half violates
-    expand(hv[0], unite(hv[1], rem), depth - 1, want);         // interference
-    expand(hv[1], unite(hv[0], rem), depth - 1, want);
-  }
-
-  void evaluate(std::vector<Mask>& want) {
-    std::sort(want.begin(), want.end());
-    want.erase(std::unique(want.begin(), want.end()), want.end());
-    if (want.empty()) return;
+// STSSched as DDMin's TestOracle: a batch of masks = one replay launch
+struct StsDDMinDriver : DDMinDriver {
+  int32_t evaluate_batch(const std::vector<Mask>& want, std::vector<char>& out) override {
     std::vector<uint64_t> flat(want.size() * mw);
     for (size_t i = 0; i < want.size(); i++) std::copy(want[i].begin(), want[i].end(), flat.begin() + i * mw);
     std::vector<demi_replay_result> res(want.size());
     int32_t rc = demi_replay_batch(h, flat.data(), (uint32_t)want.size(), mw, looking_for, flags, res.data());
-    if (rc != DEMI_OK) { error = rc; return; }
+    if (rc != DEMI_OK) return rc;
     for (size_t i = 0; i < want.size(); i++) {
-      if (res[i].status != 0) { error = fail(h, DEMI_ERR_CAPACITY, "demi_ddmin: a replay reported status %u", (unsigned)res[i].status); return; }
-      memo[want[i]] = res[i].violation != 0;
+      if (res[i].status != 0) return fail(h, DEMI_ERR_CAPACITY, "demi_ddmin: a replay reported status %u", (unsigned)res[i].status);
+      out[i] = res[i].violation != 0;
     }
-    replays_executed += (uint32_t)want.size();
-    batches++;
-  }
-
-  // TestOracle.test for the sequential walk
-  bool test(const Mask& m, const Mask& cur_dag, const Mask& cur_rem) {
-    auto it = memo.find(m);
-    if (it == memo.end()) {
-      std::vector<Mask> want;
-      want.push_back(m);
-      // depth: 4^d frames * 2 tests; stay near BATCH_TARGET
-      int depth = 5;
-      expand(cur_dag, cur_rem, depth, want);
-      for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend() && want.size() < BATCH_TARGET; ++it2)
-        expand(it2->first, it2->second, 3, want);
-      evaluate(want);
-      if (error != DEMI_OK) return false;
-      it = memo.find(m);
-    }
-    return it->second;
-  }
-
-  // DDMin.ddmin2 (DeltaDebugging.scala:73-109)
-  Mask ddmin2(const Mask& dag, const Mask& rem) {
-    if (error != DEMI_OK) return dag;
-    Mask hv[2]; size_t na;
-    if (!halves(dag, hv, na)) { malformed = true; error = fail(h, DEMI_ERR_INVALID, "demi_ddmin: Kill/UnPartition without preceding Start/Partition"); return dag; }
-    if (na <= 1) return dag;                                             // base case :74-77
-    const uint32_t dag_len = popcount(dag);
-    for (int k = 0; k < 2; k++) {                                        // :88-102
-      Mask t = unite(hv[k], rem);
-      bool violates = test(t, dag, rem);
-      if (error != DEMI_OK) return dag;
-      total_replays++;
-      iteration_sizes.push_back(original_num_events - total_inputs_pruned);
-      if (violates) {
-        total_inputs_pruned += dag_len - popcount(hv[k]);
-        return ddmin2(hv[k], rem);
-      }
-    }
-    // interference :104-108 — the right-hand recursion does not depend on the left-hand result
-    Mask rem_l = unite(hv[1], rem), rem_r = unite(hv[0], rem);
-    pending_siblings.push_back({hv[1], rem_r});
-    Mask left = ddmin2(hv[0], rem_l);
-    pending_siblings.pop_back();
-    Mask right = ddmin2(hv[1], rem_r);
-    return unite(left, right);
+    return DEMI_OK;
   }
 };
 
@@ -418,7 +290,7 @@ extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t fla
   const uint32_t n_ext = (uint32_t)h->trace_ext_host.size();
   if (mask_words * 64 < n_ext) return fail(h, DEMI_ERR_INVALID, "mask_words too small");
   memset(out, 0, sizeof(*out));
-  DDMinDriver d;
+  StsDDMinDriver d;
   d.h = h; d.looking_for = looking_for; d.flags = flags; d.mw = mask_words; d.n_ext = n_ext;
   d.ext = h->trace_ext_host.data();
   // STSSched ignores WaitQuiescence: drop them from the DAG (RunnerUtils.scala:678-684)

@@ -49,6 +49,18 @@ struct DporArgs {
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
   uint32_t* node_pos;           // [node_cap] (interleaving stamp << 12 | first position in the current trace)
   uint32_t* scan;               // [T1] per trace position: parent's first position << 8 | receiver
+  // RunnerUtils.editDistanceDporDDMin configuration (RunnerUtils.scala:822-835)
+  uint32_t flags;               // DEMI_DF_*
+  const uint4* init_nodes; uint32_t n_init_nodes;       // setInitialDepGraph: {hdr, p0, p1, parent | depth << 20}
+  const uint32_t* init_trace; uint32_t n_init_trace;    // setInitialTrace
+  const int32_t* orig_index;    // ArvindDistanceOrdering.originalIndices: node -> index in the original trace, -1 absent
+  uint32_t* heap_dist;          // [heap_cap] per search: distance of each heap entry (ArvindDistanceOrdering only)
+  int32_t* path;                // [2*T1+4] per search: arvindDistance scratch
+  // ResumableDPOR (IncrementalDeltaDebugging.scala:90-122): search i performs one DPORwHeuristics.test per entry of
+  // caps[cap_offsets[i] .. cap_offsets[i+1]) on ONE instance, each preceded by setMaxDistance(cap) (< 0: no cap).
+  // An instance's state is a function of the caps it was tested with, so a launch that replays that history is
+  // side-effect free — which is what lets DDMin's tests be evaluated speculatively.  caps == null: one test, no cap.
+  const int32_t* caps; const uint32_t* cap_offsets;
 };
 
 template <class MODEL, int BD>
@@ -62,9 +74,10 @@ struct DporMachine {
   uint32_t* smw; const DporArgs* A;
   uint4* nodes; uint32_t* child_hash; uint32_t* queues; uint64_t* explored; DporKey* heap;
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
-  uint32_t* node_pos; uint32_t* scan;
+  uint32_t* node_pos; uint32_t* scan; uint32_t* heap_dist; int32_t* path;
   uint16_t qlen[NQ];            // local memory (small)
-  uint32_t n_nodes, n_explored, n_heap, n_traces;
+  uint32_t n_nodes, n_explored, n_heap, n_traces, found;
+  int32_t max_distance;         // setMaxDistance (:128-134); < 0 = no cap
   uint32_t registry, cancelled, isolated;
   uint32_t parent_event, current_depth, cur_len, next_len, next_pos;
   int32_t nsched;
@@ -190,9 +203,10 @@ struct DporMachine {
       nsched++;
       if (A->P.max_messages >= 0 && nsched > A->P.max_messages) return 0;       // :583-586
       uint32_t pick = 0;
-      while (next_pos < next_len && next_trace[next_pos] == 0) next_pos++;       // getNextTraceMessage :363-372
-      if (next_pos < next_len) {                                                 // getMatchingMessage :516-524
-        uint32_t want = next_trace[next_pos++];
+      do {                                                                       // getNextMatchingMessage :542-555
+        while (next_pos < next_len && next_trace[next_pos] == 0) next_pos++;     // getNextTraceMessage :363-372
+        if (next_pos >= next_len) break;
+        uint32_t want = next_trace[next_pos++];                                  // getMatchingMessage :516-524
         uint4 c = nodes[want];
         uint32_t dst = hdr_dst(c.x);
         if (!((A->blocked_mask >> dst) & 1u)) {
@@ -200,7 +214,7 @@ struct DporMachine {
           for (uint32_t i = 0; i < qlen[q]; i++)
             if (queues[q * DPOR_QCAP + i] == want) { queue_remove(q, i); pick = want; break; }
         }
-      }
+      } while (!pick && (A->flags & DEMI_DF_PRIORITIZE_PENDING));
       if (!pick) {                                                               // getPendingEvent :452-472 (canonical order)
         for (uint32_t q = 0; q < NQ; q++) {
           if (!qlen[q] || ((A->blocked_mask >> (q % N)) & 1u)) continue;
@@ -281,95 +295,193 @@ struct DporMachine {
     return a;
   }
 
+  // ArvindDistanceOrdering.arvindDistance (BacktrackOrdering.scala:119-146): path = dependency path root..e1
+  // (getCommonPrefix(e1, e1)) ++ replayThis ++ [e1, e2]; +1 per event absent from the original trace, +1 per
+  // earlier path element the original trace orders after it.  `path` holds original indices (-1 = absent).
+  __device__ uint32_t arvind_distance(uint32_t branch, const uint32_t* kt, uint32_t li, uint32_t e1, uint32_t e2) {
+    const uint32_t n0 = A->n_init_nodes;
+    auto oi_of = [&](uint32_t v) -> int32_t { return v < n0 ? __ldg(A->orig_index + v) : -1; };
+    const uint32_t depth = node_depth(e1);
+    uint32_t v = e1;
+    for (uint32_t i = depth + 1; i-- > 0; v = node_parent(v)) path[i] = oi_of(v);
+    uint32_t n = depth + 1;
+    for (uint32_t i = branch + 1; i <= li; i++) { const uint32_t id = kt[i]; if (id != e2) path[n++] = oi_of(id); }
+    path[n++] = oi_of(e1); path[n++] = oi_of(e2);
+    uint32_t dist = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      const int32_t oi = path[i];
+      if (oi < 0) { dist++; continue; }
+      for (uint32_t j = 0; j < i; j++) dist += (path[j] > oi) ? 1u : 0u;       // absent = -1 never counts
+    }
+    return dist;
+  }
+
+  // heap entries: the packed key, plus the distance in a parallel array under ArvindDistanceOrdering
+  // (getOrdered, BacktrackOrdering.scala:153-163: larger distance first, then depth, then oldest)
+  __device__ __forceinline__ bool entry_before(DporKey ka, uint32_t da, DporKey kb, uint32_t db) const {
+    return da != db ? da > db : ka > kb;
+  }
+  __device__ void heap_push2(DporKey k, uint32_t d) {
+    if (n_heap >= A->P.heap_cap) { status = DEMI_DS_HEAP_OVF; return; }
+    uint32_t i = n_heap++;
+    while (i > 0) {
+      const uint32_t p = (i - 1) / 2;
+      const DporKey pk = heap[p]; const uint32_t pd = heap_dist[p];
+      if (!entry_before(k, d, pk, pd)) break;
+      heap[i] = pk; heap_dist[i] = pd; i = p;
+    }
+    heap[i] = k; heap_dist[i] = d;
+  }
+  __device__ DporKey heap_pop2() {
+    const DporKey top = heap[0];
+    --n_heap;
+    const DporKey last = heap[n_heap]; const uint32_t ld = heap_dist[n_heap];
+    uint32_t i = 0;
+    for (;;) {
+      const uint32_t l = 2 * i + 1, r = l + 1;
+      if (l >= n_heap) break;
+      uint32_t b = l; DporKey bk = heap[l]; uint32_t bd = heap_dist[l];
+      if (r < n_heap) { const DporKey rk = heap[r]; const uint32_t rd = heap_dist[r]; if (entry_before(rk, rd, bk, bd)) { b = r; bk = rk; bd = rd; } }
+      if (!entry_before(bk, bd, last, ld)) break;
+      heap[i] = bk; heap_dist[i] = bd; i = b;
+    }
+    if (n_heap) { heap[i] = last; heap_dist[i] = ld; }
+    return top;
+  }
+
+  // dpor(trace) :1020-1185 on the finished interleaving k (still in cur_trace): race scan, then getNext.
+  // true: next_trace holds the next schedule; false: None.
+  // Every ancestor of a delivered event was delivered earlier in the same trace, so the dependency-tree
+  // walks of isCoEnabeled / getCommonPrefix run on trace POSITIONS: scan[i] = (first position of
+  // trace[i]'s parent) << 8 | receiver.  "First position" is what `trace.indexWhere` (:1058) returns
+  // when a Unique was delivered twice.
+  __device__ bool analyse(uint32_t k, demi_dpor_result& R) {
+    const bool arv = (A->flags & DEMI_DF_ARVIND_ORDERING) != 0;
+    const bool capped = max_distance >= 0;
+    const uint32_t n = cur_len;
+    const uint32_t stamp = (k + 1) << 12;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t id = cur_trace[i];
+      if ((node_pos[id] & 0xFFFFF000u) != stamp) node_pos[id] = stamp | i;
+    }
+    for (uint32_t i = 1; i < n; i++) {
+      const uint4 c = nodes[cur_trace[i]];
+      scan[i] = ((node_pos[c.w & 0xFFFFFu] & 0xFFFu) << 8) | hdr_dst(c.x);
+    }
+    scan[0] = 0xFF;                                                             // root: receiver "null"
+    for (uint32_t li = 1; li < n && !status; li++) {
+      const uint32_t later = cur_trace[li];
+      const uint32_t ldst = scan[li] & 0xFFu;
+      const uint32_t lfp = node_pos[later] & 0xFFFu;                            // first position of `later`
+      for (uint32_t ei = 1; ei < li && !status; ei++) {
+        if ((scan[ei] & 0xFFu) != ldst) continue;                               // isCoEnabeled :1096
+        const uint32_t earlier = cur_trace[ei];
+        const uint32_t efp = node_pos[earlier] & 0xFFFu;
+        uint32_t a = lfp;
+        while (a > efp) a = scan[a] >> 8;                                       // laterN.pathTo(earlierN) :1104
+        if (a == efp) continue;                                                 // later descends from earlier
+        uint32_t b = efp;                                                       // getCommonPrefix(...).last :994-1018
+        a = lfp;
+        while (a != b) { if (a > b) a = scan[a] >> 8; else b = scan[b] >> 8; }
+        const uint32_t branch = a;                                              // == trace.indexWhere(_ == lca) :1058
+        explored_add(earlier, later);                                           // :1071-1073
+        R.races++;
+        // without a distance cap a key whose reversed pair is explored would only be skipped when popped
+        // (:1156-1160); with a cap getNext looks at the head first (:1145-1146), so everything is enqueued
+        if (!capped && explored_has(later, earlier)) continue;
+        const DporKey key = dpor_key(branch, k, li, ei);
+        if (arv) heap_push2(key, arvind_distance(branch, cur_trace, li, later, earlier));
+        else heap_push(key);                                                    // :1134
+      }
+    }
+    if (status) return false;
+    uint32_t kb = 0, kl = 0, e1 = 0, e2 = 0; const uint32_t* kt = nullptr;
+    for (;;) {                                                                  // getNext :1142-1162
+      if (!n_heap) { R.exhausted = 1; return false; }
+      if (capped && (int32_t)(arv ? heap_dist[0] : 0u) >= max_distance) return false;   // :1145-1146
+      if (A->P.stop_if_found && found) return false;                            // :1147
+      const DporKey key = arv ? heap_pop2() : heap_pop();
+      kt = traces + (size_t)dpor_key_trace(key) * A->T1;
+      kb = dpor_key_branch(key); kl = dpor_key_later(key);
+      e1 = kt[kl]; e2 = kt[dpor_key_earlier(key)];
+      if (!explored_has(e1, e2)) break;
+    }
+    explored_add(e1, e2);                                                       // :1169-1171
+    if (status) return false;
+    // nextTrace = trace.take(maxIndex+1) ++ replayThis (:1180, :1060-1063)
+    next_len = 0; next_pos = 0;
+    for (uint32_t i = 0; i <= kb && i < n; i++) next_trace[next_len++] = cur_trace[i];
+    for (uint32_t i = kb + 1; i <= kl; i++) {
+      const uint32_t id = kt[i];
+      if (id != e2) next_trace[next_len++] = id;
+    }
+    return true;
+  }
+
+  // The DPORwHeuristics.test calls (:1193-1242) of one instance.
   __device__ void search(uint32_t sid) {
     const uint32_t ext_lo = A->ext_offsets[sid], ext_hi = A->ext_offsets[sid + 1];
     demi_dpor_result R; memset(&R, 0, sizeof(R));
-    n_nodes = 1; nodes[0] = make_uint4(0, 0, 0, 0);
-    n_explored = n_heap = n_traces = 0; status = 0;
-    next_len = next_pos = 0;
     uint32_t n_viol = 0;
+    n_nodes = 1; nodes[0] = make_uint4(0, 0, 0, 0);
+    n_explored = n_heap = n_traces = 0; status = 0; found = 0; cur_len = 0;
+    // setInitialDepGraph (:214-217): start from the recorded execution's graph
+    if (A->n_init_nodes) {
+      if (A->n_init_nodes > A->P.node_cap) status = DEMI_DS_NODE_OVF;
+      for (uint32_t i = 1; i < A->n_init_nodes && !status; i++) {
+        const uint4 nd = __ldg(A->init_nodes + i);
+        nodes[i] = nd;
+        uint32_t s = demi_fmix32((nd.x * 0x9E3779B1u) ^ (nd.y * 0x85EBCA77u) ^ (nd.z * 0xC2B2AE3Du) ^ ((nd.w & 0xFFFFFu) * 0x27D4EB2Fu)) &
+                     (A->child_slots - 1);
+        while (child_hash[s]) s = (s + 1) & (A->child_slots - 1);
+        child_hash[s] = i;
+      }
+      if (!status) n_nodes = A->n_init_nodes;
+    }
     for (uint32_t i = ext_lo; i < ext_hi; i++) {
       uint32_t kind = __ldg(A->ext + i).x & 0xFF;
       if (kind != DEMI_EXT_START && kind != DEMI_EXT_SEND) status = DEMI_DS_UNSUPPORTED;   // :710
     }
-    while (!status) {
-      uint32_t v = run_interleaving(ext_lo, ext_hi);
-      if (status) break;
-      const uint32_t k = n_traces++;
-      uint32_t* tk = traces + (size_t)k * A->T1;
-      uint64_t sh = 0;
-      for (uint32_t i = 0; i < cur_len; i++) {
-        uint32_t id = cur_trace[i];
-        tk[i] = id;
-        if (i) { uint4 c = nodes[id]; sh += demi_event_term(c.x & 0x00FFFFFFu, c.y, c.z, i, 0, 0); }
+    const uint32_t cap_lo = A->caps ? A->cap_offsets[sid] : 0u, cap_hi = A->caps ? A->cap_offsets[sid + 1] : 1u;
+    bool started = false;
+    for (uint32_t ci = cap_lo; ci < cap_hi && !status; ci++) {
+      max_distance = A->caps ? A->caps[ci] : -1;
+      R.exhausted = R.budget_exhausted = 0;
+      if (A->P.stop_if_found && found) break;                                     // "Already have shortestTrace!" :1197-1201
+      if (n_traces >= A->P.max_interleavings) { R.budget_exhausted = 1; continue; }
+      next_len = next_pos = 0;                                                    // initialTrace :1219-1221
+      if (started && n_heap) {
+        if (!analyse(n_traces - 1, R)) next_len = 0;                              // None: run() clears nextTrace :757-759
+        R.exhausted = 0;
+      } else if (A->n_init_trace) {
+        for (uint32_t i = 0; i < A->n_init_trace && i < A->T1; i++) next_trace[next_len++] = __ldg(A->init_trace + i);
       }
-      trace_len[k] = cur_len;
-      if (A->hashes && k < A->cap_hashes) A->hashes[(size_t)sid * A->cap_hashes + k] = sh;
-      R.interleavings++; R.deliveries += cur_len - 1;
-      if (v) {
-        if (A->viol && n_viol < A->cap_viol) {
-          demi_dpor_violation& o = A->viol[(size_t)sid * A->cap_viol + n_viol];
-          o.schedule_hash = sh; o.interleaving = k; o.length = (uint16_t)(cur_len - 1); o.code = (uint16_t)v;
+      started = true;
+      while (!status) {
+        uint32_t v = run_interleaving(ext_lo, ext_hi);
+        if (status) break;
+        const uint32_t k = n_traces++;
+        uint32_t* tk = traces + (size_t)k * A->T1;
+        uint64_t sh = 0;
+        for (uint32_t i = 0; i < cur_len; i++) {
+          uint32_t id = cur_trace[i];
+          tk[i] = id;
+          if (i) { uint4 c = nodes[id]; sh += demi_event_term(c.x & 0x00FFFFFFu, c.y, c.z, i, 0, 0); }
         }
-        n_viol++;
-        if (A->P.stop_if_found) break;                                           // test() returns Some(trace) :1236-1238
-      }
-      if (R.interleavings >= A->P.max_interleavings) { R.budget_exhausted = 1; break; }
-      // dpor(currentTrace) :1020-1185.  Every ancestor of a delivered event was delivered earlier in
-      // the same trace, so the dependency-tree walks of isCoEnabeled / getCommonPrefix run on trace
-      // POSITIONS: scan[i] = (first position of trace[i]'s parent) << 8 | receiver.  "First position"
-      // is what `trace.indexWhere` (:1058) returns when a Unique was delivered twice.
-      const uint32_t n = cur_len;
-      const uint32_t stamp = (k + 1) << 12;
-      for (uint32_t i = 0; i < n; i++) {
-        const uint32_t id = cur_trace[i];
-        if ((node_pos[id] & 0xFFFFF000u) != stamp) node_pos[id] = stamp | i;
-      }
-      for (uint32_t i = 1; i < n; i++) {
-        const uint4 c = nodes[cur_trace[i]];
-        scan[i] = ((node_pos[c.w & 0xFFFFFu] & 0xFFFu) << 8) | hdr_dst(c.x);
-      }
-      scan[0] = 0xFF;                                                             // root: receiver "null"
-      for (uint32_t li = 1; li < n && !status; li++) {
-        const uint32_t later = cur_trace[li];
-        const uint32_t ldst = scan[li] & 0xFFu;
-        const uint32_t lfp = node_pos[later] & 0xFFFu;                            // first position of `later`
-        for (uint32_t ei = 1; ei < li && !status; ei++) {
-          if ((scan[ei] & 0xFFu) != ldst) continue;                               // isCoEnabeled :1096
-          const uint32_t earlier = cur_trace[ei];
-          const uint32_t efp = node_pos[earlier] & 0xFFFu;
-          uint32_t a = lfp;
-          while (a > efp) a = scan[a] >> 8;                                       // laterN.pathTo(earlierN) :1104
-          if (a == efp) continue;                                                 // later descends from earlier
-          uint32_t b = efp;                                                       // getCommonPrefix(...).last :994-1018
-          a = lfp;
-          while (a != b) { if (a > b) a = scan[a] >> 8; else b = scan[b] >> 8; }
-          const uint32_t branch = a;                                              // == trace.indexWhere(_ == lca) :1058
-          explored_add(earlier, later);                                           // :1071-1073
-          R.races++;
-          if (explored_has(later, earlier)) continue;      // it would be skipped when popped (:1156-1160)
-          heap_push(dpor_key(branch, k, li, ei));                                 // :1134
+        trace_len[k] = cur_len;
+        if (A->hashes && k < A->cap_hashes) A->hashes[(size_t)sid * A->cap_hashes + k] = sh;
+        R.interleavings++; R.deliveries += cur_len - 1;
+        if (v) {
+          if (A->viol && n_viol < A->cap_viol) {
+            demi_dpor_violation& o = A->viol[(size_t)sid * A->cap_viol + n_viol];
+            o.schedule_hash = sh; o.interleaving = k; o.length = (uint16_t)(cur_len - 1); o.code = (uint16_t)v;
+          }
+          n_viol++;
+          found = 1;                                                             // checkInvariant :404-410
+          if (A->P.stop_if_found) break;                                         // test() returns Some(trace) :1236-1238
         }
-      }
-      if (status) break;
-      bool have = false; uint32_t kb = 0, kl = 0, e1 = 0, e2 = 0; const uint32_t* kt = nullptr;
-      while (n_heap) {                                                            // getNext :1142-1162
-        const DporKey key = heap_pop();
-        kt = traces + (size_t)dpor_key_trace(key) * A->T1;
-        kb = dpor_key_branch(key); kl = dpor_key_later(key);
-        e1 = kt[kl]; e2 = kt[dpor_key_earlier(key)];
-        if (explored_has(e1, e2)) continue;
-        have = true; break;
-      }
-      if (!have) { R.exhausted = 1; break; }
-      explored_add(e1, e2);                                                       // :1169-1171
-      if (status) break;
-      // nextTrace = trace.take(maxIndex+1) ++ replayThis (:1180, :1060-1063)
-      next_len = 0; next_pos = 0;
-      for (uint32_t i = 0; i <= kb && i < n; i++) next_trace[next_len++] = cur_trace[i];
-      for (uint32_t i = kb + 1; i <= kl; i++) {
-        uint32_t id = kt[i];
-        if (id != e2) next_trace[next_len++] = id;
+        if (n_traces >= A->P.max_interleavings) { R.budget_exhausted = 1; break; }
+        if (!analyse(k, R)) break;
       }
     }
     R.violations = n_viol; R.n_nodes = n_nodes; R.n_explored = n_explored; R.heap_left = n_heap; R.status = status;
@@ -392,12 +504,14 @@ dpor_kernel(const __grid_constant__ DporArgs args) {
   m.queues = args.queues + (size_t)sid * M::NQ * DPOR_QCAP;
   m.explored = args.explored + (size_t)sid * args.P.explored_slots;
   m.heap = args.heap + (size_t)sid * args.P.heap_cap;
+  m.heap_dist = args.heap_dist ? args.heap_dist + (size_t)sid * args.P.heap_cap : nullptr;
   m.traces = args.traces + (size_t)sid * (args.P.max_interleavings + 1) * args.T1;
   m.trace_len = args.trace_len + (size_t)sid * (args.P.max_interleavings + 1);
   m.cur_trace = args.cur_trace + (size_t)sid * args.T1;
   m.next_trace = args.next_trace + (size_t)sid * args.T1;
   m.node_pos = args.node_pos + (size_t)sid * args.P.node_cap;
   m.scan = args.scan + (size_t)sid * args.T1;
+  m.path = args.path ? args.path + (size_t)sid * (2 * args.T1 + 4) : nullptr;
   m.search(sid);
 }
 

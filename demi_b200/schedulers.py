@@ -217,6 +217,59 @@ class Engine(object):
                                             hashes.ctypes.data if want_hashes else None, cap_h))
         return res, viol, hashes
 
+    @staticmethod
+    def _seed(seed):
+        """(events, dep_parent) of a recorded execution -> demi_dpor_seed (keeps the arrays alive)."""
+        ev = np.ascontiguousarray(seed[0], dtype=N.EVENT_DTYPE)
+        par = np.ascontiguousarray(seed[1], dtype=np.uint16)
+        return N.DporSeed(ev.ctypes.data, len(ev), par.ctypes.data, len(par)), (ev, par)
+
+    def dpor_batch_ex(self, programs, max_messages, max_interleavings, seed=None, flags=0, caps=None, looking_for=0,
+                      stop_if_found=True, node_cap=4096, explored_slots=1 << 16, heap_cap=1 << 15, want_hashes=False):
+        """DPOR instances in RunnerUtils.editDistanceDporDDMin's configuration.  `seed` = (events, dep_parent) of the
+        recorded execution; `caps[i]` = the setMaxDistance values instance i is tested with, in order (None: one
+        uncapped test)."""
+        packed = [p if isinstance(p, np.ndarray) else pack_externals(p) for p in programs]
+        offs = np.zeros(len(packed) + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(p) for p in packed])
+        ext = np.ascontiguousarray(np.concatenate(packed), dtype=N.EXT_DTYPE)
+        P = N.DporParams(max_messages, -1, max_interleavings, looking_for or 0, 1 if stop_if_found else 0,
+                         node_cap, explored_slots, heap_cap)
+        ex = N.DporEx(flags, None, None, None)
+        keep = []
+        if seed is not None:
+            sd, alive = self._seed(seed)
+            keep += [sd, alive]
+            ex.seed = C.pointer(sd)
+        if caps is not None:
+            coff = np.zeros(len(packed) + 1, dtype=np.uint32)
+            coff[1:] = np.cumsum([len(c) for c in caps])
+            cflat = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in caps]), dtype=np.int32)
+            keep += [coff, cflat]
+            ex.caps, ex.cap_offsets = cflat.ctypes.data, coff.ctypes.data
+        res = np.zeros(len(packed), dtype=N.DPOR_RESULT_DTYPE)
+        cap_h = max_interleavings + 1 if want_hashes else 0
+        hashes = np.zeros((len(packed), max(cap_h, 1)), dtype=np.uint64)
+        self._check(N.lib().demi_dpor_batch_ex(self._h, ext.ctypes.data, offs.ctypes.data, len(packed), C.byref(P),
+                                               C.byref(ex), res.ctypes.data, None, 0,
+                                               hashes.ctypes.data if want_hashes else None, cap_h))
+        return res, hashes
+
+    def incremental_ddmin(self, externals, max_messages, max_interleavings, seed, looking_for=0, max_max_distance=8,
+                          stop_at_size=6, flags=N.DF_ARVIND_ORDERING | N.DF_PRIORITIZE_PENDING, node_cap=4096,
+                          explored_slots=1 << 16, heap_cap=1 << 15):
+        ext = externals if isinstance(externals, np.ndarray) else pack_externals(externals)
+        ext = np.ascontiguousarray(ext, dtype=N.EXT_DTYPE)
+        P = N.DporParams(max_messages, -1, max_interleavings, looking_for or 0, 1, node_cap, explored_slots, heap_cap)
+        sd, alive = self._seed(seed)
+        mw = max(1, (len(ext) + 63) // 64)
+        mcs = np.zeros(mw, dtype=np.uint64)
+        out = N.IncDDMinOut()
+        self._check(N.lib().demi_incremental_ddmin(self._h, ext.ctypes.data, len(ext), C.byref(P), flags, C.byref(sd),
+                                                   max_max_distance, stop_at_size, mcs.ctypes.data, mw, C.byref(out)))
+        del alive
+        return mcs, out
+
     def stats(self):
         s = N.Perf()
         self._check(N.lib().demi_stats(self._h, C.byref(s)))

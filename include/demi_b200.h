@@ -321,6 +321,49 @@ int32_t demi_dpor_batch(demi_handle* h, const demi_ext_event* ext, const uint32_
                         const demi_dpor_params* params, demi_dpor_result* results,
                         demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint32_t cap_hashes);
 
+/* Edit-distance bounded, resumable DPOR: the DPOR instances RunnerUtils.editDistanceDporDDMin builds
+ * (RunnerUtils.scala:822-835) and ResumableDPOR keeps per external subsequence
+ * (minification/IncrementalDeltaDebugging.scala:90-122). */
+#define DEMI_DF_ARVIND_ORDERING    0x1u  /* backtrackHeuristic = ArvindDistanceOrdering (BacktrackOrdering.scala:99-173),
+                                            initialised with the seed's trace; else DefaultBacktrackOrdering            */
+#define DEMI_DF_PRIORITIZE_PENDING 0x2u  /* prioritizePendingUponDivergence (DPORwHeuristics.scala:65-68, :542-555)    */
+/* The recorded execution every instance starts from: setInitialDepGraph / setInitialTrace
+ * (DPORwHeuristics.scala:210-217) — events + DepTracker tree as returned by demi_fuzz_trace. */
+typedef struct demi_dpor_seed {
+  const demi_event* events; uint32_t n_events;
+  const uint16_t*  dep_parent; uint32_t n_nodes;
+} demi_dpor_seed;
+typedef struct demi_dpor_ex {
+  uint32_t flags;                 /* DEMI_DF_*                                                                   */
+  const demi_dpor_seed* seed;     /* may be NULL                                                                 */
+  /* search s performs one DPORwHeuristics.test per entry of caps[cap_offsets[s] .. cap_offsets[s+1]) on ONE
+   * instance, each after setMaxDistance(cap) (:128-134; cap < 0 = uncapped).  An instance's state is a function of
+   * the caps it has been tested with, so "resuming" = passing the longer history.  NULL: one uncapped test.      */
+  const int32_t* caps; const uint32_t* cap_offsets;
+} demi_dpor_ex;
+/* demi_dpor_batch with the options above.  The result record accumulates over the instance's tests; the
+ * exhausted / budget_exhausted flags are the last test's; violations > 0 <=> the last test returned Some(trace). */
+int32_t demi_dpor_batch_ex(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_offsets, uint32_t n_searches,
+                           const demi_dpor_params* params, const demi_dpor_ex* ex, demi_dpor_result* results,
+                           demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint32_t cap_hashes);
+/* IncrementalDDMin(ResumableDPOR) (IncrementalDeltaDebugging.scala:20-88): DDMin over `externals` (Start / Send
+ * only) with DPOR as the test oracle, the distance cap doubling 0, 2, 4, ... while it is below max_max_distance
+ * and the MCS is larger than stop_at_size.  Decisions and counters are the sequential ones; the DPOR tests a
+ * round may need are evaluated speculatively in batches. */
+typedef struct demi_incddmin_out {
+  uint32_t mcs_size;
+  uint32_t total_replays;         /* sequential count (mergeStats, :33-41)                  */
+  uint32_t rounds;                /* DDMin runs = distance caps tried                        */
+  uint32_t instances;             /* DPOR instances the sequential run creates               */
+  uint32_t tests_executed;        /* DPOR tests evaluated on the GPU, speculation included   */
+  uint32_t batches;
+  uint64_t interleavings_executed;
+} demi_incddmin_out;
+int32_t demi_incremental_ddmin(demi_handle* h, const demi_ext_event* externals, uint32_t n_externals,
+                               const demi_dpor_params* params, uint32_t flags, const demi_dpor_seed* seed,
+                               int32_t max_max_distance, uint32_t stop_at_size,
+                               uint64_t* mcs_mask, uint32_t mask_words, demi_incddmin_out* out);
+
 /* ------------------------------------------- state-hash dedup + compaction */
 /* Frontier bookkeeping the north-star adds on top of the reference (the
  * reference has no dedup; RunnerUtils.fuzz simply discards executions):

@@ -272,3 +272,82 @@ def fuzz_provenance(model, ext, seed, max_messages, interval, mask_words, model_
                                  C.c_int64(seed), C.c_void_p(keep.ctypes.data), C.c_uint32(mask_words),
                                  C.c_void_p(out.ctypes.data))
     return keep, out[0]
+
+
+# ------------------------------------------------ resumable, edit-distance bounded DPOR / IncrementalDDMin
+class DporOpts(C.Structure):
+    _fields_ = [("init_nodes", C.c_void_p), ("n_init_nodes", C.c_uint32), ("init_trace", C.c_void_p),
+                ("n_init_trace", C.c_uint32), ("arvind", C.c_uint32), ("prioritize_pending", C.c_uint32)]
+
+
+def dpor_seed(events, dep_parent):
+    """(init_nodes, init_trace) of a recorded execution: the DepTracker graph as {src|dst<<8|type<<16, p0, p1, parent}
+    per Unique (timer markers become deadLetters, the sender both trackers use) and DepTracker.initialTrace."""
+    ev = np.asarray(events, dtype=EVENT_DTYPE)
+    n = len(dep_parent)
+    nodes = np.zeros((n, 4), dtype=np.uint32)
+    for e in ev[ev["kind"] == 1]:                      # MsgSend: the Unique was allocated here
+        src = 255 if e["src"] == 254 else int(e["src"])
+        nodes[e["node"]] = (src | (int(e["dst"]) << 8) | (int(e["type"]) << 16), e["p0"], e["p1"], dep_parent[e["node"]])
+    trace = np.concatenate([[0], ev["node"][ev["kind"] == 2]]).astype(np.uint32)
+    return nodes, trace
+
+
+class DporInstance:
+    """One live DPORwHeuristics (oracle_dpor_open/test/close)."""
+
+    def __init__(self, model, ext, max_messages, max_interleavings, seed=None, arvind=0, prioritize_pending=0,
+                 looking_for=0, stop_if_found=1, model_flags=0, node_cap=1 << 12, explored_slots=1 << 16,
+                 heap_cap=1 << 17):
+        ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+        cfg = Config(0, model, model_flags, 0, 0)
+        self.P = DporParams(max_messages, -1, max_interleavings, looking_for, stop_if_found, node_cap, explored_slots,
+                            heap_cap)
+        self.max_interleavings = max_interleavings
+        opts = DporOpts(None, 0, None, 0, arvind, prioritize_pending)
+        if seed is not None:
+            self._nodes = np.ascontiguousarray(seed[0], dtype=np.uint32)
+            self._trace = np.ascontiguousarray(seed[1], dtype=np.uint32)
+            opts = DporOpts(self._nodes.ctypes.data, len(self._nodes), self._trace.ctypes.data, len(self._trace),
+                            arvind, prioritize_pending)
+        lib().oracle_dpor_open.restype = C.c_void_p
+        self.h = lib().oracle_dpor_open(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)),
+                                        C.byref(self.P), C.byref(opts))
+        if not self.h:
+            raise RuntimeError("oracle_dpor_open failed")
+
+    def test(self, max_distance=-1):
+        res = np.zeros(1, dtype=DPOR_RESULT_DTYPE)
+        hashes = np.zeros(self.max_interleavings + 1, dtype=np.uint64)
+        lib().oracle_dpor_test(C.c_void_p(self.h), C.c_int32(max_distance), C.c_void_p(res.ctypes.data), None,
+                               C.c_uint32(0), C.c_void_p(hashes.ctypes.data), C.c_uint32(len(hashes)))
+        return res[0], hashes[:int(res[0]["interleavings"])].copy()
+
+    def close(self):
+        if self.h:
+            lib().oracle_dpor_close(C.c_void_p(self.h))
+            self.h = None
+
+
+def incremental_ddmin(model, ext, max_messages, max_interleavings, seed, max_max_distance=8, stop_at_size=6,
+                      looking_for=0, model_flags=0, node_cap=1 << 12, explored_slots=1 << 16, heap_cap=1 << 17,
+                      cap_instances=4096):
+    """RunnerUtils.editDistanceDporDDMin's minimisation (RunnerUtils.scala:822-842)."""
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    cfg = Config(0, model, model_flags, 0, 0)
+    P = DporParams(max_messages, -1, max_interleavings, looking_for, 1, node_cap, explored_slots, heap_cap)
+    nodes = np.ascontiguousarray(seed[0], dtype=np.uint32)
+    trace = np.ascontiguousarray(seed[1], dtype=np.uint32)
+    opts = DporOpts(nodes.ctypes.data, len(nodes), trace.ctypes.data, len(trace), 1, 1)
+    mw = mask_words(len(ext))
+    mcs = np.zeros(mw, dtype=np.uint64)
+    total, rounds, ninst = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    il = C.c_uint64()
+    sizes = np.zeros(64, dtype=np.uint32)
+    rc = lib().oracle_incremental_ddmin(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.byref(P),
+                                        C.byref(opts), C.c_int32(max_max_distance), C.c_uint32(stop_at_size),
+                                        C.c_uint32(cap_instances), C.c_void_p(mcs.ctypes.data), C.c_uint32(mw),
+                                        C.byref(total), C.byref(rounds), C.byref(il), C.byref(ninst),
+                                        C.c_void_p(sizes.ctypes.data), C.c_uint32(len(sizes)))
+    return rc, mcs, {"total_replays": total.value, "rounds": rounds.value, "interleavings": il.value,
+                     "instances": ninst.value, "mcs_sizes": sizes[:rounds.value].copy()}

@@ -212,6 +212,76 @@ int oracle_ddmin_sts(const demi_config* cfg, const demi_replay_input* in, uint32
   return rc;
 }
 
+/* ------------------------------------------------ IncrementalDDMin over ResumableDPOR */
+/* ResumableDPOR (IncrementalDeltaDebugging.scala:90-122): one DPORwHeuristics per external subsequence */
+#include "dpor.h"
+typedef struct {
+  const demi_config* cfg; const demi_ext_event* ext; uint32_t n_ext, mw;
+  const demi_dpor_params* P; const oracle_dpor_opts* opts;
+  int32_t max_distance;
+  uint64_t* keys; void** inst; uint32_t n_inst, cap_inst;
+  uint64_t interleavings; uint32_t dpor_tests; int error;
+} rdpor_ctx;
+static int rdpor_test(void* ctx, const uint64_t* mask) {
+  rdpor_ctx* c = (rdpor_ctx*)ctx;
+  uint32_t slot = c->n_inst;
+  for (uint32_t i = 0; i < c->n_inst; i++) if (!memcmp(c->keys + (size_t)i * c->mw, mask, c->mw * 8)) { slot = i; break; }
+  if (slot == c->n_inst) {                                                    /* subseqToDPOR(events) = ctor() :110-113 */
+    if (c->n_inst >= c->cap_inst) { c->error = 1; return 0; }
+    demi_ext_event* sub = (demi_ext_event*)malloc(sizeof(demi_ext_event) * (c->n_ext + 1));
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < c->n_ext; i++) if (bit(mask, i)) sub[n++] = c->ext[i];
+    memcpy(c->keys + (size_t)slot * c->mw, mask, c->mw * 8);
+    c->inst[slot] = oracle_dpor_open(c->cfg, sub, n, c->P, c->opts);
+    free(sub);
+    if (!c->inst[slot]) { c->error = 1; return 0; }
+    c->n_inst++;
+  }
+  demi_dpor_result r;
+  oracle_dpor_test(c->inst[slot], c->max_distance, &r, 0, 0, 0, 0);              /* setMaxDistance; test :115-116 */
+  if (r.status) c->error = 1;
+  c->interleavings += r.interleavings; c->dpor_tests++;
+  return r.violations > 0;
+}
+
+/* IncrementalDDMin.minimize (IncrementalDeltaDebugging.scala:49-77).  `dag` = the externals to minimise
+ * (Start/Send only).  iteration sizes are merged as mergeStats (:33-41) does: keyed by replay count. */
+int oracle_incremental_ddmin(const demi_config* cfg, const demi_ext_event* ext, uint32_t n_ext,
+                             const demi_dpor_params* P, const oracle_dpor_opts* opts,
+                             int32_t max_max_distance, uint32_t stop_at_size, uint32_t cap_instances,
+                             uint64_t* mcs, uint32_t mw, uint32_t* total_replays, uint32_t* rounds,
+                             uint64_t* total_interleavings, uint32_t* n_instances, uint32_t* mcs_sizes, uint32_t cap_sizes) {
+  if (mw > MW_MAX) return -3;
+  rdpor_ctx c; memset(&c, 0, sizeof(c));
+  c.cfg = cfg; c.ext = ext; c.n_ext = n_ext; c.mw = mw; c.P = P; c.opts = opts;
+  c.cap_inst = cap_instances; c.keys = (uint64_t*)calloc((size_t)cap_instances * mw, 8); c.inst = (void**)calloc(cap_instances, sizeof(void*));
+  uint64_t cur[MW_MAX], next[MW_MAX];
+  initial_dag(ext, n_ext, cur, mw);
+  int32_t dist = 0; uint32_t total = 0, nr = 0; int rc = 0;
+  c.max_distance = dist;                                                        /* oracle.setMaxDistance(currentDistance) :53 */
+  while (dist < max_max_distance && popcount_mask(cur, mw) > stop_at_size) {    /* :66 */
+    ddmin_t d; memset(&d, 0, sizeof(d));
+    d.ext = ext; d.n_ext = n_ext; d.mw = mw; d.test = rdpor_test; d.ctx = &c;
+    rc = ddmin_minimize(&d, cur, 0, next);                                      /* new DDMin(oracle, checkUnmodifed=false) :68-69 */
+    if (rc || c.error) break;
+    memcpy(cur, next, mw * 8);
+    total += d.total_replays;                                                   /* mergeStats :33-41 */
+    if (mcs_sizes && nr < cap_sizes) mcs_sizes[nr] = popcount_mask(cur, mw);
+    nr++;
+    dist = dist == 0 ? 2 : dist << 1;                                           /* :72 */
+    c.max_distance = dist;
+  }
+  memcpy(mcs, cur, mw * 8);
+  if (total_replays) *total_replays = total;
+  if (rounds) *rounds = nr;
+  if (total_interleavings) *total_interleavings = c.interleavings;
+  if (n_instances) *n_instances = c.n_inst;
+  for (uint32_t i = 0; i < c.n_inst; i++) oracle_dpor_close(c.inst[i]);
+  free(c.keys); free(c.inst);
+  if (c.error) return -4;
+  return rc;
+}
+
 /* batch of independent STS tests (CPU baseline for the replay workload) */
 #include <pthread.h>
 typedef struct { const demi_config* cfg; const demi_replay_input* in; const uint64_t* masks; uint32_t mw;

@@ -22,6 +22,15 @@
  * A search that finds a violation and is resumed by calling test() again
  * (:1219-1221) continues exactly as if it had not stopped; `stop_if_found`
  * selects between the two.
+ *
+ * oracle_dpor_open / oracle_dpor_test / oracle_dpor_close keep one DPORwHeuristics
+ * instance alive across test() calls, which is what ResumableDPOR
+ * (IncrementalDeltaDebugging.scala:90-122) relies on, and add the configuration of
+ * RunnerUtils.editDistanceDporDDMin (RunnerUtils.scala:822-835): setInitialDepGraph
+ * / setInitialTrace (:210-217), prioritizePendingUponDivergence (:65-68, :542-555),
+ * ArvindDistanceOrdering (BacktrackOrdering.scala:99-173) and setMaxDistance
+ * (:128-134, :1145-1146).  With a distance cap the enqueue-time explored filter is
+ * off, because getNext inspects the head of the queue before it filters (:1144-1160).
  */
 #include <stdlib.h>
 #include <string.h>
@@ -32,7 +41,7 @@
 #define DP_MAX_T 1024
 
 typedef struct { demi_msg msg; uint32_t parent; uint16_t depth; } dnode;
-typedef struct { uint32_t branch, seq, e1, e2, trace_ref, later_i; } bkey;
+typedef struct { uint32_t branch, seq, e1, e2, trace_ref, later_i, dist, earlier_i; } bkey;
 
 typedef struct {
   om_machine m;                         /* actor states, registry/cancelled sets, model hooks */
@@ -54,6 +63,14 @@ typedef struct {
   uint32_t next_trace[DP_MAX_T]; uint32_t next_len, next_pos;
   int32_t nsched;
   int status;
+  /* instance state that survives test() calls */
+  demi_dpor_params params;
+  demi_ext_event* ext; uint32_t n_ext;
+  oracle_dpor_opts opts;
+  int32_t* orig_index;                  /* ArvindDistanceOrdering.originalIndices: node -> index in originalTrace, -1 absent */
+  int started, found;                   /* found: shortestTraceSoFar != null */
+  int32_t max_distance;                 /* stop_at_distance; < 0: should_cap_distance = false */
+  uint32_t* path;                       /* scratch for arvindDistance */
 } dpor_t;
 
 static __thread dpor_t* g_dpor = 0;
@@ -173,8 +190,17 @@ static void explored_add(dpor_t* d, uint32_t a, uint32_t b) {
 
 /* ------------------------------------------------------------------- heap */
 static int key_before(const bkey* a, const bkey* b) {    /* a is served before b */
+  /* ArvindDistanceOrdering.getOrdered (BacktrackOrdering.scala:153-163): the LARGER distance compares
+   * higher and PriorityQueue serves the maximum; `dist` is 0 for DefaultBacktrackOrdering */
+  if (a->dist != b->dist) return a->dist > b->dist;
   if (a->branch != b->branch) return a->branch > b->branch;   /* deeper first (DefaultBacktrackOrdering) */
-  return a->seq < b->seq;                                      /* canonical FIFO among ties */
+  /* canonical order among ties: first-in first-out.  Keys are enqueued in (interleaving, later position,
+   * earlier position) order, so that triple is the sequence number; a key that a resumed test() enqueues a
+   * second time (:1219-1220) sorts next to its first copy, which no explored schedule can observe */
+  if (a->trace_ref != b->trace_ref) return a->trace_ref < b->trace_ref;
+  if (a->later_i != b->later_i) return a->later_i < b->later_i;
+  if (a->earlier_i != b->earlier_i) return a->earlier_i < b->earlier_i;
+  return a->seq < b->seq;
 }
 static void heap_push(dpor_t* d, bkey k) {
   if (d->n_heap >= d->cap_heap) { d->status = DEMI_DS_HEAP_OVF; return; }
@@ -211,9 +237,12 @@ static uint32_t dpor_schedule(dpor_t* d) {
     d->nsched++;                                            /* :583-586 */
     if (d->P->max_messages >= 0 && d->nsched > d->P->max_messages) return 0;
     uint32_t pick = 0;
-    /* getMatchingMessage :474-537 via getNextTraceMessage :363-372 (id 0 entries skipped) */
-    while (d->next_pos < d->next_len && d->next_trace[d->next_pos] == 0) d->next_pos++;
-    if (d->next_pos < d->next_len) {
+    /* getMatchingMessage :474-537 via getNextTraceMessage :363-372 (id 0 entries skipped); with
+     * prioritizePendingUponDivergence, getNextMatchingMessage (:542-555) keeps popping nextTrace until an
+     * expected message is pending */
+    do {
+      while (d->next_pos < d->next_len && d->next_trace[d->next_pos] == 0) d->next_pos++;
+      if (d->next_pos >= d->next_len) break;
       uint32_t want = d->next_trace[d->next_pos++];
       const demi_msg* c = &d->nodes[want].msg;
       if (!((d->m.blocked_mask >> c->dst) & 1u)) {
@@ -226,7 +255,7 @@ static uint32_t dpor_schedule(dpor_t* d) {
             break;
           }
       }
-    }
+    } while (!pick && d->opts.prioritize_pending);
     if (!pick) {                                            /* divergent: getPendingEvent :452-472 */
       for (uint32_t q = 0; q < nq; q++) {
         uint32_t dst = q % DEMI_MAX_ACTORS;
@@ -301,17 +330,84 @@ static uint64_t schedule_hash(const dpor_t* d, const uint32_t* tr, uint32_t len)
   return h;
 }
 
-int oracle_dpor_search(const demi_config* cfg, const demi_ext_event* ext, uint32_t n_ext,
-                       const demi_dpor_params* P, demi_dpor_result* out,
-                       demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* interleaving_hashes, uint32_t cap_hashes) {
+/* ArvindDistanceOrdering.arvindDistance (BacktrackOrdering.scala:119-146): path = the dependency path root..e1
+ * (getCommonPrefix(e1, e1)) ++ replayThis ++ [e1, e2]; +1 per event that is not in the original trace, +1 per
+ * earlier path element that the original trace orders after it */
+uint32_t oracle_arvind_distance_of(const int32_t* oi, uint32_t n) {
+  uint32_t dist = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (oi[i] < 0) { dist++; continue; }                      /* "Not in original" :133-135 */
+    for (uint32_t j = 0; j < i; j++) if (oi[j] >= 0 && oi[j] > oi[i]) dist++;   /* "Reordered" :137-142 */
+  }
+  return dist;
+}
+static uint32_t arvind_distance(dpor_t* d, const bkey* k) {
+  uint32_t n = 0, depth = d->nodes[k->e1].depth;
+  uint32_t* path = d->path;
+  for (uint32_t v = k->e1, i = depth + 1; i-- > 0; v = d->nodes[v].parent) path[i] = v;
+  n = depth + 1;
+  const uint32_t* kt = d->traces + (size_t)k->trace_ref * d->T1;
+  for (uint32_t i = k->branch + 1; i <= k->later_i; i++) if (kt[i] != k->e2) path[n++] = kt[i];
+  path[n++] = k->e1; path[n++] = k->e2;
+  int32_t* oi = (int32_t*)path;
+  for (uint32_t i = 0; i < n; i++) oi[i] = path[i] < d->opts.n_init_nodes ? d->orig_index[path[i]] : -1;
+  return oracle_arvind_distance_of(oi, n);
+}
+
+/* dpor(trace) :1020-1185: race scan over the last trace (index k in d->traces), then getNext.  Returns 1 and
+ * fills next_trace, or 0 for None. */
+static int dpor_analyse(dpor_t* d, uint32_t k, demi_dpor_result* out) {
+  const demi_dpor_params* P = &d->params;
+  const uint32_t* tr = d->traces + (size_t)k * d->T1; const uint32_t n = d->trace_len[k];
+  const int capped = d->max_distance >= 0;
+  for (uint32_t li = 1; li < n && !d->status; li++)
+    for (uint32_t ei = 1; ei < li && !d->status; ei++) {
+      uint32_t later = tr[li], earlier = tr[ei];
+      if (d->nodes[later].msg.dst != d->nodes[earlier].msg.dst) continue;       /* isCoEnabeled :1096 */
+      if (is_ancestor(d, earlier, later)) continue;                              /* :1104-1107 */
+      uint32_t l = lca(d, earlier, later);
+      uint32_t branch = 0;
+      while (branch < n && tr[branch] != l) branch++;                            /* indexWhere :1058 */
+      explored_add(d, earlier, later);                                           /* :1071-1073 */
+      out->races++;
+      if (!capped && explored_has(d, later, earlier)) continue;   /* would be skipped when popped (:1156-1160) */
+      bkey key = { branch, d->seq++, later, earlier, k, li, 0, ei };
+      if (d->opts.arvind) key.dist = arvind_distance(d, &key);
+      heap_push(d, key);                                                         /* :1134 */
+    }
+  if (d->status) return 0;
+  /* getNext :1142-1162 */
+  bkey key;
+  for (;;) {
+    if (!d->n_heap) { out->exhausted = 1; return 0; }
+    if (capped && (int32_t)(d->opts.arvind ? d->heap[0].dist : 0u) >= d->max_distance) return 0;   /* :1145-1146 */
+    if (P->stop_if_found && d->found) return 0;                                  /* :1147 */
+    key = heap_pop(d);
+    if (!explored_has(d, key.e1, key.e2)) break;
+  }
+  explored_add(d, key.e1, key.e2);                                               /* :1169-1171 */
+  if (d->status) return 0;
+  /* nextTrace = trace.take(maxIndex+1) ++ replayThis (:1180); replayThis =
+   * keyTrace.drop(branchI+1).dropRight(size-laterI-1).filter(_.id != earlier.id) (:1060-1063) */
+  d->next_len = 0; d->next_pos = 0;
+  for (uint32_t i = 0; i <= key.branch && i < n; i++) d->next_trace[d->next_len++] = tr[i];
+  const uint32_t* kt = d->traces + (size_t)key.trace_ref * d->T1;
+  for (uint32_t i = key.branch + 1; i <= key.later_i; i++)
+    if (kt[i] != key.e2) d->next_trace[d->next_len++] = kt[i];
+  return 1;
+}
+
+void* oracle_dpor_open(const demi_config* cfg, const demi_ext_event* ext, uint32_t n_ext,
+                       const demi_dpor_params* P, const oracle_dpor_opts* opts) {
   const oracle_model* model = oracle_get_model(cfg->model);
-  memset(out, 0, sizeof(*out));
-  if (!model) return DEMI_ERR_INVALID;
+  if (!model) return 0;
   for (uint32_t i = 0; i < n_ext; i++)
-    if (ext[i].kind != DEMI_EXT_START && ext[i].kind != DEMI_EXT_SEND) return DEMI_ERR_INVALID;  /* "unsuported external event" :710 */
-  if (P->max_messages + 2 > DP_MAX_T) return DEMI_ERR_INVALID;
+    if (ext[i].kind != DEMI_EXT_START && ext[i].kind != DEMI_EXT_SEND) return 0;  /* "unsuported external event" :710 */
+  if (P->max_messages + 2 > DP_MAX_T) return 0;
   dpor_t* d = (dpor_t*)calloc(1, sizeof(dpor_t));
-  d->P = P;
+  d->params = *P; d->P = &d->params;
+  d->ext = (demi_ext_event*)malloc(sizeof(demi_ext_event) * (n_ext + 1)); memcpy(d->ext, ext, sizeof(demi_ext_event) * n_ext); d->n_ext = n_ext;
+  if (opts) d->opts = *opts;
   d->m.model = model; d->m.model_flags = cfg->model_flags; d->m.blocked_mask = cfg->blocked_mask; d->m.ignore_timers = cfg->ignore_timers;
   d->cap_nodes = P->node_cap; d->nodes = (dnode*)calloc(d->cap_nodes, sizeof(dnode)); d->n_nodes = 1;
   d->explored_slots = P->explored_slots; d->explored = (uint64_t*)malloc(8ull * d->explored_slots);
@@ -321,65 +417,92 @@ int oracle_dpor_search(const demi_config* cfg, const demi_ext_event* ext, uint32
   d->cap_traces = P->max_interleavings + 1;
   d->traces = (uint32_t*)malloc(4ull * d->cap_traces * d->T1);
   d->trace_len = (uint32_t*)malloc(4ull * d->cap_traces);
-  g_dpor = d;
-  d->next_len = d->next_pos = 0;
+  d->path = (uint32_t*)malloc(4ull * (d->cap_nodes + 2 * DP_MAX_T + 4));
+  d->max_distance = -1;
+  /* setInitialDepGraph (:214-217): the instance starts from the recorded execution's graph */
+  if (d->opts.n_init_nodes) {
+    if (d->opts.n_init_nodes > d->cap_nodes) { d->status = DEMI_DS_NODE_OVF; return d; }
+    d->orig_index = (int32_t*)malloc(4ull * d->opts.n_init_nodes);
+    for (uint32_t i = 0; i < d->opts.n_init_nodes; i++) {
+      const uint32_t* w = d->opts.init_nodes + 4 * (size_t)i;
+      d->nodes[i].msg.src = (uint8_t)(w[0] & 0xFF); d->nodes[i].msg.dst = (uint8_t)((w[0] >> 8) & 0xFF);
+      d->nodes[i].msg.type = (uint8_t)((w[0] >> 16) & 0xFF); d->nodes[i].msg.flags = 0;
+      d->nodes[i].msg.p0 = w[1]; d->nodes[i].msg.p1 = w[2];
+      d->nodes[i].parent = i ? w[3] : 0;
+      d->nodes[i].depth = i ? (uint16_t)(d->nodes[w[3]].depth + 1) : 0;
+      d->orig_index[i] = -1;
+    }
+    d->n_nodes = d->opts.n_init_nodes;
+    /* ArvindDistanceOrdering.init (BacktrackOrdering.scala:110-116): later occurrences overwrite */
+    for (uint32_t i = 0; i < d->opts.n_init_trace; i++)
+      if (d->opts.init_trace[i] < d->opts.n_init_nodes) d->orig_index[d->opts.init_trace[i]] = (int32_t)i;
+  }
+  return d;
+}
+
+void oracle_dpor_close(void* s) {
+  dpor_t* d = (dpor_t*)s;
+  if (!d) return;
+  free(d->nodes); free(d->explored); free(d->heap); free(d->traces); free(d->trace_len); free(d->ext);
+  free(d->orig_index); free(d->path); free(d);
+}
+
+/* One DPORwHeuristics.test (:1193-1242) on a live instance.  max_distance < 0: no setMaxDistance.
+ * Returns DEMI_OK / DEMI_ERR_CAPACITY; out->violations > 0 <=> Some(trace). */
+int oracle_dpor_test(void* s, int32_t max_distance, demi_dpor_result* out,
+                     demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* interleaving_hashes, uint32_t cap_hashes) {
+  dpor_t* d = (dpor_t*)s;
+  const demi_dpor_params* P = &d->params;
+  memset(out, 0, sizeof(*out));
   uint32_t n_viol = 0;
-  for (;;) {
-    uint32_t v = dpor_run_interleaving(d, ext, n_ext);
+  d->max_distance = max_distance;
+  g_dpor = d;
+  if (d->status) goto finish;
+  if (P->stop_if_found && d->found) { n_viol = 1; goto finish; }                 /* "Already have shortestTrace!" :1197-1201 */
+  if (d->n_traces >= P->max_interleavings) { out->budget_exhausted = 1; goto finish; }   /* engine budget, not in the reference */
+  /* initialTrace :1219-1221 */
+  d->next_len = d->next_pos = 0;
+  if (d->started && d->n_heap) {
+    if (!dpor_analyse(d, d->n_traces - 1, out)) d->next_len = 0;                 /* None: run() clears nextTrace :757-759 */
+  } else if (d->opts.n_init_trace) {
+    for (uint32_t i = 0; i < d->opts.n_init_trace && i < DP_MAX_T; i++) d->next_trace[d->next_len++] = d->opts.init_trace[i];
+  }
+  d->started = 1;
+  out->exhausted = 0;
+  while (!d->status) {
+    uint32_t v = dpor_run_interleaving(d, d->ext, d->n_ext);
     if (d->status) break;
     uint32_t k = d->n_traces++;
     memcpy(d->traces + (size_t)k * d->T1, d->cur_trace, 4ull * d->cur_len);
     d->trace_len[k] = d->cur_len;
     uint64_t sh = schedule_hash(d, d->cur_trace, d->cur_len);
-    if (interleaving_hashes && k < cap_hashes) interleaving_hashes[k] = sh;
+    if (interleaving_hashes && out->interleavings < cap_hashes) interleaving_hashes[out->interleavings] = sh;
     out->interleavings++;
     out->deliveries += d->cur_len - 1;
     if (v) {
       if (viol && n_viol < cap_viol) { viol[n_viol].schedule_hash = sh; viol[n_viol].interleaving = k; viol[n_viol].length = d->cur_len - 1; viol[n_viol].code = v; }
       n_viol++;
-      if (P->stop_if_found) break;                              /* test() returns Some(trace) :1236-1238 */
+      d->found = 1;                                                              /* checkInvariant :404-410 */
+      if (P->stop_if_found) break;                                              /* test() returns Some(trace) :1236-1238 */
     }
-    if (out->interleavings >= P->max_interleavings) { out->budget_exhausted = 1; break; }
-    /* dpor(currentTrace) :1020-1185 — race scan */
-    const uint32_t* tr = d->cur_trace; const uint32_t n = d->cur_len;
-    for (uint32_t li = 1; li < n && !d->status; li++)
-      for (uint32_t ei = 1; ei < li && !d->status; ei++) {
-        uint32_t later = tr[li], earlier = tr[ei];
-        if (d->nodes[later].msg.dst != d->nodes[earlier].msg.dst) continue;       /* isCoEnabeled :1096 */
-        if (is_ancestor(d, earlier, later)) continue;                              /* :1104-1107 */
-        uint32_t l = lca(d, earlier, later);
-        uint32_t branch = 0;
-        while (branch < n && tr[branch] != l) branch++;                            /* indexWhere :1058 */
-        explored_add(d, earlier, later);                                           /* :1071-1073 */
-        out->races++;
-        if (explored_has(d, later, earlier)) continue;      /* would be skipped when popped (:1156-1160) */
-        bkey key = { branch, d->seq++, later, earlier, k, li };
-        heap_push(d, key);                                                         /* :1134 */
-      }
-    if (d->status) break;
-    /* getNext :1142-1162 */
-    int have = 0; bkey key;
-    while (d->n_heap) {
-      key = heap_pop(d);
-      if (explored_has(d, key.e1, key.e2)) continue;
-      have = 1; break;
-    }
-    if (!have) { out->exhausted = 1; break; }
-    explored_add(d, key.e1, key.e2);                                               /* :1169-1171 */
-    if (d->status) break;
-    /* nextTrace = trace.take(maxIndex+1) ++ replayThis (:1180); replayThis =
-     * keyTrace.drop(branchI+1).dropRight(size-laterI-1).filter(_.id != earlier.id) (:1060-1063) */
-    d->next_len = 0; d->next_pos = 0;
-    for (uint32_t i = 0; i <= key.branch && i < n; i++) d->next_trace[d->next_len++] = tr[i];
-    const uint32_t* kt = d->traces + (size_t)key.trace_ref * d->T1;
-    for (uint32_t i = key.branch + 1; i <= key.later_i; i++)
-      if (kt[i] != key.e2) d->next_trace[d->next_len++] = kt[i];
+    if (d->n_traces >= P->max_interleavings) { out->budget_exhausted = 1; break; }
+    if (!dpor_analyse(d, k, out)) break;
   }
+finish:
   g_dpor = 0;
   out->violations = n_viol;
   out->n_nodes = d->n_nodes; out->n_explored = d->n_explored; out->heap_left = d->n_heap;
   out->status = (uint32_t)d->status;
-  int rc = d->status ? DEMI_ERR_CAPACITY : DEMI_OK;
-  free(d->nodes); free(d->explored); free(d->heap); free(d->traces); free(d->trace_len); free(d);
+  return d->status ? DEMI_ERR_CAPACITY : DEMI_OK;
+}
+
+int oracle_dpor_search(const demi_config* cfg, const demi_ext_event* ext, uint32_t n_ext,
+                       const demi_dpor_params* P, demi_dpor_result* out,
+                       demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* interleaving_hashes, uint32_t cap_hashes) {
+  memset(out, 0, sizeof(*out));
+  void* s = oracle_dpor_open(cfg, ext, n_ext, P, 0);
+  if (!s) return DEMI_ERR_INVALID;
+  int rc = oracle_dpor_test(s, -1, out, viol, cap_viol, interleaving_hashes, cap_hashes);
+  oracle_dpor_close(s);
   return rc;
 }

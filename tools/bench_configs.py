@@ -158,6 +158,36 @@ def provenance():
                              "sample": "%d executions, literal pair-set closure, one core" % nc}}
 
 
+def incddmin():
+    """§8(f) rank 2: IncrementalDDMin over ResumableDPOR (RunnerUtils.editDistanceDporDDMin)."""
+    eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    prog = D.raft5_program(client_cmds=6)
+    eng.set_externals(prog)
+    ext_all = D.pack_externals(prog)
+    dext = ext_all[(ext_all["kind"] == 1) | (ext_all["kind"] == 3)]
+    res = eng.fuzz_batch(1, 20000, 60, 5)
+    viol = np.nonzero(res["violation"] == 1)[0]
+    rows = []
+    for i in viol[:8]:
+        ev, par, r = eng.fuzz_trace(1 + int(i), 60, 5)
+        steps = int(r["steps"])
+        t0 = time.perf_counter()
+        mcs, out = eng.incremental_ddmin(dext, steps, 4000, (ev, par), looking_for=1, stop_at_size=1, max_max_distance=64,
+                                         heap_cap=1 << 17)
+        gt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rc, mcs_o, st = O.incremental_ddmin(N.MODEL_RAFT5, dext, steps, 4000, O.dpor_seed(ev, par), model_flags=1,
+                                            looking_for=1, stop_at_size=1, max_max_distance=64)
+        ct = time.perf_counter() - t0
+        rows.append({"prefix": int(i), "deliveries": steps, "externals": int(len(dext)), "mcs": int(out.mcs_size),
+                     "identical_to_sequential_oracle": bool(rc == 0 and np.array_equal(mcs, mcs_o) and out.total_replays == st["total_replays"]),
+                     "sequential_tests": int(out.total_replays), "tests_on_gpu": int(out.tests_executed),
+                     "batches": int(out.batches), "interleavings_on_gpu": int(out.interleavings_executed),
+                     "oracle_interleavings": int(st["interleavings"]), "gpu_s": gt, "cpu_oracle_s": ct})
+    return {"config": "IncrementalDDMin(ResumableDPOR, ArvindDistanceOrdering) on violating raft5 executions, caps 0..32",
+            "metric": "minimisations", "rows": rows}
+
+
 def config5_bcast():
     """bcast32 depth-200 fuzz with state-hash dedup + compaction."""
     eng = D.Engine(D.SchedulerConfig(N.MODEL_BCAST32))
@@ -214,5 +244,5 @@ def config5_bcast():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c4", "c3", "c5"]
     for w in which:
-        fn = {"c4": config4_ddmin, "c3": config3_dpor, "c5": config5_bcast, "prov": provenance}[w]
+        fn = {"c4": config4_ddmin, "c3": config3_dpor, "c5": config5_bcast, "prov": provenance, "incddmin": incddmin}[w]
         print(json.dumps(fn()), flush=True)
