@@ -5,4 +5,5 @@ from .events import (Start, Kill, Send, WaitQuiescence, Partition, UnPartition, 
                      pack_externals, unpack_externals, raft5_program, pingpong3_program, bcast32_program)
 from .schedulers import (DemiError, SchedulerConfig, Engine, RandomScheduler, STSScheduler, ReplayScheduler,  # noqa: F401
                          DDMin, MinimizationStats, DPORwHeuristics, STSSchedMinimizer, LeftToRightOneAtATime,
-                         ProvenanceTracker, mask_of, events_of)
+                         ProvenanceTracker, ResumableDPOR, IncrementalDDMin, ArvindDistanceOrdering,
+                         DefaultBacktrackOrdering, mask_of, events_of)

@@ -501,6 +501,86 @@ class DPORwHeuristics(object):
         return viol[0][0] if res[0]["violations"] else None
 
 
+class DefaultBacktrackOrdering(object):
+    """Deeper backtrack points first (schedulers/BacktrackOrdering.scala:58-69)."""
+    pass
+
+
+class ArvindDistanceOrdering(object):
+    """Backtrack points ordered by their edit distance from the original trace
+    (schedulers/BacktrackOrdering.scala:99-173); init() is given the recorded execution."""
+
+    def __init__(self):
+        self.original = None
+
+    def init(self, events, dep_parent):
+        self.original = (events, dep_parent)
+
+
+class ResumableDPOR(object):
+    """One DPORwHeuristics per external-event subsequence (minification/IncrementalDeltaDebugging.scala:90-122),
+    configured as RunnerUtils.editDistanceDporDDMin does (RunnerUtils.scala:822-835): seeded with the recorded
+    execution's dependency graph and trace, ArvindDistanceOrdering, prioritizePendingUponDivergence.
+
+    An instance's state is a function of the distance caps it has been tested with, so the engine keeps that list
+    per subsequence and replays it — test() is side-effect free on the device."""
+
+    def __init__(self, schedulerConfig, events, dep_parent, max_messages=None, max_interleavings=1000, engine=None,
+                 backtrackHeuristic=None, prioritizePendingUponDivergence=True):
+        self.engine = engine or Engine(schedulerConfig)
+        self.seed = (events, dep_parent)
+        self.max_messages = max_messages if max_messages is not None else int((np.asarray(events)["kind"] == N.EV_MSG_EVENT).sum()) + 1
+        self.max_interleavings = max_interleavings
+        heuristic = backtrackHeuristic if backtrackHeuristic is not None else ArvindDistanceOrdering()
+        self.flags = (N.DF_ARVIND_ORDERING if isinstance(heuristic, ArvindDistanceOrdering) else 0) | \
+                     (N.DF_PRIORITIZE_PENDING if prioritizePendingUponDivergence else 0)
+        self.currentMaxDistance = 0
+        self.subseqToDPOR = {}            # ids of the subsequence's events -> caps tested so far
+
+    def getName(self):
+        return "DPOR"
+
+    def setMaxDistance(self, dist):
+        self.currentMaxDistance = dist
+
+    def test(self, events, violation_fingerprint, stats=None):
+        prog = [e for e in events if e.kind in (N.EXT_START, N.EXT_SEND)]
+        key = tuple(e._id for e in prog)
+        caps = self.subseqToDPOR.setdefault(key, [])
+        caps.append(self.currentMaxDistance)
+        res, _ = self.engine.dpor_batch_ex([prog], self.max_messages, self.max_interleavings, seed=self.seed,
+                                           flags=self.flags, caps=[caps], looking_for=violation_fingerprint)
+        if res[0]["status"]:
+            raise DemiError(N.ERR_CAPACITY, "DPOR instance status %d" % res[0]["status"])
+        if stats is not None:
+            stats.increment_replays()
+        return bool(res[0]["violations"])
+
+
+class IncrementalDDMin(object):
+    """IncrementalDDMin(oracle: ResumableDPOR, maxMaxDistance, stopAtSize) —
+    minification/IncrementalDeltaDebugging.scala:20-88.  minimize() runs DDMin under distance caps 0, 2, 4, ...;
+    the DPOR tests a round may need are evaluated speculatively in batches, the decisions are the sequential ones."""
+
+    def __init__(self, oracle, maxMaxDistance=256, stopAtSize=1, stats=None):
+        self.oracle, self.maxMaxDistance, self.stopAtSize = oracle, maxMaxDistance, stopAtSize
+        self._stats = stats or MinimizationStats()
+        self.last = None
+
+    def minimize(self, events, violation_fingerprint):
+        prog = [e for e in events if e.kind in (N.EXT_START, N.EXT_SEND)]
+        o = self.oracle
+        mcs, out = o.engine.incremental_ddmin(prog, o.max_messages, o.max_interleavings, o.seed,
+                                              looking_for=violation_fingerprint, max_max_distance=self.maxMaxDistance,
+                                              stop_at_size=self.stopAtSize, flags=o.flags)
+        self.last = out
+        self._stats.increment_replays(out.total_replays)
+        return [e for i, e in enumerate(prog) if (int(mcs[i >> 6]) >> (i & 63)) & 1]
+
+    def verify_mcs(self, mcs, violation_fingerprint):
+        return self.oracle.test(mcs, violation_fingerprint)
+
+
 class LeftToRightOneAtATime(object):
     """RemovalStrategy that ignores deliveries one at a time, left to right
     (minification/internal_minimization/OneAtATimeRemoval.scala:131-137)."""

@@ -22,6 +22,7 @@
 // CUDA device the constructors throw demi::Error(DEMI_ERR_NO_DEVICE).
 #pragma once
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -316,6 +317,67 @@ class DPORwHeuristics {
   demi_dpor_result last{};
  private:
   std::shared_ptr<Engine> engine; int32_t depth_bound; bool stop; uint32_t budget; int32_t max_messages = -1;
+};
+
+// ResumableDPOR (minification/IncrementalDeltaDebugging.scala:90-122) in RunnerUtils.editDistanceDporDDMin's
+// configuration (RunnerUtils.scala:822-835): every instance starts from the recorded execution's dependency graph
+// and trace, orders backtrack points by ArvindDistanceOrdering and prioritises pending messages on divergence.
+// An instance's state is a function of the caps it has been tested with; that list is what is kept per subsequence.
+class ResumableDPOR {
+ public:
+  ResumableDPOR(const SchedulerConfig& cfg, EventTrace trace, std::vector<uint16_t> depGraph, int32_t max_messages,
+                uint32_t max_interleavings = 1000, std::shared_ptr<Engine> e = nullptr,
+                uint32_t flags = DEMI_DF_ARVIND_ORDERING | DEMI_DF_PRIORITIZE_PENDING)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), trace(std::move(trace)), depGraph(std::move(depGraph)),
+        max_messages(max_messages), budget(max_interleavings), flags(flags) {}
+  std::string getName() const { return "DPOR"; }
+  void setMaxDistance(int32_t d) { currentMaxDistance = d; }
+  demi_dpor_seed seed() const { return demi_dpor_seed{trace.data(), (uint32_t)trace.size(), depGraph.data(), (uint32_t)depGraph.size()}; }
+  demi_dpor_params params(ViolationFingerprint fp) const { return demi_dpor_params{max_messages, -1, budget, fp, 1u, 4096, 1u << 16, 1u << 16}; }
+  // Some(trace) <=> true (:102-121)
+  bool test(const ExternalEvents& events, ViolationFingerprint fp, MinimizationStats* stats = nullptr) {
+    ExternalEvents prog; std::vector<uint32_t> key;
+    for (const demi_ext_event& e : events) if (e.kind == DEMI_EXT_START || e.kind == DEMI_EXT_SEND) { prog.push_back(e); key.push_back(e.id); }
+    std::vector<int32_t>& caps = subseqToDPOR[key];
+    caps.push_back(currentMaxDistance);
+    const uint32_t offs[2] = {0, (uint32_t)prog.size()}, coffs[2] = {0, (uint32_t)caps.size()};
+    const demi_dpor_seed sd = seed();
+    const demi_dpor_params P = params(fp);
+    const demi_dpor_ex ex{flags, &sd, caps.data(), coffs};
+    engine->check(demi_dpor_batch_ex(engine->handle(), prog.data(), offs, 1, &P, &ex, &last, nullptr, 0, nullptr, 0));
+    if (last.status) throw Error(DEMI_ERR_CAPACITY, "DPOR instance reported a capacity status");
+    if (stats) stats->increment_replays();
+    return last.violations != 0;
+  }
+  std::shared_ptr<Engine> engine;
+  demi_dpor_result last{};
+  uint32_t flags_value() const { return flags; }
+ private:
+  EventTrace trace; std::vector<uint16_t> depGraph; int32_t max_messages; uint32_t budget, flags;
+  int32_t currentMaxDistance = 0;
+  std::map<std::vector<uint32_t>, std::vector<int32_t>> subseqToDPOR;
+};
+
+// IncrementalDDMin(oracle, maxMaxDistance, stopAtSize) (minification/IncrementalDeltaDebugging.scala:20-88)
+class IncrementalDDMin {
+ public:
+  IncrementalDDMin(ResumableDPOR& oracle, int32_t maxMaxDistance = 256, uint32_t stopAtSize = 1, MinimizationStats* stats = nullptr)
+      : oracle(oracle), maxMaxDistance(maxMaxDistance), stopAtSize(stopAtSize), stats(stats) {}
+  ExternalEvents minimize(const ExternalEvents& events, ViolationFingerprint fp) {
+    ExternalEvents prog;
+    for (const demi_ext_event& e : events) if (e.kind == DEMI_EXT_START || e.kind == DEMI_EXT_SEND) prog.push_back(e);
+    std::vector<uint64_t> mcs((prog.size() + 63) / 64 ? (prog.size() + 63) / 64 : 1, 0);
+    const demi_dpor_seed sd = oracle.seed();
+    const demi_dpor_params P = oracle.params(fp);
+    oracle.engine->check(demi_incremental_ddmin(oracle.engine->handle(), prog.data(), (uint32_t)prog.size(), &P, oracle.flags_value(),
+                                                &sd, maxMaxDistance, stopAtSize, mcs.data(), (uint32_t)mcs.size(), &last));
+    if (stats) stats->increment_replays(last.total_replays);
+    return events_of(prog, mcs);
+  }
+  bool verify_mcs(const ExternalEvents& mcs, ViolationFingerprint fp) { return oracle.test(mcs, fp); }
+  demi_incddmin_out last{};
+ private:
+  ResumableDPOR& oracle; int32_t maxMaxDistance; uint32_t stopAtSize; MinimizationStats* stats;
 };
 
 }  // namespace demi

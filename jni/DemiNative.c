@@ -58,3 +58,65 @@ JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_ddmin(JNIEnv* 
 JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_stats(JNIEnv* env, jclass c, jlong h, jobject out) {
   return demi_stats(H(h), (demi_perf*)BUF(env, out));
 }
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_replayBatchEx(JNIEnv* env, jclass c, jlong h, jobject masks,
+    jobject skipEvents, jint nTests, jint maskWords, jint lookingFor, jint flags, jobject out) {
+  return demi_replay_batch_ex(H(h), masks ? (const uint64_t*)BUF(env, masks) : 0, skipEvents ? (const uint32_t*)BUF(env, skipEvents) : 0,
+                              (uint32_t)nTests, (uint32_t)maskWords, (uint32_t)lookingFor, (uint32_t)flags,
+                              (demi_replay_result*)BUF(env, out));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_replayTrace(JNIEnv* env, jclass c, jlong h, jobject mask, jint maskWords,
+    jint skipEvent, jint lookingFor, jint flags, jobject events, jint capEvents, jobject count /* u32 */, jobject result) {
+  return demi_replay_trace(H(h), (const uint64_t*)BUF(env, mask), (uint32_t)maskWords, (uint32_t)skipEvent, (uint32_t)lookingFor,
+                           (uint32_t)flags, (demi_event*)BUF(env, events), (uint32_t)capEvents, (uint32_t*)BUF(env, count),
+                           (demi_replay_result*)BUF(env, result));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_internalMinimize(JNIEnv* env, jclass c, jlong h, jint lookingFor,
+    jint flags, jobject events, jint capEvents, jobject sizes, jint capSizes, jobject out) {
+  return demi_internal_minimize(H(h), (uint32_t)lookingFor, (uint32_t)flags, (demi_event*)BUF(env, events), (uint32_t)capEvents,
+                                (uint32_t*)BUF(env, sizes), (uint32_t)capSizes, (demi_intmin_out*)BUF(env, out));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dporBatch(JNIEnv* env, jclass c, jlong h, jobject ext, jobject extOffsets,
+    jint nSearches, jobject params, jobject results, jobject viol, jint capViol) {
+  return demi_dpor_batch(H(h), (const demi_ext_event*)BUF(env, ext), (const uint32_t*)BUF(env, extOffsets), (uint32_t)nSearches,
+                         (const demi_dpor_params*)BUF(env, params), (demi_dpor_result*)BUF(env, results),
+                         viol ? (demi_dpor_violation*)BUF(env, viol) : 0, (uint32_t)capViol, 0, 0);
+}
+/* seed = {events, nEvents, depParent, nNodes}; caps / capOffsets may be null (one uncapped test per instance) */
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dporBatchEx(JNIEnv* env, jclass c, jlong h, jobject ext, jobject extOffsets,
+    jint nSearches, jobject params, jint flags, jobject seedEvents, jint nSeedEvents, jobject seedParents, jint nSeedNodes,
+    jobject caps, jobject capOffsets, jobject results) {
+  demi_dpor_seed seed = { seedEvents ? (const demi_event*)BUF(env, seedEvents) : 0, (uint32_t)nSeedEvents,
+                          seedParents ? (const uint16_t*)BUF(env, seedParents) : 0, (uint32_t)nSeedNodes };
+  demi_dpor_ex ex = { (uint32_t)flags, seedEvents ? &seed : 0, caps ? (const int32_t*)BUF(env, caps) : 0,
+                      capOffsets ? (const uint32_t*)BUF(env, capOffsets) : 0 };
+  return demi_dpor_batch_ex(H(h), (const demi_ext_event*)BUF(env, ext), (const uint32_t*)BUF(env, extOffsets), (uint32_t)nSearches,
+                            (const demi_dpor_params*)BUF(env, params), &ex, (demi_dpor_result*)BUF(env, results), 0, 0, 0, 0);
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_incrementalDdmin(JNIEnv* env, jclass c, jlong h, jobject externals,
+    jint nExternals, jobject params, jint flags, jobject seedEvents, jint nSeedEvents, jobject seedParents, jint nSeedNodes,
+    jint maxMaxDistance, jint stopAtSize, jobject mcsMask, jint maskWords, jobject out) {
+  demi_dpor_seed seed = { (const demi_event*)BUF(env, seedEvents), (uint32_t)nSeedEvents,
+                          (const uint16_t*)BUF(env, seedParents), (uint32_t)nSeedNodes };
+  return demi_incremental_ddmin(H(h), (const demi_ext_event*)BUF(env, externals), (uint32_t)nExternals,
+                                (const demi_dpor_params*)BUF(env, params), (uint32_t)flags, &seed, maxMaxDistance,
+                                (uint32_t)stopAtSize, (uint64_t*)BUF(env, mcsMask), (uint32_t)maskWords,
+                                (demi_incddmin_out*)BUF(env, out));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_provenance(JNIEnv* env, jclass c, jlong h, jobject events, jint nEvents,
+    jobject depParent, jint nNodes, jint affectedMask, jobject keepMask, jint maskWords, jobject out) {
+  return demi_provenance(H(h), (const demi_event*)BUF(env, events), (uint32_t)nEvents, (const uint16_t*)BUF(env, depParent),
+                         (uint32_t)nNodes, (uint32_t)affectedMask, (uint64_t*)BUF(env, keepMask), (uint32_t)maskWords,
+                         (demi_provenance_out*)BUF(env, out));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_fuzzProvenance(JNIEnv* env, jclass c, jlong h, jobject params,
+    jobject prefixIndex, jint n, jobject keepMasks, jint maskWords, jobject out, jobject results) {
+  return demi_fuzz_provenance(H(h), (const demi_fuzz_params*)BUF(env, params), (const uint32_t*)BUF(env, prefixIndex), (uint32_t)n,
+                              (uint64_t*)BUF(env, keepMasks), (uint32_t)maskWords, (demi_provenance_out*)BUF(env, out),
+                              results ? (demi_fuzz_result*)BUF(env, results) : 0);
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dedupCompact(JNIEnv* env, jclass c, jlong h, jobject results, jlong n,
+    jint mode, jobject outRecords, jobject outIndex, jobject outCount /* u64 */) {
+  return demi_dedup_compact(H(h), (const demi_fuzz_result*)BUF(env, results), (uint64_t)n, mode,
+                            (demi_fuzz_result*)BUF(env, outRecords), outIndex ? (uint32_t*)BUF(env, outIndex) : 0,
+                            (uint64_t*)BUF(env, outCount));
+}

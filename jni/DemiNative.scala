@@ -21,6 +21,26 @@ object DemiNative {
   @native def ddmin(h: Long, lookingFor: Int, flags: Int, checkUnmodified: Int, mcsMask: ByteBuffer, maskWords: Int,
                     iterationSizes: ByteBuffer, capIterations: Int, out: ByteBuffer): Int
   @native def stats(h: Long, out: ByteBuffer): Int
+  @native def replayBatchEx(h: Long, masks: ByteBuffer, skipEvents: ByteBuffer, nTests: Int, maskWords: Int, lookingFor: Int,
+                            flags: Int, out: ByteBuffer): Int
+  @native def replayTrace(h: Long, mask: ByteBuffer, maskWords: Int, skipEvent: Int, lookingFor: Int, flags: Int,
+                          events: ByteBuffer, capEvents: Int, count: ByteBuffer, result: ByteBuffer): Int
+  @native def internalMinimize(h: Long, lookingFor: Int, flags: Int, events: ByteBuffer, capEvents: Int, sizes: ByteBuffer,
+                               capSizes: Int, out: ByteBuffer): Int
+  @native def dporBatch(h: Long, ext: ByteBuffer, extOffsets: ByteBuffer, nSearches: Int, params: ByteBuffer,
+                        results: ByteBuffer, viol: ByteBuffer, capViol: Int): Int
+  @native def dporBatchEx(h: Long, ext: ByteBuffer, extOffsets: ByteBuffer, nSearches: Int, params: ByteBuffer, flags: Int,
+                          seedEvents: ByteBuffer, nSeedEvents: Int, seedParents: ByteBuffer, nSeedNodes: Int,
+                          caps: ByteBuffer, capOffsets: ByteBuffer, results: ByteBuffer): Int
+  @native def incrementalDdmin(h: Long, externals: ByteBuffer, nExternals: Int, params: ByteBuffer, flags: Int,
+                               seedEvents: ByteBuffer, nSeedEvents: Int, seedParents: ByteBuffer, nSeedNodes: Int,
+                               maxMaxDistance: Int, stopAtSize: Int, mcsMask: ByteBuffer, maskWords: Int, out: ByteBuffer): Int
+  @native def provenance(h: Long, events: ByteBuffer, nEvents: Int, depParent: ByteBuffer, nNodes: Int, affectedMask: Int,
+                         keepMask: ByteBuffer, maskWords: Int, out: ByteBuffer): Int
+  @native def fuzzProvenance(h: Long, params: ByteBuffer, prefixIndex: ByteBuffer, n: Int, keepMasks: ByteBuffer,
+                             maskWords: Int, out: ByteBuffer, results: ByteBuffer): Int
+  @native def dedupCompact(h: Long, results: ByteBuffer, n: Long, mode: Int, outRecords: ByteBuffer, outIndex: ByteBuffer,
+                           outCount: ByteBuffer): Int
 
   def direct(n: Int): ByteBuffer = ByteBuffer.allocateDirect(n).order(ByteOrder.LITTLE_ENDIAN)
 }

@@ -40,6 +40,18 @@ int main() {
   CHECK(!kept.empty() && kept.size() + 1 == prov.last.n_kept && prov.last.n_kept < prov.last.n_trace);
   for (uint32_t i : kept) CHECK(trace[i].kind == DEMI_EV_MSG_EVENT);
 
+  // RunnerUtils.editDistanceDporDDMin (RunnerUtils.scala:812-842)
+  {
+    int32_t deliveries = 0;
+    for (const demi_event& e : trace) deliveries += e.kind == DEMI_EV_MSG_EVENT;
+    ResumableDPOR rdpor(cfg, trace, sched.depGraph, deliveries, 2000, sched.engine);
+    IncrementalDDMin inc(rdpor, /*maxMaxDistance=*/8, /*stopAtSize=*/1);
+    ExternalEvents dmcs = inc.minimize(prog, fp);
+    std::printf("IncrementalDDMin(DPOR): %u rounds, %u sequential tests, %u DPOR instances -> %zu externals\n",
+                inc.last.rounds, inc.last.total_replays, inc.last.instances, dmcs.size());
+    CHECK(inc.last.rounds >= 1 && dmcs.size() <= prog.size() - 1 && inc.last.mcs_size == dmcs.size());
+  }
+
   ReplayScheduler replayer(cfg, trace, prog);
   demi_replay_result rr = replayer.replay(fp);                     // validate_replay (RunnerUtils.scala:101-128)
   CHECK(rr.violation == fp && rr.ignored == 0);

@@ -98,3 +98,24 @@ def test_arvind_needs_a_seed(world):
     eng, dext, recs = world
     with pytest.raises(D.DemiError):
         eng.dpor_batch_ex([dext], 10, 10, flags=N.DF_ARVIND_ORDERING)
+
+
+def test_host_mirror_classes(world):
+    """ResumableDPOR / IncrementalDDMin as the reference's drivers use them (RunnerUtils.scala:822-842)."""
+    eng, dext, recs = world
+    i, (ev, par, steps) = list(recs.items())[0]
+    prog = [e for e in D.raft5_program() if e.kind in (N.EXT_START, N.EXT_SEND)]
+    cfg = D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1)
+    heuristic = D.ArvindDistanceOrdering()
+    heuristic.init(ev, par)
+    oracle = D.ResumableDPOR(cfg, ev, par, max_messages=steps, max_interleavings=2000, engine=eng,
+                             backtrackHeuristic=heuristic)
+    ddmin = D.IncrementalDDMin(oracle, maxMaxDistance=64, stopAtSize=1)
+    mcs = ddmin.minimize(prog, 1)
+    rc, mcs_o, st = O.incremental_ddmin(N.MODEL_RAFT5, D.pack_externals(prog), steps, 2000, O.dpor_seed(ev, par),
+                                        model_flags=1, looking_for=1, stop_at_size=1, max_max_distance=64)
+    assert [e._id for e in mcs] == [e._id for k, e in enumerate(prog) if (int(mcs_o[0]) >> k) & 1]
+    assert ddmin._stats.total_replays == st["total_replays"]
+    # the instance of the full sequence: found under cap 0, and answers at once afterwards
+    oracle.setMaxDistance(0)
+    assert oracle.test(prog, 1) and oracle.test(prog, 1)
