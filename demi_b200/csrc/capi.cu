@@ -113,6 +113,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->ext_dev); cudaFree(h->results_dev); cudaFree(h->node_scratch); cudaFree(h->pend_scratch);
   cudaFree(h->counters_dev); cudaFree(h->rec_counts_dev); cudaFree(h->prov_scratch);
+  for (void* b : h->dpor_buf) cudaFree(b);
   cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count); cudaFree(h->fifo_scratch);
   demi_replay_free(h);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);

@@ -109,15 +109,28 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
     {&d_sn, std::max<size_t>(n_seed_nodes, 1) * sizeof(uint4), -1}, {&d_st, std::max<size_t>(n_seed_trace, 1) * sizeof(uint32_t), -1},
     {&d_oi, std::max<size_t>(n_seed_nodes, 1) * sizeof(int32_t), -1},
   };
+  // the buffers live in the handle and only grow: a DDMin run issues many launches of similar size
   cudaError_t e = cudaSuccess;
   size_t total = 0;
-  for (Buf& b : bufs) {
+  constexpr size_t NB = sizeof(bufs) / sizeof(bufs[0]);
+  static_assert(NB <= sizeof(h->dpor_buf) / sizeof(h->dpor_buf[0]), "dpor_buf too small");
+  for (size_t i = 0; i < NB; i++) {
+    Buf& b = bufs[i];
+    total += b.bytes;
     if (e != cudaSuccess) break;
-    e = cudaMalloc(b.p, b.bytes); total += b.bytes;
+    if (h->dpor_buf_bytes[i] < b.bytes) {
+      cudaFree(h->dpor_buf[i]); h->dpor_buf[i] = nullptr; h->dpor_buf_bytes[i] = 0;
+      e = cudaMalloc(&h->dpor_buf[i], b.bytes);
+      if (e == cudaSuccess) h->dpor_buf_bytes[i] = b.bytes;
+    }
+    *b.p = h->dpor_buf[i];
     if (e == cudaSuccess && b.fill >= 0) e = cudaMemsetAsync(*b.p, b.fill, b.bytes, h->stream);
   }
-  auto cleanup = [&]() { for (Buf& b : bufs) cudaFree(*b.p); };
-  if (e != cudaSuccess) { cleanup(); return fail(h, DEMI_ERR_CUDA, "demi_dpor_batch: %s (%.1f MB of search state)", cudaGetErrorString(e), total / 1e6); }
+  auto cleanup = [&]() {};
+  if (e != cudaSuccess) {
+    for (size_t i = 0; i < NB; i++) { cudaFree(h->dpor_buf[i]); h->dpor_buf[i] = nullptr; h->dpor_buf_bytes[i] = 0; }
+    return fail(h, DEMI_ERR_CUDA, "demi_dpor_batch: %s (%.1f MB of search state)", cudaGetErrorString(e), total / 1e6);
+  }
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
   };

@@ -41,6 +41,7 @@ struct demi_handle {
   int use_lane_engine = 1;
   uint32_t* rec_counts_dev = nullptr;
   void* prov_scratch = nullptr; size_t prov_scratch_bytes = 0;
+  void* dpor_buf[24] = {}; size_t dpor_buf_bytes[24] = {};     // K3 per-search structures (capi_dpor.cu)
   // pinned staging for host transfers
   void* pinned = nullptr; size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
