@@ -278,7 +278,8 @@ def main():
                                  "evicted from L2)"},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        line["cpu_baseline"] = None                 # timed at N=1 only (rank 0)
+        if not args.no_cpu_baseline and world == 1:
             from oracle import binding as O
             build.build_oracle()
             cores = host_cores()
