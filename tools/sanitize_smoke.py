@@ -46,4 +46,21 @@ eng.internal_minimize(code)
 progs = [[D.Start(a) for a in range(5)] + [D.Send(a, 1, 0x1F) for a in range(k)] for k in (2, 3, 5)] * 4
 eng.dpor_batch(progs, 30, 40)
 u, i = eng.dedup_compact(eng.fuzz_batch(1, 5000, 6, 5, flags=1) if eng.set_externals(ext) is None else None, 0)
-print("sanitize smoke ok", len(u))
+# provenance pruning, seeded / capped DPOR instances, IncrementalDDMin
+res = eng.fuzz_batch(1, 2000, 40, 5)
+viol = np.nonzero(res["violation"] == 1)[0].astype(np.uint32)
+keep, pout, _ = eng.fuzz_provenance(1, viol[:40], 40, 5)
+assert (pout["status"] == 0).all()
+sev, spar, sr = eng.fuzz_trace(1 + int(viol[0]), 40, 5)
+k2, o2 = eng.provenance(sev, spar, int(pout[0]["affected_mask"]))
+assert (k2[:len(keep[0])] == keep[0][:len(k2)]).all()
+dext = ext[(ext["kind"] == 1) | (ext["kind"] == 3)]
+steps = int(sr["steps"])
+caps = [[0, 2, 4, -1], [0], [0, 2], [-1]]
+progs2 = [dext, dext[1:], dext[:-2], dext]
+for fl in (0, 3):
+    r2, h2 = eng.dpor_batch_ex(progs2, steps, 40, seed=(sev, spar), flags=fl, caps=caps, looking_for=1, heap_cap=1 << 15,
+                               want_hashes=True)
+    assert (r2["status"] == 0).all()
+m2, io = eng.incremental_ddmin(dext, steps, 200, (sev, spar), looking_for=1, stop_at_size=1, max_max_distance=8)
+print("sanitize smoke ok", len(u), int(io.mcs_size))
