@@ -4,6 +4,6 @@ from . import _native  # noqa: F401
 from .events import (Start, Kill, Send, WaitQuiescence, Partition, UnPartition,  # noqa: F401
                      pack_externals, unpack_externals, raft5_program, pingpong3_program, bcast32_program)
 from .schedulers import (DemiError, SchedulerConfig, Engine, RandomScheduler, STSScheduler, ReplayScheduler,  # noqa: F401
-                         DDMin, MinimizationStats, DPORwHeuristics, STSSchedMinimizer, LeftToRightOneAtATime,
+                         DDMin, MinimizationStats, DPORwHeuristics, STSSchedMinimizer, LeftToRightOneAtATime, SrcDstFIFORemoval,
                          ProvenanceTracker, ResumableDPOR, IncrementalDDMin, ArvindDistanceOrdering,
                          DefaultBacktrackOrdering, mask_of, events_of)

@@ -80,6 +80,7 @@ class IncDDMinOut(C.Structure):
 
 
 DF_ARVIND_ORDERING, DF_PRIORITIZE_PENDING = 1, 2
+IM_SRC_DST_FIFO = 0x100
 
 DPOR_RESULT_DTYPE = np.dtype([("interleavings", "<u4"), ("violations", "<u4"), ("deliveries", "<u8"), ("races", "<u8"),
                               ("n_nodes", "<u4"), ("n_explored", "<u4"), ("heap_left", "<u4"), ("exhausted", "<u4"),

@@ -1,6 +1,6 @@
 // capi_intmin.cu — internal-event minimization: STSSchedMinimizer
 // (minification/internal_minimization/ScheduleCheckers.scala:19-107) with the
-// LeftToRightOneAtATime removal strategy (OneAtATimeRemoval.scala:17-137).
+// LeftToRightOneAtATime (OneAtATimeRemoval.scala:17-137) or SrcDstFIFORemoval (:139-251) removal strategy.
 //
 // The reference tries ONE delivery at a time: drop it from the last failing trace,
 // ask STSSched whether the violation still shows, and on success continue from the
@@ -19,6 +19,69 @@ typedef std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t> Key;   // (
 typedef std::map<Key, uint32_t> MultiSet;
 Key key_of(const demi_event& e) { return Key(e.src, e.dst, e.type, e.p0, e.p1); }
 uint32_t count_of(const MultiSet& m, const Key& k) { auto it = m.find(k); return it == m.end() ? 0u : it->second; }
+
+// RemovalStrategy state.  Copyable: the candidates the strategy would produce if every test failed are obtained
+// from a copy, the real object then replays the same calls as results are committed.
+struct Strategy {
+  typedef std::tuple<uint32_t, uint32_t, uint32_t> Fp;               // (type, p0, p1)
+  bool fifo = false;
+  MultiSet tried;                                                    // triedIgnoring (:20)
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<Fp>> src_dst;  // srcDstToMessages (:150)
+  std::map<std::pair<uint32_t, uint32_t>, int> cur_idx;              // srcDstToCurrentIdx (:168)
+  bool have_prev = false; std::pair<uint32_t, uint32_t> prev;        // previouslyChosenSrcDst (:162)
+  const std::vector<demi_event>* verified = nullptr;
+
+  void init_fifo(const std::vector<demi_event>& v) {                 // :152-159
+    fifo = true; verified = &v;
+    for (const demi_event& e : v)
+      if (e.kind == DEMI_EV_MSG_EVENT && e.src < DEMI_MAX_ACTORS) src_dst[{e.src, e.dst}].push_back(Fp(e.type, e.p0, e.p1));
+  }
+  bool choice(const demi_event& e) {                                 // choiceFilter :178-203 (LeftToRight: true, :131-137)
+    if (!fifo) return true;
+    if (e.src < DEMI_MAX_ACTORS) {
+      auto it = src_dst.find({e.src, e.dst});
+      if (it != src_dst.end()) {
+        int idx = ++cur_idx[{e.src, e.dst}];
+        if (idx == (int)it->second.size() - 1) {
+          it->second.pop_back();
+          if (it->second.empty()) src_dst.erase(it);
+          have_prev = true; prev = {e.src, e.dst};
+          return true;
+        }
+      }
+    }
+    have_prev = false;
+    return e.src >= DEMI_MAX_ACTORS;                                 // "deadLetters": a timer
+  }
+  // getNextTrace (:57-124; SrcDstFIFORemoval's prologue :209-249): index of the delivery to drop, or -1
+  int next(const std::vector<demi_event>& trace, const MultiSet& pruned, bool triggered) {
+    if (fifo) {
+      if (!triggered && have_prev) src_dst.erase(prev);              // "this src,dst is done"
+      if (triggered) {
+        src_dst.clear();
+        MultiSet copy = pruned;
+        for (size_t i = verified->size(); i-- > 0;) {
+          const demi_event& e = (*verified)[i];
+          if (e.kind != DEMI_EV_MSG_EVENT || e.src >= DEMI_MAX_ACTORS) continue;
+          auto it = copy.find(key_of(e));
+          if (it != copy.end() && it->second) { it->second--; continue; }
+          auto& vec = src_dst[{e.src, e.dst}];
+          vec.insert(vec.begin(), Fp(e.type, e.p0, e.p1));
+        }
+      }
+      cur_idx.clear();
+      for (auto& kv : src_dst) cur_idx[kv.first] = -1;
+    }
+    MultiSet keys = pruned;                                          // keysThisIteration ++= alreadyRemoved
+    for (uint32_t i = 0; i < trace.size(); i++) {
+      if (trace[i].kind != DEMI_EV_MSG_EVENT) continue;
+      const Key k = key_of(trace[i]);
+      const uint32_t c = ++keys[k];
+      if (c > count_of(tried, k) && choice(trace[i])) { tried[k]++; return (int)i; }
+    }
+    return -1;
+  }
+};
 }
 
 extern "C" int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, uint32_t flags,
@@ -29,14 +92,20 @@ extern "C" int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, 
   if (h->trace_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
   memset(out, 0, sizeof(*out));
   const uint32_t ext_mask = demi_external_type_mask(h->cfg.model);
+  const bool use_fifo = (flags & DEMI_IM_SRC_DST_FIFO) != 0;
+  flags &= ~DEMI_IM_SRC_DST_FIFO;
+  const std::vector<demi_event> verified = h->trace_host;
   std::vector<demi_event> cur = h->trace_host;
   const std::vector<demi_ext_event> ext = h->trace_ext_host;
   const uint32_t mw = std::max<uint32_t>(1, ((uint32_t)ext.size() + 63) / 64);
-  MultiSet tried, pruned;
+  MultiSet pruned;
+  Strategy strat;
+  if (use_fifo) strat.init_fifo(verified);
   // OneAtATimeStrategy.init (:27-48): external deliveries are never ignored
   for (const demi_event& e : cur)
-    if (e.kind == DEMI_EV_MSG_EVENT && ((ext_mask >> (e.type & 31)) & 1u)) tried[key_of(e)]++;
-  for (auto& kv : tried) out->unignorable += kv.second;
+    if (e.kind == DEMI_EV_MSG_EVENT && ((ext_mask >> (e.type & 31)) & 1u)) strat.tried[key_of(e)]++;
+  for (auto& kv : strat.tried) out->unignorable += kv.second;
+  bool triggered = false;                                             // violationTriggered (ScheduleCheckers.scala:48)
   uint32_t last_size = 0;
   for (const demi_event& e : cur) last_size += e.kind == DEMI_EV_MSG_EVENT;
   out->deliveries_before = last_size;
@@ -47,18 +116,13 @@ extern "C" int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, 
     // The candidate list getNextTrace would produce on this base trace if every test failed (:57-124)
     std::vector<uint32_t> cand;
     {
-      MultiSet t = tried;
+      Strategy spec = strat;
+      bool t = triggered;
       for (;;) {
-        MultiSet keys = pruned;                                       // keysThisIteration ++= alreadyRemoved
-        int found = -1;
-        for (uint32_t i = 0; i < cur.size() && found < 0; i++) {
-          if (cur[i].kind != DEMI_EV_MSG_EVENT) continue;
-          Key k = key_of(cur[i]);
-          uint32_t c = ++keys[k];
-          if (c > count_of(t, k)) { t[k]++; found = (int)i; }         // choiceFilter == true
-        }
+        const int found = spec.next(cur, pruned, t);
         if (found < 0) break;
         cand.push_back((uint32_t)found);
+        t = false;
       }
     }
     if (cand.empty()) break;
@@ -71,7 +135,9 @@ extern "C" int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, 
     for (size_t c = 0; c < cand.size(); c++) {
       if (res[c].status) return fail(h, DEMI_ERR_CAPACITY, "demi_internal_minimize: a replay reported status %u", (unsigned)res[c].status);
       out->total_replays++;                                           // stats.increment_replays
-      tried[key_of(cur[cand[c]])]++;                                  // triedIgnoring += key (:84)
+      const int chosen = strat.next(cur, pruned, triggered);          // the real strategy takes the same step
+      if (chosen != (int)cand[c]) return fail(h, DEMI_ERR_STATE, "demi_internal_minimize: speculation diverged from the strategy");
+      triggered = res[c].violation != 0;
       if (!res[c].violation) { sizes.push_back(last_size); continue; }   // "Ignoring didn't work."
       // success: the trace STSSched recorded becomes lastFailingTrace (:57-91)
       uint32_t n_rec = 0; demi_replay_result r1;

@@ -587,14 +587,21 @@ class LeftToRightOneAtATime(object):
     pass
 
 
+class SrcDstFIFORemoval(object):
+    """RemovalStrategy that keeps per-(src,dst) FIFO delivery and only tries the last message of each pair, timers in
+    any order (minification/internal_minimization/OneAtATimeRemoval.scala:139-251)."""
+    pass
+
+
 class STSSchedMinimizer(object):
     """STSSchedMinimizer(mcs, verified_mcs, violation, removalStrategy, schedulerConfig, ...) —
     minification/internal_minimization/ScheduleCheckers.scala:19-107; minimize() returns
     (MinimizationStats, minimized EventTrace) like RunnerUtils.minimizeInternals (RunnerUtils.scala:980-1003)."""
 
     def __init__(self, mcs, verified_mcs, violation, removalStrategy, schedulerConfig, stats=None, engine=None):
-        if not isinstance(removalStrategy, LeftToRightOneAtATime):
-            raise NotImplementedError("only LeftToRightOneAtATime is accelerated")
+        if not isinstance(removalStrategy, (LeftToRightOneAtATime, SrcDstFIFORemoval)):
+            raise NotImplementedError("LeftToRightOneAtATime and SrcDstFIFORemoval are the accelerated strategies")
+        self.flags = N.IM_SRC_DST_FIFO if isinstance(removalStrategy, SrcDstFIFORemoval) else 0
         self.mcs, self.verified_mcs, self.violation = list(mcs), verified_mcs, violation
         self.engine = engine or Engine(schedulerConfig)
         self._stats = stats or MinimizationStats()
@@ -602,7 +609,7 @@ class STSSchedMinimizer(object):
 
     def minimize(self):
         self.engine.set_trace(self.verified_mcs, pack_externals(self.mcs))
-        trace, sizes, out = self.engine.internal_minimize(self.violation)
+        trace, sizes, out = self.engine.internal_minimize(self.violation, flags=self.flags)
         self._stats.total_replays += out.total_replays
         self._stats.internal_sizes = [int(x) for x in sizes]
         self.last = out

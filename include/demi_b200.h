@@ -244,6 +244,8 @@ int32_t demi_replay_trace(demi_handle* h, const uint64_t* mask, uint32_t mask_wo
  * MCS trace; its externals are the MCS): RunnerUtils.minimizeInternals (RunnerUtils.scala:980-1003;
  * internal_minimization/ScheduleCheckers.scala:19-107).  Decisions and counters are the sequential ones;
  * candidate removals are evaluated speculatively in batches.  On return the handle's trace is the minimized one. */
+#define DEMI_IM_SRC_DST_FIFO 0x100u   /* in `flags`: removalStrategy = SrcDstFIFORemoval (OneAtATimeRemoval.scala:139-251)
+                                         instead of LeftToRightOneAtATime (:131-137)                                     */
 typedef struct demi_intmin_out {
   uint32_t n_events;            /* length of the minimized EventTrace                       */
   uint32_t deliveries_before, deliveries_after;

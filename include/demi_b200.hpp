@@ -240,6 +240,7 @@ class DDMin {
 };
 
 struct LeftToRightOneAtATime {};       // RemovalStrategy (OneAtATimeRemoval.scala:131-137)
+struct SrcDstFIFORemoval {};           // RemovalStrategy (OneAtATimeRemoval.scala:139-251)
 
 class STSSchedMinimizer {
  public:
@@ -247,6 +248,10 @@ class STSSchedMinimizer {
                     LeftToRightOneAtATime, const SchedulerConfig& cfg, std::shared_ptr<Engine> e = nullptr)
       : engine(e ? e : std::make_shared<Engine>(cfg)), mcs(mcs), verified_mcs(verified_mcs), violation(violation),
         flags(cfg.filterKnownAbsents ? DEMI_RF_FILTER_KNOWN_ABSENTS : 0) {}
+  STSSchedMinimizer(const ExternalEvents& mcs, const EventTrace& verified_mcs, ViolationFingerprint violation,
+                    SrcDstFIFORemoval, const SchedulerConfig& cfg, std::shared_ptr<Engine> e = nullptr)
+      : engine(e ? e : std::make_shared<Engine>(cfg)), mcs(mcs), verified_mcs(verified_mcs), violation(violation),
+        flags((cfg.filterKnownAbsents ? DEMI_RF_FILTER_KNOWN_ABSENTS : 0) | DEMI_IM_SRC_DST_FIFO) {}
   std::pair<MinimizationStats, EventTrace> minimize() {
     engine->check(demi_set_trace(engine->handle(), verified_mcs.data(), (uint32_t)verified_mcs.size(), mcs.data(), (uint32_t)mcs.size()));
     EventTrace out(65536); std::vector<uint32_t> sizes(65536);

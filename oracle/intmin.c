@@ -4,7 +4,7 @@
  *
  * Internal-event minimization: STSSchedMinimizer
  * (minification/internal_minimization/ScheduleCheckers.scala:19-107) driving
- * LeftToRightOneAtATime (OneAtATimeRemoval.scala:17-137), strictly sequential.
+ * LeftToRightOneAtATime (OneAtATimeRemoval.scala:17-137) or SrcDstFIFORemoval (:139-251), strictly sequential.
  * Each step removes ONE delivery (UniqueMsgEvent) from the last failing trace and
  * asks STSSched whether the violation still shows (RunnerUtils.testWithStsSched,
  * RunnerUtils.scala:913-943); on success the trace STSSched recorded becomes the
@@ -33,8 +33,77 @@ static void mset_add(mset* s, const demi_event* e, uint32_t c) {
   q->src = e->src; q->dst = e->dst; q->type = e->type; q->p0 = e->p0; q->p1 = e->p1; q->count = c;
 }
 
+/* SrcDstFIFORemoval (OneAtATimeRemoval.scala:139-251): per (snd,rcv) pair the fingerprints of its deliveries in
+ * the verified trace; only the LAST one of a pair is eligible, timers always are */
+#define FP_PAIRS (DEMI_MAX_ACTORS * DEMI_MAX_ACTORS)
+typedef struct { uint8_t type; uint32_t p0, p1; } fprint;
+typedef struct {
+  int enabled;
+  fprint* msgs[FP_PAIRS]; uint32_t len[FP_PAIRS]; uint8_t present[FP_PAIRS];   /* srcDstToMessages */
+  int32_t cur_idx[FP_PAIRS];                                                     /* srcDstToCurrentIdx */
+  int32_t prev;                                                                  /* previouslyChosenSrcDst, -1 = None */
+  const demi_event* verified; uint32_t n_verified;
+} fifo_strategy;
+
+static void fifo_push(fifo_strategy* f, uint32_t pair, const demi_event* e, int prepend) {
+  f->msgs[pair] = (fprint*)realloc(f->msgs[pair], sizeof(fprint) * (f->len[pair] + 1));
+  fprint q; q.type = e->type; q.p0 = e->p0; q.p1 = e->p1;
+  if (prepend) { memmove(f->msgs[pair] + 1, f->msgs[pair], sizeof(fprint) * f->len[pair]); f->msgs[pair][0] = q; }
+  else f->msgs[pair][f->len[pair]] = q;
+  f->len[pair]++; f->present[pair] = 1;
+}
+static void fifo_init(fifo_strategy* f, const demi_event* verified, uint32_t n) {          /* :152-159 */
+  memset(f, 0, sizeof(*f));
+  f->enabled = 1; f->prev = -1; f->verified = verified; f->n_verified = n;
+  for (uint32_t i = 0; i < n; i++)
+    if (verified[i].kind == DEMI_EV_MSG_EVENT && verified[i].src < DEMI_MAX_ACTORS)
+      fifo_push(f, (uint32_t)verified[i].src * DEMI_MAX_ACTORS + verified[i].dst, &verified[i], 0);
+}
+static void fifo_free(fifo_strategy* f) { for (int i = 0; i < FP_PAIRS; i++) free(f->msgs[i]); }
+/* choiceFilter (:178-203) */
+static int fifo_choice(fifo_strategy* f, const demi_event* e) {
+  if (e->src < DEMI_MAX_ACTORS) {
+    uint32_t pair = (uint32_t)e->src * DEMI_MAX_ACTORS + e->dst;
+    if (f->present[pair]) {
+      int32_t idx = ++f->cur_idx[pair];
+      if (idx == (int32_t)f->len[pair] - 1) {
+        f->len[pair]--;                                                  /* dropRight(1) */
+        if (!f->len[pair]) f->present[pair] = 0;
+        f->prev = (int32_t)pair;
+        return 1;
+      }
+    }
+  }
+  f->prev = -1;
+  return e->src >= DEMI_MAX_ACTORS;                                      /* snd == "deadLetters": a timer */
+}
+/* the part of SrcDstFIFORemoval.getNextTrace that precedes super.getNextTrace (:209-249) */
+static void fifo_before_next(fifo_strategy* f, const mset* already_removed, int triggered) {
+  if (!triggered && f->prev >= 0) { f->present[f->prev] = 0; f->len[f->prev] = 0; }          /* "this src,dst is done" */
+  if (triggered) {
+    for (int i = 0; i < FP_PAIRS; i++) { f->present[i] = 0; f->len[i] = 0; }
+    mset copy = {0, 0, 0};
+    for (uint32_t i = 0; i < already_removed->n; i++) {
+      demi_event t; t.src = already_removed->k[i].src; t.dst = already_removed->k[i].dst; t.type = already_removed->k[i].type;
+      t.p0 = already_removed->k[i].p0; t.p1 = already_removed->k[i].p1;
+      mset_add(&copy, &t, already_removed->k[i].count);
+    }
+    for (uint32_t i = f->n_verified; i-- > 0;) {                          /* reverse order, prepend */
+      const demi_event* e = &f->verified[i];
+      if (e->kind != DEMI_EV_MSG_EVENT || e->src >= DEMI_MAX_ACTORS) continue;
+      mkey* k = mset_find(&copy, e);
+      if (k && k->count) { k->count--; continue; }
+      fifo_push(f, (uint32_t)e->src * DEMI_MAX_ACTORS + e->dst, e, 1);
+    }
+    free(copy.k);
+  }
+  for (int i = 0; i < FP_PAIRS; i++) f->cur_idx[i] = -1;                  /* resetSrcDstToCurrentIdx */
+}
+
 /* OneAtATimeStrategy.getNextTrace (OneAtATimeRemoval.scala:57-124): index of the delivery to drop next, or -1 */
-static int next_to_ignore(const demi_event* ev, uint32_t n, mset* tried, const mset* already_removed) {
+static int next_to_ignore(const demi_event* ev, uint32_t n, mset* tried, const mset* already_removed,
+                          fifo_strategy* fifo, int triggered) {
+  if (fifo && fifo->enabled) fifo_before_next(fifo, already_removed, triggered);
   mset keys = {0, 0, 0};
   for (uint32_t i = 0; i < already_removed->n; i++) {
     demi_event t; t.src = already_removed->k[i].src; t.dst = already_removed->k[i].dst; t.type = already_removed->k[i].type;
@@ -45,7 +114,8 @@ static int next_to_ignore(const demi_event* ev, uint32_t n, mset* tried, const m
   for (uint32_t i = 0; i < n && found < 0; i++) {
     if (ev[i].kind != DEMI_EV_MSG_EVENT) continue;
     mset_add(&keys, &ev[i], 1);                                       /* checkDelivery :71-93 */
-    if (mset_count(&keys, &ev[i]) > mset_count(tried, &ev[i])) {      /* choiceFilter == true (LeftToRightOneAtATime :131-137) */
+    if (mset_count(&keys, &ev[i]) > mset_count(tried, &ev[i]) &&
+        (!(fifo && fifo->enabled) || fifo_choice(fifo, &ev[i]))) {    /* choiceFilter: LeftToRightOneAtATime = true (:131-137) */
       mset_add(tried, &ev[i], 1);
       found = (int)i;
     }
@@ -55,11 +125,15 @@ static int next_to_ignore(const demi_event* ev, uint32_t n, mset* tried, const m
 }
 
 int oracle_internal_minimize(const demi_config* cfg, const demi_event* verified, uint32_t n_verified,
-                             const demi_ext_event* mcs_ext, uint32_t n_ext, uint32_t looking_for, uint32_t flags,
+                             const demi_ext_event* mcs_ext, uint32_t n_ext, uint32_t looking_for, uint32_t flags_in,
                              demi_event* out_trace, uint32_t cap_out, uint32_t* n_out,
                              uint32_t* total_replays, uint32_t* internal_sizes, uint32_t cap_sizes, uint32_t* n_sizes,
                              uint32_t* unignorable) {
   const uint32_t ext_mask = demi_external_type_mask(cfg->model);
+  const uint32_t flags = flags_in & ~DEMI_IM_SRC_DST_FIFO;
+  fifo_strategy* fifo = 0;
+  if (flags_in & DEMI_IM_SRC_DST_FIFO) { fifo = (fifo_strategy*)malloc(sizeof(fifo_strategy)); fifo_init(fifo, verified, n_verified); }
+  int triggered = 0;                                                  /* violationTriggered (ScheduleCheckers.scala:48) */
   demi_event* cur = (demi_event*)malloc(sizeof(demi_event) * (n_verified + 1));
   demi_event* rec = (demi_event*)malloc(sizeof(demi_event) * 65536);
   memcpy(cur, verified, sizeof(demi_event) * n_verified);
@@ -77,7 +151,7 @@ int oracle_internal_minimize(const demi_config* cfg, const demi_event* verified,
   for (uint32_t i = 0; i < n_cur; i++) last_size += cur[i].kind == DEMI_EV_MSG_EVENT;
   int rc = 0;
   for (;;) {
-    int skip = next_to_ignore(cur, n_cur, &tried, &pruned);
+    int skip = next_to_ignore(cur, n_cur, &tried, &pruned, fifo, triggered);
     if (skip < 0) break;
     /* nextTrace = cur minus that one delivery; STSScheduler(nextTrace).test(mcs) */
     demi_replay_input in;
@@ -90,6 +164,7 @@ int oracle_internal_minimize(const demi_config* cfg, const demi_event* verified,
     oracle_sts_replay_ex(cfg, &in, full, looking_for, flags, (uint32_t)skip, &r, rec, 65536, &n_rec, scratch);
     replays++;                                                         /* stats.increment_replays (STSScheduler.scala:213-215) */
     if (r.status) { rc = -1; break; }
+    triggered = r.violation != 0;
     if (r.violation) {
       /* prunedThisRun = deliveries(lastFailingTrace) - deliveries(new trace) (:69-84) */
       mset prior = {0, 0, 0}, fresh = {0, 0, 0};
@@ -116,6 +191,7 @@ int oracle_internal_minimize(const demi_config* cfg, const demi_event* verified,
   if (n_sizes) *n_sizes = ns;
   if (unignorable) *unignorable = unig;
   free(cur); free(rec); free(tried.k); free(pruned.k); free(scratch);
+  if (fifo) { fifo_free(fifo); free(fifo); }
   return rc;
 }
 

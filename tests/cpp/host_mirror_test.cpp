@@ -75,6 +75,11 @@ int main() {
   std::printf("internal minimization: %u -> %u deliveries in %u replays\n", im.last.deliveries_before,
               im.last.deliveries_after, res.first.total_replays);
   CHECK(im.last.deliveries_after <= im.last.deliveries_before);
+  STSSchedMinimizer fifo_min(mcs, *verified, fp, SrcDstFIFORemoval(), cfg);
+  auto fres = fifo_min.minimize();
+  std::printf("internal minimization (SrcDstFIFORemoval): %u -> %u deliveries in %u replays\n", fifo_min.last.deliveries_before,
+              fifo_min.last.deliveries_after, fres.first.total_replays);
+  CHECK(fifo_min.last.deliveries_after <= fifo_min.last.deliveries_before);
   ReplayScheduler final_check(cfg, res.second, mcs);
   CHECK(final_check.replay(fp).violation == fp);
 

@@ -64,6 +64,17 @@ def test_recorded_replay_and_internal_minimization_match_oracle(oracle, which):
     eng.set_trace(mtrace, mcs_ext)
     r3, _ = eng.replay_trace(None, looking_for=code)
     assert r3["violation"] == code and r3["ignored"] == 0
+    # SrcDstFIFORemoval (OneAtATimeRemoval.scala:139-251): only the last delivery of each (src,dst) pair, plus timers
+    sf = D.STSSchedMinimizer(mcs_events, vtrace, code, D.SrcDstFIFORemoval(), cfg, engine=eng)
+    fstats, ftrace = sf.minimize()
+    rc, cftrace, ftotal, fsizes, funig = oracle.internal_minimize(N.MODEL_RAFT5, vtrace, mcs_ext, code, model_flags=1,
+                                                                  flags=N.IM_SRC_DST_FIFO)
+    assert rc == 0
+    assert len(ftrace) == len(cftrace) and (ftrace == cftrace).all()
+    assert sf.last.total_replays == ftotal and fstats.internal_sizes == [int(x) for x in fsizes]
+    eng.set_trace(ftrace, mcs_ext)
+    r4, _ = eng.replay_trace(None, looking_for=code)
+    assert r4["violation"] == code
 
 
 def test_internal_minimization_pingpong(oracle):
