@@ -47,4 +47,26 @@ elif which == "dedup":
     for _ in range(2):
         eng.dedup_compact_dev(big.data_ptr(), m, 0, bout.data_ptr(), bidx.data_ptr(), cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+elif which == "prov":
+    eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    eng.set_externals(D.raft5_program())
+    res = eng.fuzz_batch(1, 1_000_000, 50, 5)
+    viol = np.nonzero(res["violation"])[0].astype(np.uint32)
+    eng.fuzz_provenance(1, viol, 50, 5)
+elif which == "dpor_arvind":
+    eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    prog = D.raft5_program()
+    eng.set_externals(prog)
+    ext_all = D.pack_externals(prog)
+    dext = ext_all[(ext_all["kind"] == 1) | (ext_all["kind"] == 3)]
+    res = eng.fuzz_batch(1, 3000, 40, 5)
+    i = int(np.nonzero(res["violation"] == 1)[0][3])
+    ev, par, r = eng.fuzz_trace(1 + i, 40, 5)
+    rng = np.random.default_rng(3)
+    progs, caps = [], []
+    for t in range(4096):
+        keep = np.ones(len(dext), dtype=bool)
+        keep[rng.integers(0, len(dext), size=int(rng.integers(0, 4)))] = False
+        progs.append(dext[keep]); caps.append([0, 2, 4, 8, 16, 32][:int(rng.integers(1, 7))])
+    eng.dpor_batch_ex(progs, int(r["steps"]), 64, seed=(ev, par), flags=3, caps=caps, looking_for=1, heap_cap=1 << 14)
 print("done", which)
