@@ -39,6 +39,7 @@ static const std::vector<Variant>& variants() {
     make_variant<PingPong3, 16384, 1024, true, true>(),
     make_variant<Raft5, 256, 32, false, false>(),
     make_variant<Raft5, 512, 32, false, false>(),
+    make_variant<Raft5, 256, 32, false, true>(),          // recording, shared-memory pending set (provenance batches)
     make_variant<Raft5, 16384, 1024, true, false>(),
     make_variant<Raft5, 16384, 1024, true, true>(),
     make_variant<Bcast32, 16384, 32, true, false>(),
