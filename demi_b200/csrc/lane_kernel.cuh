@@ -205,50 +205,43 @@ struct LaneMachine {
     }
     handle_timer(slot);
   }
-  // One loop, one event_produced call site (code size): first the ops receive() left
-  // in the outbox (`n_ops`, sender `self`), in program order; then, if `do_flush`,
-  // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365).
+  // First the ops receive() left in the outbox (`n_ops`, sender `self`), in program order; then, if `do_flush`,
+  // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365).  Two loops, so that the
+  // lanes of a warp reconverge between the phases and their flush items are processed together.
   __device__ __forceinline__ void drain(uint32_t n_ops, uint32_t self, bool do_flush) {
     uint32_t* ob = smw + N * SW * BD;
-    uint32_t i = 0;
-    bool flushing = false;
-    for (;;) {
-      if (status) return;
-      if (!flushing && i >= n_ops) { if (!do_flush) return; flushing = true; i = 0; }
-      if (flushing && i >= tosend.n) { tosend.clear(); return; }
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_ops && !status; i++) {
+      const uint32_t w0 = ob[(i * 3) * BD], p0 = ob[(i * 3 + 1) * BD], p1 = ob[(i * 3 + 2) * BD];
+      const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+      if (kind == OP_SEND) { event_produced(make_hdr(self, odst, otype, 0), p0, p1, -2); continue; }
+      if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
+      int s2 = MODEL::timer_slot(odst, otype, p0, p1);
+      if (s2 < 0) { defer(); return; }
+      if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
+      if (kind == OP_SCHED_REPEAT) {
+        if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); return; }
+        registry |= 1u << s2;
+      }
+      enqueue_timer((uint32_t)s2);
+    }
+    if (status || !do_flush) return;
+#pragma unroll 1
+    for (uint32_t i = 0; i < tosend.n && !status; i++) {
+      const uint32_t b = tosend.get(i);
       uint32_t hdr, p0, p1; int slot = -2;
-      if (!flushing) {
-        uint32_t w0 = ob[(i * 3) * BD]; p0 = ob[(i * 3 + 1) * BD]; p1 = ob[(i * 3 + 2) * BD];
-        uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-        i++;
-        if (kind != OP_SEND) {
-          if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
-          int s2 = MODEL::timer_slot(odst, otype, p0, p1);
-          if (s2 < 0) { defer(); return; }
-          if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
-          if (kind == OP_SCHED_REPEAT) {
-            if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); return; }
-            registry |= 1u << s2;
-          }
-          enqueue_timer((uint32_t)s2);
-          continue;
-        }
-        hdr = make_hdr(self, odst, otype, 0);
+      if (b & 0x80u) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
+        hdr = raw.x; p0 = raw.y; p1 = raw.z;
       } else {
-        uint32_t b = tosend.get(i);
-        i++;
-        if (b & 0x80u) {
-          uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
-          hdr = raw.x; p0 = raw.y; p1 = raw.z;
-        } else {
-          uint32_t dst, type;
-          MODEL::slot_msg(b, dst, type, p0, p1);
-          hdr = make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER);
-          slot = (int)b;
-        }
+        uint32_t dst, type;
+        MODEL::slot_msg(b, dst, type, p0, p1);
+        hdr = make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER);
+        slot = (int)b;
       }
       event_produced(hdr, p0, p1, slot);
     }
+    if (!status) tosend.clear();
   }
 
   // Cancellable.cancel(): Instrumenter.cancelTimer (Instrumenter.scala:159-168) ->
