@@ -486,6 +486,20 @@ extern "C" int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* 
   // an execution records at most one MsgSend + one MsgEvent per message, plus the external markers
   const uint32_t node_cap = plan.args.node_cap;
   const uint32_t ev_cap = 2 * node_cap + 2 * plan.args.n_ext + 16;
+  {
+    // bound the per-slot recording buffers to ~4 GB per launch: larger requests run in chunks
+    const size_t per_slot = (size_t)ev_cap * sizeof(demi_event) + (size_t)node_cap * 2 + 64 + (size_t)mask_words * 8;
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, ((size_t)4 << 30) / per_slot);
+    if (n > chunk) {
+      for (uint32_t off = 0; off < n; off += chunk) {
+        const uint32_t m = std::min(chunk, n - off);
+        rc = demi_fuzz_provenance(h, p, prefix_index + off, m, keep_masks + (size_t)off * mask_words, mask_words, out + off,
+                                  results ? results + off : nullptr);
+        if (rc != DEMI_OK) return rc;
+      }
+      return DEMI_OK;
+    }
+  }
   const size_t b_ev = (size_t)n * ev_cap * sizeof(demi_event), b_par = (((size_t)n * node_cap * 2) + 15) & ~(size_t)15,
                b_cnt = (size_t)n * 16, b_res = (size_t)n * sizeof(demi_fuzz_result), b_idx = (((size_t)n * 4) + 15) & ~(size_t)15,
                b_keep = (size_t)n * mask_words * 8, b_out = (size_t)n * sizeof(demi_provenance_out);
