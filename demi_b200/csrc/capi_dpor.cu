@@ -88,13 +88,16 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
   a.child_slots = demi_pow2_at_least(2 * P.node_cap, 4, 1u << 22);
   a.flags = flags;
   const bool arv = (flags & DEMI_DF_ARVIND_ORDERING) != 0;
+  // a single uncapped test with the default ordering (the classic batch) uses the bucket queue; instances that are
+  // resumed re-enqueue keys, and for those the binary heap keeps the oracle's order among the duplicates
+  const bool use_buckets = !arv && !caps;
   const size_t S = n_searches, NI = (size_t)P.max_interleavings + 1;
   const size_t n_caps = caps ? cap_offsets[n_searches] : 0;
   const size_t n_seed_nodes = seed ? seed->nodes.size() : 0, n_seed_trace = seed ? seed->trace.size() : 0;
   struct Buf { void** p; size_t bytes; int fill; };
   void *d_ext = 0, *d_off = 0, *d_res = 0, *d_viol = 0, *d_hash = 0, *d_nodes = 0, *d_child = 0, *d_q = 0, *d_ex = 0, *d_heap = 0,
        *d_tr = 0, *d_tl = 0, *d_cur = 0, *d_next = 0, *d_npos = 0, *d_scan = 0, *d_hd = 0, *d_path = 0, *d_caps = 0, *d_coff = 0,
-       *d_sn = 0, *d_st = 0, *d_oi = 0;
+       *d_sn = 0, *d_st = 0, *d_oi = 0, *d_bk = 0;
   Buf bufs[] = {
     {&d_ext, std::max<size_t>(n_ext, 1) * sizeof(demi_ext_event), -1}, {&d_off, (S + 1) * sizeof(uint32_t), -1},
     {&d_res, S * sizeof(demi_dpor_result), 0}, {&d_viol, std::max<size_t>(S * cap_viol, 1) * sizeof(demi_dpor_violation), 0},
@@ -104,10 +107,11 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
     {&d_heap, S * P.heap_cap * sizeof(DporKey), -1}, {&d_tr, S * NI * a.T1 * sizeof(uint32_t), -1},
     {&d_tl, S * NI * sizeof(uint32_t), -1}, {&d_cur, S * a.T1 * sizeof(uint32_t), -1}, {&d_next, S * a.T1 * sizeof(uint32_t), -1},
     {&d_npos, S * P.node_cap * sizeof(uint32_t), 0}, {&d_scan, S * a.T1 * sizeof(uint32_t), -1},
-    {&d_hd, arv ? S * P.heap_cap * sizeof(uint32_t) : 16, -1}, {&d_path, arv ? S * (2 * (size_t)a.T1 + 4) * sizeof(int32_t) : 16, -1},
+    {&d_hd, (arv || use_buckets) ? S * P.heap_cap * sizeof(uint32_t) : 16, -1}, {&d_path, arv ? S * (2 * (size_t)a.T1 + 4) * sizeof(int32_t) : 16, -1},
     {&d_caps, std::max<size_t>(n_caps, 1) * sizeof(int32_t), -1}, {&d_coff, (S + 1) * sizeof(uint32_t), -1},
     {&d_sn, std::max<size_t>(n_seed_nodes, 1) * sizeof(uint4), -1}, {&d_st, std::max<size_t>(n_seed_trace, 1) * sizeof(uint32_t), -1},
     {&d_oi, std::max<size_t>(n_seed_nodes, 1) * sizeof(int32_t), -1},
+    {&d_bk, use_buckets ? S * 2 * (size_t)a.T1 * sizeof(uint32_t) : 16, -1},
   };
   // the buffers live in the handle and only grow: a DDMin run issues many launches of similar size
   cudaError_t e = cudaSuccess;
@@ -148,15 +152,21 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
   a.heap = (DporKey*)d_heap; a.traces = (uint32_t*)d_tr; a.trace_len = (uint32_t*)d_tl;
   a.cur_trace = (uint32_t*)d_cur; a.next_trace = (uint32_t*)d_next;
   a.node_pos = (uint32_t*)d_npos; a.scan = (uint32_t*)d_scan;
-  a.heap_dist = arv ? (uint32_t*)d_hd : nullptr; a.path = arv ? (int32_t*)d_path : nullptr;
+  a.heap_dist = (arv || use_buckets) ? (uint32_t*)d_hd : nullptr;
+  a.buckets = use_buckets ? (uint32_t*)d_bk : nullptr; a.path = arv ? (int32_t*)d_path : nullptr;
   a.caps = caps ? (const int32_t*)d_caps : nullptr; a.cap_offsets = (const uint32_t*)d_coff;
   a.init_nodes = (const uint4*)d_sn; a.n_init_nodes = (uint32_t)n_seed_nodes;
   a.init_trace = (const uint32_t*)d_st; a.n_init_trace = (uint32_t)n_seed_trace;
   a.orig_index = (const int32_t*)d_oi;
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(dv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dv->smem);
+  // the race scan's position table goes to shared memory when it leaves room for >= 8 blocks per SM
+  size_t smem = dv->smem;
+  const size_t scan_bytes = (size_t)a.T1 * dv->bd * sizeof(uint32_t);
+  a.scan_in_smem = (dv->smem + scan_bytes <= 27 * 1024) ? 1u : 0u;
+  if (a.scan_in_smem) smem += scan_bytes;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
   if (e == cudaSuccess) {
-    dv->fn<<<(n_searches + dv->bd - 1) / dv->bd, dv->bd, dv->smem, h->stream>>>(a);
+    dv->fn<<<(n_searches + dv->bd - 1) / dv->bd, dv->bd, smem, h->stream>>>(a);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(h->ev1, h->stream);

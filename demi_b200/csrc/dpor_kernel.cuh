@@ -48,13 +48,16 @@ struct DporArgs {
   uint4* nodes; uint32_t* child_hash; uint32_t* queues; uint64_t* explored; DporKey* heap;
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
   uint32_t* node_pos;           // [node_cap] (interleaving stamp << 12 | first position in the current trace)
-  uint32_t* scan;               // [T1] per trace position: parent's first position << 8 | receiver
+  uint32_t* scan;               // [T1] per trace position (global fallback): see DporMachine::analyse
+  uint32_t scan_in_smem;        // the scan array lives in shared memory ([position][lane]) — it is what the race scan walks
   // RunnerUtils.editDistanceDporDDMin configuration (RunnerUtils.scala:822-835)
   uint32_t flags;               // DEMI_DF_*
   const uint4* init_nodes; uint32_t n_init_nodes;       // setInitialDepGraph: {hdr, p0, p1, parent | depth << 20}
   const uint32_t* init_trace; uint32_t n_init_trace;    // setInitialTrace
   const int32_t* orig_index;    // ArvindDistanceOrdering.originalIndices: node -> index in the original trace, -1 absent
-  uint32_t* heap_dist;          // [heap_cap] per search: distance of each heap entry (ArvindDistanceOrdering only)
+  uint32_t* heap_dist;          // [heap_cap] per search: distance of each heap entry (ArvindDistanceOrdering), or the
+                                // `next` links of the bucket queue
+  uint32_t* buckets;            // [2*T1] per search: head / tail of each branch depth's FIFO (bucket queue), or null
   int32_t* path;                // [2*T1+4] per search: arvindDistance scratch
   // ResumableDPOR (IncrementalDeltaDebugging.scala:90-122): search i performs one DPORwHeuristics.test per entry of
   // caps[cap_offsets[i] .. cap_offsets[i+1]) on ONE instance, each preceded by setMaxDistance(cap) (< 0: no cap).
@@ -74,7 +77,8 @@ struct DporMachine {
   uint32_t* smw; const DporArgs* A;
   uint4* nodes; uint32_t* child_hash; uint32_t* queues; uint64_t* explored; DporKey* heap;
   uint32_t* traces; uint32_t* trace_len; uint32_t* cur_trace; uint32_t* next_trace;
-  uint32_t* node_pos; uint32_t* scan; uint32_t* heap_dist; int32_t* path;
+  uint32_t* node_pos; uint32_t* scan; uint32_t scan_stride; uint32_t* heap_dist; int32_t* path;
+  uint32_t* bk_head; uint32_t* bk_tail; uint32_t pool_top, free_head, max_branch;   // bucket queue (see bq_push)
   uint16_t qlen[NQ];            // local memory (small)
   uint32_t n_nodes, n_explored, n_heap, n_traces, found;
   int32_t max_distance;         // setMaxDistance (:128-134); < 0 = no cap
@@ -192,6 +196,41 @@ struct DporMachine {
     }
     if (n_heap) heap[i] = last;
     return top;
+  }
+
+  // DefaultBacktrackOrdering serves the deepest branch first and, in this engine's canonical tie order, the oldest
+  // key first.  Keys are produced oldest-first, so one FIFO list per branch depth is an exact replacement for the
+  // binary heap: a push is an append (no dependent loads through a megabyte-sized heap), a pop takes the head of the
+  // deepest non-empty list.  Entries live in `heap` (the key) and `heap_dist` (the next link); freed entries are reused.
+  static constexpr uint32_t BQ_NIL = 0xFFFFFFFFu;
+  __device__ __forceinline__ void bq_reset() {
+    for (uint32_t b = 0; b < A->T1; b++) { bk_head[b] = BQ_NIL; bk_tail[b] = BQ_NIL; }
+    pool_top = 0; free_head = BQ_NIL; max_branch = 0;
+  }
+  __device__ __forceinline__ void bq_push(DporKey k) {
+    uint32_t idx;
+    if (free_head != BQ_NIL) { idx = free_head; free_head = heap_dist[idx]; }
+    else { if (pool_top >= A->P.heap_cap) { status = DEMI_DS_HEAP_OVF; return; } idx = pool_top++; }
+    heap[idx] = k; heap_dist[idx] = BQ_NIL;
+    const uint32_t b = dpor_key_branch(k);
+    const uint32_t t = bk_tail[b];
+    if (t == BQ_NIL) bk_head[b] = idx; else heap_dist[t] = idx;
+    bk_tail[b] = idx;
+    n_heap++;
+    if (b > max_branch) max_branch = b;
+  }
+  __device__ __forceinline__ DporKey bq_pop() {          // n_heap > 0
+    uint32_t b = max_branch;
+    while (bk_head[b] == BQ_NIL) b--;
+    const uint32_t idx = bk_head[b];
+    const DporKey k = heap[idx];
+    const uint32_t nx = heap_dist[idx];
+    bk_head[b] = nx;
+    if (nx == BQ_NIL) bk_tail[b] = BQ_NIL;
+    heap_dist[idx] = free_head; free_head = idx;
+    n_heap--;
+    max_branch = b;
+    return k;
   }
 
   __device__ __forceinline__ void set_parent(uint32_t node) { parent_event = node; current_depth = node_depth(node) + 1; }
@@ -364,25 +403,29 @@ struct DporMachine {
       const uint32_t id = cur_trace[i];
       if ((node_pos[id] & 0xFFFFF000u) != stamp) node_pos[id] = stamp | i;
     }
+    // sc(i) = first position of trace[i]'s parent : 12 | first position of trace[i] itself : 12 | receiver : 8
+    auto sc = [&](uint32_t i) -> uint32_t& { return scan[i * scan_stride]; };
     for (uint32_t i = 1; i < n; i++) {
-      const uint4 c = nodes[cur_trace[i]];
-      scan[i] = ((node_pos[c.w & 0xFFFFFu] & 0xFFFu) << 8) | hdr_dst(c.x);
+      const uint32_t id = cur_trace[i];
+      const uint4 c = nodes[id];
+      sc(i) = ((node_pos[c.w & 0xFFFFFu] & 0xFFFu) << 20) | ((node_pos[id] & 0xFFFu) << 8) | hdr_dst(c.x);
     }
-    scan[0] = 0xFF;                                                             // root: receiver "null"
+    sc(0) = 0xFF;                                                               // root: receiver "null"
     for (uint32_t li = 1; li < n && !status; li++) {
-      const uint32_t later = cur_trace[li];
-      const uint32_t ldst = scan[li] & 0xFFu;
-      const uint32_t lfp = node_pos[later] & 0xFFFu;                            // first position of `later`
+      const uint32_t sl = sc(li);
+      const uint32_t ldst = sl & 0xFFu;
+      const uint32_t lfp = (sl >> 8) & 0xFFFu;                                  // first position of `later`
       for (uint32_t ei = 1; ei < li && !status; ei++) {
-        if ((scan[ei] & 0xFFu) != ldst) continue;                               // isCoEnabeled :1096
-        const uint32_t earlier = cur_trace[ei];
-        const uint32_t efp = node_pos[earlier] & 0xFFFu;
+        const uint32_t se = sc(ei);
+        if ((se & 0xFFu) != ldst) continue;                                     // isCoEnabeled :1096
+        const uint32_t efp = (se >> 8) & 0xFFFu;
         uint32_t a = lfp;
-        while (a > efp) a = scan[a] >> 8;                                       // laterN.pathTo(earlierN) :1104
+        while (a > efp) a = sc(a) >> 20;                                        // laterN.pathTo(earlierN) :1104
         if (a == efp) continue;                                                 // later descends from earlier
         uint32_t b = efp;                                                       // getCommonPrefix(...).last :994-1018
         a = lfp;
-        while (a != b) { if (a > b) a = scan[a] >> 8; else b = scan[b] >> 8; }
+        while (a != b) { if (a > b) a = sc(a) >> 20; else b = sc(b) >> 20; }
+        const uint32_t later = cur_trace[li], earlier = cur_trace[ei];
         const uint32_t branch = a;                                              // == trace.indexWhere(_ == lca) :1058
         explored_add(earlier, later);                                           // :1071-1073
         R.races++;
@@ -391,6 +434,7 @@ struct DporMachine {
         if (!capped && explored_has(later, earlier)) continue;
         const DporKey key = dpor_key(branch, k, li, ei);
         if (arv) heap_push2(key, arvind_distance(branch, cur_trace, li, later, earlier));
+        else if (bk_head) bq_push(key);
         else heap_push(key);                                                    // :1134
       }
     }
@@ -400,7 +444,7 @@ struct DporMachine {
       if (!n_heap) { R.exhausted = 1; return false; }
       if (capped && (int32_t)(arv ? heap_dist[0] : 0u) >= max_distance) return false;   // :1145-1146
       if (A->P.stop_if_found && found) return false;                            // :1147
-      const DporKey key = arv ? heap_pop2() : heap_pop();
+      const DporKey key = arv ? heap_pop2() : bk_head ? bq_pop() : heap_pop();
       kt = traces + (size_t)dpor_key_trace(key) * A->T1;
       kb = dpor_key_branch(key); kl = dpor_key_later(key);
       e1 = kt[kl]; e2 = kt[dpor_key_earlier(key)];
@@ -425,6 +469,7 @@ struct DporMachine {
     uint32_t n_viol = 0;
     n_nodes = 1; nodes[0] = make_uint4(0, 0, 0, 0);
     n_explored = n_heap = n_traces = 0; status = 0; found = 0; cur_len = 0;
+    if (bk_head) bq_reset();
     // setInitialDepGraph (:214-217): start from the recorded execution's graph
     if (A->n_init_nodes) {
       if (A->n_init_nodes > A->P.node_cap) status = DEMI_DS_NODE_OVF;
@@ -510,8 +555,11 @@ dpor_kernel(const __grid_constant__ DporArgs args) {
   m.cur_trace = args.cur_trace + (size_t)sid * args.T1;
   m.next_trace = args.next_trace + (size_t)sid * args.T1;
   m.node_pos = args.node_pos + (size_t)sid * args.P.node_cap;
-  m.scan = args.scan + (size_t)sid * args.T1;
+  if (args.scan_in_smem) { m.scan = lane_smem + (size_t)M::WORDS * BD + threadIdx.x; m.scan_stride = BD; }
+  else { m.scan = args.scan + (size_t)sid * args.T1; m.scan_stride = 1; }
   m.path = args.path ? args.path + (size_t)sid * (2 * args.T1 + 4) : nullptr;
+  m.bk_head = args.buckets ? args.buckets + (size_t)sid * 2 * args.T1 : nullptr;
+  m.bk_tail = args.buckets ? m.bk_head + args.T1 : nullptr;
   m.search(sid);
 }
 
