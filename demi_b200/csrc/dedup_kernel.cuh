@@ -28,7 +28,10 @@ dedup_insert_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, unsign
     if (key == DD_EMPTY) key = 0x5D5D5D5D5D5D5D5Dull;                         // reserve the sentinel
     uint64_t s = dd_slot(key, slots);
     for (;;) {
-      unsigned long long prev = atomicCAS(&keys[s], (unsigned long long)DD_EMPTY, (unsigned long long)key);
+      // a slot never changes once it holds a key, so a plain read that already shows a key is final: only an
+      // empty-looking slot needs the compare-and-swap (duplicates, the common case, cost one L2 read)
+      unsigned long long prev = __ldcg(&keys[s]);
+      if (prev == DD_EMPTY) prev = atomicCAS(&keys[s], (unsigned long long)DD_EMPTY, (unsigned long long)key);
       if (prev == DD_EMPTY || prev == key) {
         // the value only ever decreases: a plain (possibly stale, hence larger) read that already shows a
         // smaller index means this record cannot win, and the second atomic is skipped
