@@ -75,7 +75,14 @@ struct ReplayMachine {
 
   __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OB * 3 + a) * BD]; }
   __device__ __forceinline__ LaneState actor(uint32_t a) { return LaneState{smw + a * SW * BD, BD}; }
-  __device__ __forceinline__ bool in_mask(uint32_t i) const { return !mask || ((mask[i >> 6] >> (i & 63)) & 1ull); }
+  // externals are consulted in (nearly) increasing index order: keep the current 64-bit word of the mask in registers
+  uint32_t mword_idx; uint64_t mword;
+  __device__ __forceinline__ bool in_mask(uint32_t i) {
+    if (!mask) return true;
+    const uint32_t w = i >> 6;
+    if (w != mword_idx) { mword_idx = w; mword = __ldg(mask + w); }
+    return (mword >> (i & 63)) & 1ull;
+  }
   // ---- recording (REC): trace + Uniq ids; the pending set becomes an insertion-ordered list so that
   // equal messages leave oldest-first (Queue.dequeue, STSScheduler.scala:729) and Uniq ids pair up
   uint32_t n_rec, n_uniq, n_list;
@@ -244,6 +251,7 @@ struct ReplayMachine {
 
   __device__ __forceinline__ void run(uint32_t test_idx, uint32_t generation, demi_replay_result& out) {
     mask = A->masks ? A->masks + (size_t)test_idx * A->mask_words : nullptr;
+    mword_idx = 0xFFFFFFFFu; mword = 0;
     const uint32_t skip = A->skips ? A->skips[test_idx] : 0xFFFFFFFFu;
     n_rec = n_uniq = n_list = 0;
     gen = generation;
