@@ -130,7 +130,6 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
     *b.p = h->dpor_buf[i];
     if (e == cudaSuccess && b.fill >= 0) e = cudaMemsetAsync(*b.p, b.fill, b.bytes, h->stream);
   }
-  auto cleanup = [&]() {};
   if (e != cudaSuccess) {
     for (size_t i = 0; i < NB; i++) { cudaFree(h->dpor_buf[i]); h->dpor_buf[i] = nullptr; h->dpor_buf_bytes[i] = 0; }
     return fail(h, DEMI_ERR_CUDA, "demi_dpor_batch: %s (%.1f MB of search state)", cudaGetErrorString(e), total / 1e6);
@@ -176,7 +175,6 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   float ms = 0;
   if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-  cleanup();
   if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_dpor_batch: %s", cudaGetErrorString(e));
   h->perf.kernel_ms = ms; h->perf.kernel_launches = 1;
   uint64_t il = 0, del = 0, vi = 0;
@@ -272,10 +270,8 @@ extern "C" int32_t demi_incremental_ddmin(demi_handle* h, const demi_ext_event* 
     d.cap = dist;
     d.memo.clear();                                                              // ddmin = new DDMin(oracle, checkUnmodifed=false) :68
     d.original_num_events = DDMinDriver::popcount(cur); d.total_inputs_pruned = 0;
-    const uint32_t before = d.total_replays;
     cur = d.ddmin2(cur, zero);
     if (d.error != DEMI_OK) return d.error;
-    (void)before;
     out->rounds++;
     dist = dist == 0 ? 2 : dist << 1;                                            // :72
   }
