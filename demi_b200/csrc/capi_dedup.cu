@@ -19,19 +19,17 @@ extern "C" int32_t demi_dedup_compact_dev(demi_handle* h, const void* results_de
   const uint32_t n_blocks = (uint32_t)((n + DD_BLOCK - 1) / DD_BLOCK);
   int32_t rc;
   if (mode == DEMI_DM_UNIQUE) {
-    if ((rc = ensure_bytes(h, &S.keys, &S.keys_b, slots * 8)) != DEMI_OK) return rc;
-    if ((rc = ensure_bytes(h, &S.vals, &S.vals_b, slots * 4)) != DEMI_OK) return rc;
-    CUDA_TRY(h, cudaMemsetAsync(S.keys, 0xFF, slots * 8, s));
-    CUDA_TRY(h, cudaMemsetAsync(S.vals, 0xFF, slots * 4, s));
+    if ((rc = ensure_bytes(h, &S.keys, &S.keys_b, slots * sizeof(DDSlot))) != DEMI_OK) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(S.keys, 0xFF, slots * sizeof(DDSlot), s));
   }
   if ((rc = ensure_bytes(h, &S.keep, &S.keep_b, n)) != DEMI_OK) return rc;
   if ((rc = ensure_bytes(h, &S.counts, &S.counts_b, (size_t)n_blocks * 4)) != DEMI_OK) return rc;
   const demi_fuzz_result* rec = (const demi_fuzz_result*)results_dev;
   if (mode == DEMI_DM_UNIQUE) {
     int grid = (int)std::min<uint64_t>(n_blocks, (uint64_t)h->sm_count * 8);
-    dedup_insert_kernel<<<grid, DD_BLOCK, 0, s>>>(rec, n, (unsigned long long*)S.keys, (uint32_t*)S.vals, slots);
+    dedup_insert_kernel<<<grid, DD_BLOCK, 0, s>>>(rec, n, (DDSlot*)S.keys, slots);
   }
-  dedup_flag_kernel<<<n_blocks, DD_BLOCK, 0, s>>>(rec, n, mode, (const unsigned long long*)S.keys, (const uint32_t*)S.vals, slots,
+  dedup_flag_kernel<<<n_blocks, DD_BLOCK, 0, s>>>(rec, n, mode, (const DDSlot*)S.keys, slots,
                                                   (uint8_t*)S.keep, (uint32_t*)S.counts);
   dedup_scan_kernel<<<1, 1024, 0, s>>>((uint32_t*)S.counts, n_blocks, (unsigned long long*)out_count_dev);
   compact_kernel<<<n_blocks, DD_BLOCK, 0, s>>>(rec, n, (const uint8_t*)S.keep, (const uint32_t*)S.counts,

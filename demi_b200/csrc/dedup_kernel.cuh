@@ -1,7 +1,8 @@
 // dedup_kernel.cuh — K5 (state-hash dedup) and K4 (stable stream compaction).
 // These are the HBM-bound kernels of the engine (SURVEY §8d regime R2): every
-// record is read once (32 B), probes an 8-byte-key / 4-byte-value open-
-// addressing table in HBM with atomics, and kept records are written once.
+// record is read once (32 B), probes an open-addressing table of 16-byte slots
+// {8-byte key, 4-byte value} in HBM with atomics (key and value share a 32-byte
+// sector, so a probe costs one sector), and kept records are written once.
 //   K5a dedup_insert : key = state_hash; table value = min prefix index with that key
 //   K5b dedup_flag   : keep[i] = (value[slot(key_i)] == i)  (or violation != 0); per-block counts
 //   scan             : exclusive scan of the block counts (one block)
@@ -15,27 +16,31 @@ namespace demi {
 
 constexpr int DD_BLOCK = 256;
 constexpr uint64_t DD_EMPTY = ~0ull;
+struct __align__(16) DDSlot { unsigned long long key; uint32_t val; uint32_t pad; };   // memset 0xFF = empty, val = "no index"
 
 __device__ __forceinline__ uint64_t dd_slot(uint64_t key, uint64_t slots) {
   return ((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull >> 20) & (slots - 1);
 }
 
 __global__ void __launch_bounds__(DD_BLOCK)
-dedup_insert_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, unsigned long long* keys, uint32_t* vals, uint64_t slots) {
+dedup_insert_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, DDSlot* table, uint64_t slots) {
   for (uint64_t i = (uint64_t)blockIdx.x * DD_BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * DD_BLOCK) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(rec + i));          // {violation, steps, state_hash lo, hi}
     uint64_t key = (uint64_t)a.z | ((uint64_t)a.w << 32);
     if (key == DD_EMPTY) key = 0x5D5D5D5D5D5D5D5Dull;                         // reserve the sentinel
     uint64_t s = dd_slot(key, slots);
     for (;;) {
-      // a slot never changes once it holds a key, so a plain read that already shows a key is final: only an
-      // empty-looking slot needs the compare-and-swap (duplicates, the common case, cost one L2 read)
-      unsigned long long prev = __ldcg(&keys[s]);
-      if (prev == DD_EMPTY) prev = atomicCAS(&keys[s], (unsigned long long)DD_EMPTY, (unsigned long long)key);
+      // one 16-byte read shows the slot's key and current index.  A slot never changes once it holds a key, so a
+      // key seen here is final and only an empty-looking slot needs the compare-and-swap; the index only ever
+      // decreases, so a (possibly stale, hence larger) value that is already smaller means this record cannot win.
+      // (two 64-bit elements: the memory model treats a vector access as one access per element, so the key
+      // cannot tear)
+      const ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2*>(table + s));
+      unsigned long long prev = q.x;
+      uint32_t seen = (uint32_t)q.y;
+      if (prev == DD_EMPTY) { prev = atomicCAS(&table[s].key, (unsigned long long)DD_EMPTY, (unsigned long long)key); seen = 0xFFFFFFFFu; }
       if (prev == DD_EMPTY || prev == key) {
-        // the value only ever decreases: a plain (possibly stale, hence larger) read that already shows a
-        // smaller index means this record cannot win, and the second atomic is skipped
-        if (__ldcg(&vals[s]) > (uint32_t)i) atomicMin(&vals[s], (uint32_t)i);
+        if (seen > (uint32_t)i) atomicMin(&table[s].val, (uint32_t)i);
         break;
       }
       s = (s + 1) & (slots - 1);
@@ -45,8 +50,7 @@ dedup_insert_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, unsign
 
 __global__ void __launch_bounds__(DD_BLOCK)
 dedup_flag_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, int mode,
-                  const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t slots,
-                  uint8_t* keep, uint32_t* block_counts) {
+                  const DDSlot* __restrict__ table, uint64_t slots, uint8_t* keep, uint32_t* block_counts) {
   const uint64_t i = (uint64_t)blockIdx.x * DD_BLOCK + threadIdx.x;
   bool k = false;
   if (i < n) {
@@ -57,8 +61,11 @@ dedup_flag_kernel(const demi_fuzz_result* __restrict__ rec, uint64_t n, int mode
       uint64_t key = (uint64_t)a.z | ((uint64_t)a.w << 32);
       if (key == DD_EMPTY) key = 0x5D5D5D5D5D5D5D5Dull;
       uint64_t s = dd_slot(key, slots);
-      while (keys[s] != key) s = (s + 1) & (slots - 1);
-      k = vals[s] == (uint32_t)i;
+      for (;;) {
+        const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2*>(table + s));
+        if (q.x == key) { k = (uint32_t)q.y == (uint32_t)i; break; }
+        s = (s + 1) & (slots - 1);
+      }
     }
     keep[i] = k ? 1 : 0;
   }
