@@ -98,126 +98,156 @@ struct Raft5 {
   }
 
   // S is an accessor: s[i] is byte i of this actor's state
-  template <class S, class O>
-  __device__ static __forceinline__ void step_down(O& out, S& s, uint32_t t) {
-    if (s[ROLE] == LEADER) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
-    if (t > s[TERM]) { s[TERM] = (uint8_t)t; s[VOTED] = (uint8_t)NONE; }
-    s[ROLE] = FOLLOWER;
-    s[VOTES] = 0;
+  template <class C, class O>
+  __device__ static __forceinline__ void step_down(O& out, C& c, uint32_t t) {
+    if (c[ROLE] == LEADER) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
+    if (t > c[TERM]) { c[TERM] = (uint8_t)t; c[VOTED] = (uint8_t)NONE; }
+    c[ROLE] = FOLLOWER;
+    c[VOTES] = 0;
   }
-  template <class S, class O>
-  __device__ static __forceinline__ void send_append(O& out, S& s, uint32_t j) {
+  template <class S, class C, class O>
+  __device__ static __forceinline__ void send_append(O& out, S& s, C& c, uint32_t j) {
     uint32_t prev = s[NEXT + j];
     uint32_t pt = prev ? s[LOGTERM + prev - 1] : 0u;
-    uint32_t has = prev < s[LOGLEN] ? 1u : 0u;
+    uint32_t has = prev < c[LOGLEN] ? 1u : 0u;
     uint32_t et = has ? s[LOGTERM + prev] : 0u, ev = has ? s[LOGVAL + prev] : 0u;
-    out.send(j, APPEND_ENTRIES, (uint32_t)s[TERM] | (prev << 8) | (pt << 16) | ((uint32_t)s[COMMIT] << 24),
+    out.send(j, APPEND_ENTRIES, (uint32_t)c[TERM] | (prev << 8) | (pt << 16) | ((uint32_t)c[COMMIT] << 24),
              has | (et << 8) | (ev << 16));
   }
+
+  // The eight scalar bytes of the state (words 0 and 1) are held in two registers for the duration of a receive():
+  // a field access is a bit-field extract / insert instead of a byte load or store in (interleaved) shared memory.
+  template <class S>
+  struct Scalars {
+    uint32_t w0, w1;
+    struct Ref {
+      Scalars* c; uint32_t i;
+      __device__ __forceinline__ operator uint32_t() const { return ((i < 4 ? c->w0 : c->w1) >> ((i & 3) * 8)) & 0xFFu; }
+      __device__ __forceinline__ Ref& operator=(uint32_t v) {
+        const uint32_t sh = (i & 3) * 8;
+        uint32_t& w = i < 4 ? c->w0 : c->w1;
+        w = (w & ~(0xFFu << sh)) | ((v & 0xFFu) << sh);
+        return *this;
+      }
+      __device__ __forceinline__ Ref& operator=(const Ref& o) { return *this = (uint32_t)o; }
+      __device__ __forceinline__ Ref& operator|=(uint32_t v) { return *this = (uint32_t)*this | v; }
+      __device__ __forceinline__ Ref& operator++(int) { return *this = (uint32_t)*this + 1u; }
+    };
+    __device__ __forceinline__ explicit Scalars(const S& s) : w0(s.w(0)), w1(s.w(1)) {}
+    __device__ __forceinline__ Ref operator[](uint32_t i) { return Ref{this, i}; }
+    __device__ __forceinline__ void flush(const S& s) const { s.w(0) = w0; s.w(1) = w1; }
+  };
 
   template <class S, class O>
   __device__ static __forceinline__ void receive(O& out, uint32_t self, S s, uint32_t src,
                                                  uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
-    const uint32_t last_idx = s[LOGLEN];
+    Scalars<S> c(s);
+    receive_body(out, self, s, c, src, type, p0, p1, flags);
+    c.flush(s);
+  }
+  template <class S, class C, class O>
+  __device__ static __forceinline__ void receive_body(O& out, uint32_t self, S& s, C& c, uint32_t src,
+                                                      uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
+    const uint32_t last_idx = c[LOGLEN];
     const uint32_t last_term = last_idx ? s[LOGTERM + last_idx - 1] : 0u;
     const uint32_t t = p0 & 0xFF;
-    if (type != BOOT && type != CLIENT_CMD && s[ROLE] == INIT) return;
+    if (type != BOOT && type != CLIENT_CMD && c[ROLE] == INIT) return;
     switch (type) {
       case BOOT:
-        if (s[ROLE] == INIT) { s[ROLE] = FOLLOWER; out.schedule_repeating(ELECTION_TICK, 0, 0); }
+        if (c[ROLE] == INIT) { c[ROLE] = FOLLOWER; out.schedule_repeating(ELECTION_TICK, 0, 0); }
         break;
       case CLIENT_CMD:
-        if (s[ROLE] == LEADER && s[LOGLEN] < LOG_CAP) {
-          s[LOGTERM + s[LOGLEN]] = s[TERM];
-          s[LOGVAL + s[LOGLEN]] = (uint8_t)(p0 & 0x7F);
-          s[LOGLEN]++;
+        if (c[ROLE] == LEADER && c[LOGLEN] < LOG_CAP) {
+          s[LOGTERM + c[LOGLEN]] = c[TERM];
+          s[LOGVAL + c[LOGLEN]] = (uint8_t)(p0 & 0x7F);
+          c[LOGLEN]++;
         }
         break;
       case ELECTION_TICK:
-        if (s[ROLE] == LEADER) break;
-        if (s[HEARD]) { s[HEARD] = 0; break; }
-        if (s[TERM] == 255) break;
-        s[TERM]++;
-        s[ROLE] = CANDIDATE;
-        s[VOTED] = (uint8_t)self;
-        s[VOTES] = (uint8_t)(1u << self);
+        if (c[ROLE] == LEADER) break;
+        if (c[HEARD]) { c[HEARD] = 0; break; }
+        if (c[TERM] == 255) break;
+        c[TERM]++;
+        c[ROLE] = CANDIDATE;
+        c[VOTED] = (uint8_t)self;
+        c[VOTES] = (uint8_t)(1u << self);
 #pragma unroll 1
         for (uint32_t j = 0; j < 5; j++)
-          if (j != self) out.send(j, REQUEST_VOTE, (uint32_t)s[TERM] | (last_idx << 8) | (last_term << 16), 0);
+          if (j != self) out.send(j, REQUEST_VOTE, (uint32_t)c[TERM] | (last_idx << 8) | (last_term << 16), 0);
         break;
       case REQUEST_VOTE: {
         uint32_t li = (p0 >> 8) & 0xFF, lt = (p0 >> 16) & 0xFF;
-        if (t > s[TERM]) step_down(out, s, t);
+        if (t > c[TERM]) step_down(out, c, t);
         bool up_to_date = lt > last_term || (lt == last_term && li >= last_idx);
-        bool can_vote = (s[VOTED] == NONE || s[VOTED] == src) || (flags & BUG_DOUBLE_VOTE);
-        uint32_t grant = (t == s[TERM] && can_vote && up_to_date) ? 1u : 0u;
-        if (grant) { s[VOTED] = (uint8_t)src; s[HEARD] = 1; }
-        out.send(src, VOTE_REPLY, (uint32_t)s[TERM] | (grant << 8), 0);
+        bool can_vote = (c[VOTED] == NONE || c[VOTED] == src) || (flags & BUG_DOUBLE_VOTE);
+        uint32_t grant = (t == c[TERM] && can_vote && up_to_date) ? 1u : 0u;
+        if (grant) { c[VOTED] = (uint8_t)src; c[HEARD] = 1; }
+        out.send(src, VOTE_REPLY, (uint32_t)c[TERM] | (grant << 8), 0);
         break;
       }
       case VOTE_REPLY: {
         uint32_t g = (p0 >> 8) & 1u;
-        if (t > s[TERM]) { step_down(out, s, t); break; }
-        if (s[ROLE] == CANDIDATE && t == s[TERM] && g) {
-          s[VOTES] |= (uint8_t)(1u << src);
-          if (__popc((uint32_t)s[VOTES]) >= 3) {
-            s[ROLE] = LEADER;
-            for (uint32_t j = 0; j < 5; j++) { s[NEXT + j] = s[LOGLEN]; s[MATCH + j] = 0; }
-            if (s[LOGLEN] < LOG_CAP) {                       // leader no-op entry
-              s[LOGTERM + s[LOGLEN]] = s[TERM];
-              s[LOGVAL + s[LOGLEN]] = (uint8_t)(0x80u | self);
-              s[LOGLEN]++;
+        if (t > c[TERM]) { step_down(out, c, t); break; }
+        if (c[ROLE] == CANDIDATE && t == c[TERM] && g) {
+          c[VOTES] |= (uint8_t)(1u << src);
+          if (__popc((uint32_t)c[VOTES]) >= 3) {
+            c[ROLE] = LEADER;
+            for (uint32_t j = 0; j < 5; j++) { s[NEXT + j] = c[LOGLEN]; s[MATCH + j] = 0; }
+            if (c[LOGLEN] < LOG_CAP) {                       // leader no-op entry
+              s[LOGTERM + c[LOGLEN]] = c[TERM];
+              s[LOGVAL + c[LOGLEN]] = (uint8_t)(0x80u | self);
+              c[LOGLEN]++;
             }
 #pragma unroll 1
-            for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
+            for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, c, j);
             out.schedule_repeating(HEARTBEAT_TICK, 0, 0);
           }
         }
         break;
       }
       case HEARTBEAT_TICK:
-        if (s[ROLE] == LEADER) {
+        if (c[ROLE] == LEADER) {
 #pragma unroll 1
-          for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, j);
+          for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, c, j);
         }
         break;
       case APPEND_ENTRIES: {
         uint32_t prev = (p0 >> 8) & 0xFF, pt = (p0 >> 16) & 0xFF, lc = (p0 >> 24) & 0xFF;
         uint32_t has = p1 & 1u, et = (p1 >> 8) & 0xFF, ev = (p1 >> 16) & 0xFF;
-        if (t < s[TERM]) { out.send(src, APPEND_REPLY, (uint32_t)s[TERM], 0); break; }
-        if (t > s[TERM] || s[ROLE] != FOLLOWER) step_down(out, s, t);
-        s[HEARD] = 1;
-        bool ok = prev <= s[LOGLEN] && (prev == 0 || s[LOGTERM + prev - 1] == pt);
-        if (!ok) { out.send(src, APPEND_REPLY, (uint32_t)s[TERM], 0); break; }
+        if (t < c[TERM]) { out.send(src, APPEND_REPLY, (uint32_t)c[TERM], 0); break; }
+        if (t > c[TERM] || c[ROLE] != FOLLOWER) step_down(out, c, t);
+        c[HEARD] = 1;
+        bool ok = prev <= c[LOGLEN] && (prev == 0 || s[LOGTERM + prev - 1] == pt);
+        if (!ok) { out.send(src, APPEND_REPLY, (uint32_t)c[TERM], 0); break; }
         uint32_t mi = prev;
         if (has) {
-          if (s[LOGLEN] > prev && s[LOGTERM + prev] != et) {          // conflict: truncate
+          if (c[LOGLEN] > prev && s[LOGTERM + prev] != et) {          // conflict: truncate
             for (uint32_t k = prev; k < LOG_CAP; k++) { s[LOGTERM + k] = 0; s[LOGVAL + k] = 0; }
-            s[LOGLEN] = (uint8_t)prev;
+            c[LOGLEN] = (uint8_t)prev;
           }
-          if (s[LOGLEN] == prev && prev < LOG_CAP) {
+          if (c[LOGLEN] == prev && prev < LOG_CAP) {
             s[LOGTERM + prev] = (uint8_t)et; s[LOGVAL + prev] = (uint8_t)ev;
-            s[LOGLEN] = (uint8_t)(prev + 1);
+            c[LOGLEN] = (uint8_t)(prev + 1);
           }
-          if (s[LOGLEN] > prev) mi = prev + 1;
+          if (c[LOGLEN] > prev) mi = prev + 1;
         }
         uint32_t nc = lc < mi ? lc : mi;
-        if (nc > s[COMMIT]) s[COMMIT] = (uint8_t)nc;
-        out.send(src, APPEND_REPLY, (uint32_t)s[TERM] | (1u << 8) | (mi << 16), 0);
+        if (nc > c[COMMIT]) c[COMMIT] = (uint8_t)nc;
+        out.send(src, APPEND_REPLY, (uint32_t)c[TERM] | (1u << 8) | (mi << 16), 0);
         break;
       }
       case APPEND_REPLY: {
         uint32_t ok = (p0 >> 8) & 1u, mi = (p0 >> 16) & 0xFF;
-        if (t > s[TERM]) { step_down(out, s, t); break; }
-        if (s[ROLE] != LEADER || t != s[TERM]) break;
+        if (t > c[TERM]) { step_down(out, c, t); break; }
+        if (c[ROLE] != LEADER || t != c[TERM]) break;
         if (ok) {
           if (mi > s[MATCH + src]) s[MATCH + src] = (uint8_t)mi;
           if (mi > s[NEXT + src]) s[NEXT + src] = (uint8_t)mi;
-          for (uint32_t idx = s[LOGLEN]; idx > s[COMMIT]; idx--) {
-            if (s[LOGTERM + idx - 1] != s[TERM] && !(flags & BUG_STALE_COMMIT)) continue;
+          for (uint32_t idx = c[LOGLEN]; idx > c[COMMIT]; idx--) {
+            if (s[LOGTERM + idx - 1] != c[TERM] && !(flags & BUG_STALE_COMMIT)) continue;
             uint32_t cnt = 1;
             for (uint32_t k = 0; k < 5; k++) if (k != self && s[MATCH + k] >= idx) cnt++;
-            if (cnt >= 3) { s[COMMIT] = (uint8_t)idx; break; }
+            if (cnt >= 3) { c[COMMIT] = (uint8_t)idx; break; }
           }
         } else if (s[NEXT + src] > 0) {
           s[NEXT + src]--;
