@@ -355,7 +355,16 @@ struct LaneMachine {
     ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
     MODEL::receive(ob, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
     if (ob.overflow) { defer(); return 0; }
-    // equal sends out of one receive() would share a Unique (child reuse): defer
+    // equal sends out of one receive() would share a Unique (child reuse): defer.  A 64-bit filter over the
+    // (op, dst, type) words settles the common case — all headers distinct — in one pass; only a filter hit
+    // (a real duplicate, or a 1-in-64 collision) pays for the pairwise comparison.
+    uint64_t seen = 0; bool maybe = false;
+    for (uint32_t i = 0; i < ob.n; i++) {
+      const uint64_t bit = 1ull << ((ob.base[(i * 3) * BD] * 0x9E3779B1u) >> 26);
+      maybe |= (seen & bit) != 0;
+      seen |= bit;
+    }
+    if (maybe)
     for (uint32_t i = 1; i < ob.n; i++) {
       const uint32_t wi = ob.base[(i * 3) * BD];
       for (uint32_t j = 0; j < i; j++)
