@@ -36,7 +36,7 @@ MODEL_FLAGS = 1            # Raft5 BUG_DOUBLE_VOTE: gives a non-empty, stable vi
 RESULT_BYTES = 32          # sizeof(demi_fuzz_result): the algorithmic HBM bytes per prefix
 # dram__bytes_read.sum + dram__bytes_write.sum of fuzz_lane_kernel per prefix, from the one
 # `ncu --set full` capture in profiles/r1_ncu_summary.md (v3, 4e6 prefixes: 2.18 GB)
-NCU_DRAM_BYTES_PER_PREFIX = 545.0
+NCU_DRAM_BYTES_PER_PREFIX = 502.0
 PREFIXES_PER_STEP = 10_000_000
 METRIC = "schedule prefixes/sec (5-actor Raft, depth 50)"
 
@@ -270,10 +270,10 @@ def main():
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PREFIX * n, "peak_kind": peak_kind,
                          "kernel": "fuzz_lane_kernel<Raft5,256,96> (+ fuzz_kernel<Raft5,256,32> for deferred prefixes)", "algorithmic_bytes_per_prefix": RESULT_BYTES,
                          "kernel_ms": k_ms,
-                         "issue_slot_utilisation": 0.695, "warp_instructions_per_prefix": 3712,
+                         "issue_slot_utilisation": 0.680, "warp_instructions_per_prefix": 3472,
                          "note": "on-chip-state fuzz regime (SURVEY §8d R1): the only algorithmic HBM traffic is "
                                  "the 32 B result record, so the kernel is issue-slot bound, not HBM bound "
-                                 "(smsp__issue_active 69.5 % of peak, profiles/r1_ncu_summary.md); `traffic` is the ncu "
+                                 "(smsp__issue_active 68.0 % of peak, profiles/r1_ncu_summary.md, v4 capture); `traffic` is the ncu "
                                  "DRAM bytes per launch scaled from the 4e6-prefix capture (pending-array lines "
                                  "evicted from L2)"},
             "clocks": sampler.summary(),
