@@ -47,6 +47,41 @@ def main():
                         result=np.array([r]), mcs=mcs, total_replays=np.int64(total), iteration_sizes=iters,
                         verified=np.int64(ver), masks=masks, replay=rep)
     print("trace", len(ev), "events; MCS", bin(int(mcs[0])), "tests", total)
+    extras(model, flags, ext, seed, ev, par, int(r["violation"]), int(r["steps"]))
+
+
+def extras(model, flags, ext, seed, ev, par, code, steps):
+    """Round-1 additions on the same recorded execution: provenance pruning, plain and seeded / capped DPOR,
+    IncrementalDDMin, internal minimization with both removal strategies."""
+    out = {}
+    keep, po = O.fuzz_provenance(model, ext, seed, 50, 5, 1, model_flags=flags)
+    out["prov_keep"], out["prov_out"] = keep, np.array([po])
+    dext = ext[(ext["kind"] == 1) | (ext["kind"] == 3)]
+    rc, dr, dv, dh = O.dpor_search(model, dext, 40, 60, model_flags=flags, node_cap=4096, explored_slots=1 << 16, heap_cap=1 << 16)
+    out["dpor_result"], out["dpor_hashes"] = np.array([dr]), dh
+    sd = O.dpor_seed(ev, par)
+    rows, hashes = [], []
+    for arvind, prio, caps in ((1, 1, [0, 2, 4, 8, -1]), (0, 1, [0, 0, -1]), (0, 0, [-1])):
+        inst = O.DporInstance(model, dext, steps, 80, seed=sd, arvind=arvind, prioritize_pending=prio, model_flags=flags,
+                              looking_for=code)
+        for c in caps:
+            rr, hh = inst.test(c)
+            rows.append(rr); hashes.append(hh)
+        inst.close()
+    out["inst_results"] = np.array(rows)
+    out["inst_hashes"] = np.concatenate(hashes) if hashes else np.zeros(0, dtype=np.uint64)
+    rc, mcs, st = O.incremental_ddmin(model, dext, steps, 2000, sd, model_flags=flags, looking_for=code, stop_at_size=1,
+                                      max_max_distance=64)
+    out["inc_mcs"] = mcs
+    out["inc_stats"] = np.array([st["total_replays"], st["rounds"], st["interleavings"], st["instances"]], dtype=np.int64)
+    rr, vtrace = O.replay_trace(model, ev, ext, O.full_mask(ext), looking_for=code, model_flags=flags)
+    mext = ext[ext["kind"] != 4]
+    for name, fl in (("ltr", 0), ("fifo", 0x100)):
+        rc, tr, total, sizes, unig = O.internal_minimize(model, vtrace, mext, code, model_flags=flags, flags=fl)
+        out["im_%s_trace" % name], out["im_%s_sizes" % name] = tr, sizes
+        out["im_%s_meta" % name] = np.array([rc, total, unig], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "raft5_round1_extras.npz"), **out)
+    print("extras:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
 if __name__ == "__main__":
