@@ -10,6 +10,9 @@
  *   STSScheduler.test                   (schedulers/STSScheduler.scala:199-310)
  *   DDMin.minimize                      (minification/DeltaDebugging.scala:27-62)
  *   DPORwHeuristics.test                (schedulers/DPORwHeuristics.scala:1193-1242)
+ *   IncrementalDDMin / ResumableDPOR    (minification/IncrementalDeltaDebugging.scala:20-122)
+ *   STSSchedMinimizer.minimize          (minification/internal_minimization/ScheduleCheckers.scala:19-107)
+ *   ProvenanceTracker.pruneConcurrentEvents (schedulers/Util.scala:267-376)
  * Each entry point below names the reference method it replaces.  A JVM host
  * binds these through a ~150-line JNI shim (jni/DemiNative.c).
  *
