@@ -32,6 +32,32 @@ def test_struct_sizes(native):
     assert native.RESULT_DTYPE.itemsize == 32 and native.EVENT_DTYPE.itemsize == 16 and native.EXT_DTYPE.itemsize == 16
 
 
+def test_binding_layouts_match_the_header(native, tmp_path):
+    """sizeof() of every POD of include/demi_b200.h, as the C compiler sees it, equals the ctypes / numpy mirror."""
+    import subprocess
+    mirror = {
+        "demi_msg": 12, "demi_ext_event": native.EXT_DTYPE.itemsize, "demi_event": native.EVENT_DTYPE.itemsize,
+        "demi_config": C.sizeof(native.Config), "demi_fuzz_result": native.RESULT_DTYPE.itemsize,
+        "demi_fuzz_params": C.sizeof(native.FuzzParams), "demi_perf": C.sizeof(native.Perf),
+        "demi_replay_result": native.REPLAY_DTYPE.itemsize, "demi_ddmin_out": C.sizeof(native.DDMinOut),
+        "demi_intmin_out": C.sizeof(native.IntMinOut), "demi_dpor_params": C.sizeof(native.DporParams),
+        "demi_dpor_result": native.DPOR_RESULT_DTYPE.itemsize, "demi_dpor_violation": native.DPOR_VIOL_DTYPE.itemsize,
+        "demi_dpor_seed": C.sizeof(native.DporSeed), "demi_dpor_ex": C.sizeof(native.DporEx),
+        "demi_incddmin_out": C.sizeof(native.IncDDMinOut), "demi_provenance_out": native.PROVENANCE_DTYPE.itemsize,
+    }
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "demi_b200.h"\nint main(void) {\n' +
+                   "".join('  printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in mirror) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {l.split()[0]: int(l.split()[1]) for l in out.strip().splitlines()}
+    assert got == mirror
+    # every typedef'd struct of the header is covered
+    declared = set(re.findall(r"typedef struct (demi_[a-z_0-9]+)", open(os.path.join(ROOT, "include", "demi_b200.h")).read()))
+    assert declared - {"demi_handle"} == set(mirror)
+
+
 def test_no_cpu_fallback(native):
     """Without a CUDA device the product path fails loudly instead of computing on the host."""
     import demi_b200 as D
