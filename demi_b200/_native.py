@@ -103,7 +103,29 @@ EXPORTS = [
     "demi_dedup_compact_dev", "demi_dedup_compact",
     "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
     "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
+    "demi_dpor_frontier", "demi_dpor_frontier_multi", "demi_comm_unique_id", "demi_comm_init", "demi_comm_rank",
+    "demi_create_multi",
 ]
+
+
+class FrontierParams(C.Structure):
+    _fields_ = [("max_messages", C.c_int32), ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32),
+                ("width", C.c_uint32), ("max_interleavings", C.c_uint64), ("explored_slots", C.c_uint64),
+                ("pool_cap", C.c_uint64), ("trace_cap", C.c_uint32), ("rounds_per_exchange", C.c_uint32),
+                ("steal_max", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FRONTIER_RESULT_DTYPE = np.dtype([
+    ("interleavings", "<u8"), ("violations", "<u8"), ("deliveries", "<u8"), ("races", "<u8"),
+    ("keys_enqueued", "<u8"), ("keys_dropped", "<u8"), ("explored_pairs", "<u8"), ("pool_left", "<u8"),
+    ("records_sent", "<u8"), ("records_received", "<u8"), ("bytes_sent", "<u8"),
+    ("rounds", "<u4"), ("exchanges", "<u4"), ("exhausted", "<u4"), ("budget_exhausted", "<u4"),
+    ("status", "<u4"), ("trace_slots", "<u4"),
+    ("exec_ms", "<f8"), ("scan_ms", "<f8"), ("select_ms", "<f8"), ("exchange_ms", "<f8")])
+FRONTIER_ENTRY_DTYPE = np.dtype([("id", "<u8"), ("src", "u1"), ("dst", "u1"), ("type", "u1"), ("pad", "u1"),
+                                 ("parent_pos", "<u2"), ("pad2", "<u2")])
+assert FRONTIER_RESULT_DTYPE.itemsize == 144 and C.sizeof(FrontierParams) == 56 and FRONTIER_ENTRY_DTYPE.itemsize == 16
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -170,6 +192,19 @@ def lib():
     L.demi_incremental_ddmin.restype = C.c_int32
     L.demi_incremental_ddmin.argtypes = [vp, vp, C.c_uint32, C.POINTER(DporParams), C.c_uint32, C.POINTER(DporSeed),
                                          C.c_int32, C.c_uint32, vp, C.c_uint32, C.POINTER(IncDDMinOut)]
+    L.demi_dpor_frontier.restype = C.c_int32
+    L.demi_dpor_frontier.argtypes = [vp, vp, C.c_uint32, C.POINTER(FrontierParams), vp, vp, C.c_uint32, vp, C.c_uint64]
+    L.demi_dpor_frontier_multi.restype = C.c_int32
+    L.demi_dpor_frontier_multi.argtypes = [vp, C.c_int32, vp, C.c_uint32, C.POINTER(FrontierParams), vp, vp, C.c_uint32,
+                                           vp, C.c_uint64]
+    L.demi_comm_unique_id.restype = C.c_int32
+    L.demi_comm_unique_id.argtypes = [vp]
+    L.demi_comm_init.restype = C.c_int32
+    L.demi_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.demi_comm_rank.restype = C.c_int32
+    L.demi_comm_rank.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.demi_create_multi.restype = C.c_int32
+    L.demi_create_multi.argtypes = [C.POINTER(Config), vp, C.c_int32, vp]
     L.demi_stats.restype = C.c_int32
     L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
     _lib = L

@@ -48,11 +48,37 @@ def build_engine(force=False, verbose=False):
     return LIB
 
 
+def _cpu_stamp():
+    """The oracle is compiled -march=native, so a library built on another machine (it travels with the
+    gpurun snapshot) is rebuilt on the machine that runs it: model name + ISA flags identify the CPU."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            if line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+            if model and flags:
+                break
+    except OSError:
+        pass
+    return hashlib.sha1((model + "|" + flags).encode()).hexdigest()
+
+
+ORACLE_STAMP = os.path.join(ORACLE_DIR, ".build_cpu")
+
+
 def build_oracle(force=False):
     srcs = _sources(ORACLE_DIR, (".c", ".h")) + _sources(os.path.join(ROOT, "include"), (".h",))
-    if not force and _newer(ORACLE_LIB, srcs):
+    srcs.append(os.path.join(ORACLE_DIR, "Makefile"))
+    stamp = _cpu_stamp()
+    same_cpu = os.path.exists(ORACLE_STAMP) and open(ORACLE_STAMP).read().strip() == stamp
+    if not force and same_cpu and _newer(ORACLE_LIB, srcs):
         return ORACLE_LIB
     subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle.so"])
+    with open(ORACLE_STAMP, "w") as f:
+        f.write(stamp + "\n")
     return ORACLE_LIB
 
 

@@ -60,8 +60,11 @@ struct demi_handle {
   void* rp_masks = nullptr; size_t rp_masks_bytes = 0;
   void* rp_results = nullptr; size_t rp_results_bytes = 0;
   unsigned long long* rp_counters = nullptr;
+  // ---- communicator (capi_frontier.cu): NCCL inside the library
+  void* comm = nullptr;
 };
 void demi_replay_free(demi_handle* h);
+void demi_comm_free(demi_handle* h);
 
 inline int32_t ensure_bytes(demi_handle* h, void** p, size_t* cap, size_t need);
 

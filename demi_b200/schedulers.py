@@ -270,6 +270,44 @@ class Engine(object):
         del alive
         return mcs, out
 
+    # ---- frontier ("wide") DPOR: one DPORwHeuristics.test explored as a frontier of backtrack points
+    @staticmethod
+    def frontier_params(max_messages, max_interleavings, width, looking_for=0, stop_if_found=False,
+                        explored_slots=1 << 22, pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096):
+        if trace_cap is None:
+            trace_cap = int(max_interleavings) + 8 * steal_max + 16
+        return N.FrontierParams(max_messages, looking_for or 0, 1 if stop_if_found else 0, width, max_interleavings,
+                                explored_slots, pool_cap, trace_cap, rounds_per_exchange, steal_max, 0)
+
+    def comm_init(self, unique_id, rank, world):
+        """Join the library's NCCL communicator (demi_comm_init); unique_id = the 128 bytes rank 0 made."""
+        buf = (C.c_uint8 * N.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._check(N.lib().demi_comm_init(self._h, buf, rank, world))
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * N.COMM_ID_BYTES)()
+        rc = N.lib().demi_comm_unique_id(buf)
+        if rc != N.OK:
+            raise DemiError(rc, (N.lib().demi_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def dpor_frontier(self, program, F, cap_viol=4096, want_hashes=True):
+        """demi_dpor_frontier on this handle's device (collective when the handle has a communicator).
+        Returns (result record, violations, schedule hashes of this rank's interleavings in execution order)."""
+        ext = program if isinstance(program, np.ndarray) else pack_externals(program)
+        ext = np.ascontiguousarray(ext, dtype=N.EXT_DTYPE)
+        res = np.zeros(1, dtype=N.FRONTIER_RESULT_DTYPE)
+        viol = np.zeros(cap_viol, dtype=N.DPOR_VIOL_DTYPE)
+        cap_h = int(F.max_interleavings) + int(F.width) + 1 if want_hashes else 0
+        hashes = np.zeros(max(cap_h, 1), dtype=np.uint64)
+        rc = N.lib().demi_dpor_frontier(self._h, ext.ctypes.data, len(ext), C.byref(F), res.ctypes.data,
+                                        viol.ctypes.data, cap_viol, hashes.ctypes.data if want_hashes else None, cap_h)
+        self.last_frontier = res[0]
+        self._check(rc)
+        r = res[0]
+        return r, viol[:min(int(r["violations"]), cap_viol)].copy(), hashes[:min(int(r["interleavings"]), cap_h)].copy()
+
     def stats(self):
         s = N.Perf()
         self._check(N.lib().demi_stats(self._h, C.byref(s)))

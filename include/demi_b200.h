@@ -369,6 +369,91 @@ int32_t demi_incremental_ddmin(demi_handle* h, const demi_ext_event* externals, 
                                int32_t max_max_distance, uint32_t stop_at_size,
                                uint64_t* mcs_mask, uint32_t mask_words, demi_incddmin_out* out);
 
+/* ---------------------------------------------------- frontier ("wide") DPOR */
+/* ONE DPORwHeuristics.test (DPORwHeuristics.scala:1193-1242, dpor() :1020-1185) explored as a frontier of
+ * backtrack points instead of one interleaving at a time (BASELINE.json configs[2]).  The algorithmic content is the
+ * reference's: the same race test (isCoEnabeled :1091-1110), the same backtrack point (analyze_dep :1043-1077:
+ * branchI = trace index of the common ancestor, replayThis = trace(branchI+1..laterI) minus `earlier`), the same
+ * explored-pair history (ExploredTacker, AuxilaryTypes.scala:209-246; setExplored at :1071-1073 and :1169-1171,
+ * isExplored at :1156-1160) and DefaultBacktrackOrdering (deeper branch first, BacktrackOrdering.scala:58-69).
+ * What changes is how many backtrack points leave the queue between two race scans: a ROUND dequeues up to `width`
+ * unexplored points in queue order, replays them concurrently, then scans all new traces.  width = 1 is the
+ * reference's order (one getNext per dpor(), :1142-1185); for width > 1 the set of visited interleavings is that of
+ * the same algorithm under a different — but fully specified, deterministic — dequeue schedule:
+ *   - queue order: branch descending, then trace slot, later position, earlier position ascending (the FIFO order
+ *     of the reference's enqueue loop, :1122-1139, when width = 1);
+ *   - a dequeued point whose pair is explored is dropped (:1156-1160); the others are marked explored (:1169-1171)
+ *     in queue order, so of two points with the same pair in one round the first one runs;
+ *   - nextTrace = keyTrace.take(branchI+1) ++ replayThis: the prefix comes from the trace the point was computed
+ *     on (under depth-first order that is the reference's `trace.take(maxIndex+1)`, :1180);
+ *   - after a round every new trace is scanned for laterI beyond its own branch point (the pairs below it were
+ *     scanned on the parent trace and would only re-enqueue copies that are dropped when dequeued); all races of the
+ *     round are marked explored before any of its points is enqueued (enqueueing an explored point is a no-op).
+ * Dependency-graph nodes are content-addressed: id(child) = hash(id(parent), snd, rcv, fingerprint) — the child
+ * reuse rule of getMessage (:773-801) without a shared table, so a backtrack record is self-contained and can move
+ * to another GPU.  Multi-GPU: every rank owns a queue, an explored set and a trace store; after every
+ * `rounds_per_exchange` rounds the ranks all-gather their queue lengths, compute the same transfer plan and move
+ * surplus records (shallowest first) with grouped ncclSend/ncclRecv (demi_comm_*).  Results are deterministic for a
+ * given (width, ranks, rounds_per_exchange, steal_max). */
+typedef struct demi_frontier_params {
+  int32_t  max_messages;          /* setMaxMessagesToSchedule (:121-126); 1..1000                        */
+  uint32_t looking_for;           /* ViolationFingerprint code, 0 = any                                  */
+  uint32_t stop_if_found;         /* stopIfViolationFound (:82), applied at round granularity            */
+  uint32_t width;                 /* backtrack points replayed per round per rank                        */
+  uint64_t max_interleavings;     /* exploration budget over all ranks                                    */
+  uint64_t explored_slots;        /* per rank, power of two                                              */
+  uint64_t pool_cap;              /* per rank: queued backtrack points                                   */
+  uint32_t trace_cap;             /* per rank: trace slots (executed + imported)                         */
+  uint32_t rounds_per_exchange;   /* steal period in rounds (ignored on one rank)                        */
+  uint32_t steal_max;             /* most records one rank sends to one other rank per exchange          */
+  uint32_t reserved;
+} demi_frontier_params;
+typedef struct demi_frontier_result {   /* per rank */
+  uint64_t interleavings;         /* executions performed on this rank                                   */
+  uint64_t violations;
+  uint64_t deliveries;
+  uint64_t races;                 /* co-enabled pairs analysed                                           */
+  uint64_t keys_enqueued, keys_dropped;   /* backtrack points enqueued / dropped as explored when dequeued */
+  uint64_t explored_pairs;
+  uint64_t pool_left;
+  uint64_t records_sent, records_received, bytes_sent;
+  uint32_t rounds, exchanges;
+  uint32_t exhausted;             /* every rank's queue ran empty ("Tutto finito!", :1148)               */
+  uint32_t budget_exhausted;
+  uint32_t status;                /* 0 ok, DEMI_DS_*                                                     */
+  uint32_t trace_slots;
+  double   exec_ms, scan_ms, select_ms, exchange_ms;
+} demi_frontier_result;
+/* One self-contained backtrack record as it travels between ranks: 16-byte header + (later_i + 1) trace entries. */
+typedef struct demi_frontier_entry {    /* one delivered event of a trace, 16 bytes */
+  uint64_t id;                    /* content-addressed node id                                           */
+  uint8_t  src, dst, type, pad;
+  uint16_t parent_pos;            /* trace position of the delivery that created the message (0 = root)  */
+  uint16_t pad2;
+} demi_frontier_entry;
+/* Runs on this handle's device; with a communicator (demi_comm_init) every rank calls it collectively.
+ * hashes (cap_hashes, may be NULL): schedule hash of every interleaving executed on this rank, in slot order;
+ * viol (cap_viol): this rank's violating interleavings in slot order. */
+int32_t demi_dpor_frontier(demi_handle* h, const demi_ext_event* ext, uint32_t n_ext,
+                           const demi_frontier_params* params, demi_frontier_result* result,
+                           demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint64_t cap_hashes);
+
+/* ------------------------------------------------------------ communicator */
+/* NCCL inside the library ("NCCL is internal").  Multi-process: rank 0 calls demi_comm_unique_id and
+ * the host ships the 128 bytes to the other ranks by any means; every rank then calls demi_comm_init.
+ * Single-process hosts (a JVM) use demi_create_multi, which creates one handle per device and wires them up. */
+#define DEMI_COMM_ID_BYTES 128
+int32_t demi_comm_unique_id(uint8_t id[DEMI_COMM_ID_BYTES]);
+int32_t demi_comm_init(demi_handle* h, const uint8_t id[DEMI_COMM_ID_BYTES], int32_t rank, int32_t world);
+int32_t demi_comm_rank(const demi_handle* h, int32_t* rank, int32_t* world);
+/* n handles on `devices[0..n)` in one process, already connected; cfg->device is ignored. */
+int32_t demi_create_multi(const demi_config* cfg, const int32_t* devices, int32_t n, demi_handle** out);
+/* demi_dpor_frontier on n connected handles of one process (one host thread per device inside the call);
+ * results / viol / hashes are per rank (rank r at index r, r*cap_viol, r*cap_hashes). */
+int32_t demi_dpor_frontier_multi(demi_handle** hs, int32_t n, const demi_ext_event* ext, uint32_t n_ext,
+                                 const demi_frontier_params* params, demi_frontier_result* results,
+                                 demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint64_t cap_hashes);
+
 /* ------------------------------------------- state-hash dedup + compaction */
 /* Frontier bookkeeping the north-star adds on top of the reference (the
  * reference has no dedup; RunnerUtils.fuzz simply discards executions):

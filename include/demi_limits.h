@@ -99,4 +99,40 @@ DEMI_HD uint64_t demi_pending_term(uint32_t hdr_noflags, uint32_t p0, uint32_t p
   return demi_hash6(hdr_noflags, p0, p1, 0x50454E44u, 0, 0);
 }
 
+/* ---- frontier DPOR (demi_dpor_frontier): content-addressed dependency-graph ids, explored-pair keys and the
+ * queue order of a backtrack point are part of the observable behaviour, so engine and oracle share them. */
+#define DEMI_FR_ROOT_ID 0x9E3779B97F4A7C15ull
+/* id of the message (snd, rcv, fingerprint) created while `parent` is being delivered: the child-reuse rule of
+ * DPORwHeuristics.getMessage (:773-801) as a hash.  hdr = src | dst << 8 | type << 16. */
+DEMI_HD uint64_t demi_fr_child_id(uint64_t parent, uint32_t hdr, uint32_t p0, uint32_t p1) {
+  return demi_hash6((uint32_t)parent, (uint32_t)(parent >> 32), hdr, p0, p1, 0x46524944u);
+}
+/* ordered pair (first, second) of node ids -> explored-set key (0 is the empty slot) */
+DEMI_HD uint64_t demi_fr_pair_key(uint64_t first, uint64_t second) {
+  uint64_t k = demi_hash6((uint32_t)first, (uint32_t)(first >> 32), (uint32_t)second, (uint32_t)(second >> 32), 0x50414952u, 0);
+  return k ? k : 1ull;
+}
+/* queue order: ascending `ord` = deeper branch first, then trace slot, later position, earlier position */
+#define DEMI_FR_MAX_POS 4095u
+DEMI_HD uint64_t demi_fr_ord(uint32_t branch, uint32_t slot, uint32_t li, uint32_t ei) {
+  return ((uint64_t)(DEMI_FR_MAX_POS - branch) << 52) | ((uint64_t)slot << 24) | ((uint64_t)li << 12) | (uint64_t)ei;
+}
+DEMI_HD uint32_t demi_fr_ord_branch(uint64_t o) { return DEMI_FR_MAX_POS - (uint32_t)(o >> 52); }
+DEMI_HD uint32_t demi_fr_ord_slot(uint64_t o) { return (uint32_t)(o >> 24) & 0x0FFFFFFFu; }
+DEMI_HD uint32_t demi_fr_ord_later(uint64_t o) { return (uint32_t)(o >> 12) & 0xFFFu; }
+DEMI_HD uint32_t demi_fr_ord_earlier(uint64_t o) { return (uint32_t)o & 0xFFFu; }
+DEMI_HD uint64_t demi_fr_explored_slot(uint64_t key, uint64_t slots) {
+  return ((key * 0x9E3779B97F4A7C15ull) >> 20) & (slots - 1);
+}
+/* executor capacities per interleaving: messages created (pool entries never outlive the execution) */
+static inline uint32_t demi_fr_pool_entries(int model, int32_t max_messages, uint32_t n_ext_sends) {
+  uint32_t d = (uint32_t)max_messages + 1u;
+  switch (model) {
+    case 1: return n_ext_sends + 2u * d + 8u;
+    case 2: return n_ext_sends + 16u + 7u * d;     /* <= 6 outbox ops + one re-arm per delivery */
+    case 3: return n_ext_sends + 8u + 32u * d;
+    default: return 64u;
+  }
+}
+
 #endif /* DEMI_LIMITS_H */

@@ -36,8 +36,11 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError("oracle library missing: run `make -C oracle`")
+        # -march=native build: (re)built on the machine that runs it (demi_b200/build.py keeps a CPU stamp)
+        import sys
+        sys.path.insert(0, os.path.dirname(_HERE))
+        from demi_b200 import build
+        build.build_oracle()
         _lib = C.CDLL(LIB_PATH)
     return _lib
 
@@ -351,3 +354,45 @@ def incremental_ddmin(model, ext, max_messages, max_interleavings, seed, max_max
                                         C.c_void_p(sizes.ctypes.data), C.c_uint32(len(sizes)))
     return rc, mcs, {"total_replays": total.value, "rounds": rounds.value, "interleavings": il.value,
                      "instances": ninst.value, "mcs_sizes": sizes[:rounds.value].copy()}
+
+
+# ------------------------------------------------ frontier ("wide") DPOR
+class FrontierParams(C.Structure):
+    _fields_ = [("max_messages", C.c_int32), ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32),
+                ("width", C.c_uint32), ("max_interleavings", C.c_uint64), ("explored_slots", C.c_uint64),
+                ("pool_cap", C.c_uint64), ("trace_cap", C.c_uint32), ("rounds_per_exchange", C.c_uint32),
+                ("steal_max", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FRONTIER_RESULT_DTYPE = np.dtype([
+    ("interleavings", "<u8"), ("violations", "<u8"), ("deliveries", "<u8"), ("races", "<u8"),
+    ("keys_enqueued", "<u8"), ("keys_dropped", "<u8"), ("explored_pairs", "<u8"), ("pool_left", "<u8"),
+    ("records_sent", "<u8"), ("records_received", "<u8"), ("bytes_sent", "<u8"),
+    ("rounds", "<u4"), ("exchanges", "<u4"), ("exhausted", "<u4"), ("budget_exhausted", "<u4"),
+    ("status", "<u4"), ("trace_slots", "<u4"),
+    ("exec_ms", "<f8"), ("scan_ms", "<f8"), ("select_ms", "<f8"), ("exchange_ms", "<f8")])
+assert FRONTIER_RESULT_DTYPE.itemsize == 144 and C.sizeof(FrontierParams) == 56
+
+
+def frontier_params(max_messages, max_interleavings, width, looking_for=0, stop_if_found=0, explored_slots=1 << 22,
+                    pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096):
+    if trace_cap is None:
+        trace_cap = int(max_interleavings) + 8 * steal_max + 16
+    return FrontierParams(max_messages, looking_for, stop_if_found, width, max_interleavings, explored_slots,
+                          pool_cap, trace_cap, rounds_per_exchange, steal_max, 0)
+
+
+def dpor_frontier(model, ext, F, n_ranks=1, model_flags=0, blocked_mask=0, ignore_timers=0, cap_viol=4096):
+    """oracle_dpor_frontier: per-rank results, violations and schedule hashes (each in slot order)."""
+    ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
+    cfg = Config(0, model, model_flags, blocked_mask, ignore_timers, 0)
+    res = np.zeros(n_ranks, dtype=FRONTIER_RESULT_DTYPE)
+    viol = np.zeros((n_ranks, cap_viol), dtype=DPOR_VIOL_DTYPE)
+    cap_h = int(F.max_interleavings) + 1
+    hashes = np.zeros((n_ranks, cap_h), dtype=np.uint64)
+    rc = lib().oracle_dpor_frontier(C.byref(cfg), C.c_void_p(ext.ctypes.data), C.c_uint32(len(ext)), C.byref(F),
+                                    C.c_uint32(n_ranks), C.c_void_p(res.ctypes.data), C.c_void_p(viol.ctypes.data),
+                                    C.c_uint32(cap_viol), C.c_void_p(hashes.ctypes.data), C.c_uint64(cap_h))
+    vs = [viol[r, :min(int(res[r]["violations"]), cap_viol)].copy() for r in range(n_ranks)]
+    hs = [hashes[r, :int(res[r]["interleavings"])].copy() for r in range(n_ranks)]
+    return rc, res, vs, hs

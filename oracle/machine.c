@@ -12,6 +12,7 @@
 #include "machine.h"
 #include "sts.h"
 #include "dpor.h"
+#include "dpor_frontier.h"
 
 /* ------------------------------------------------------------------ helpers */
 static int key_eq(const om_timer_key* k, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
@@ -138,8 +139,8 @@ static int fifo_get_non_blocked(om_machine* m, om_pending* out) {
  * child of parentEvent with equal (snd, rcv, fingerprint), else allocate a new
  * Unique.  Canonical order among equal children: lowest id. */
 static uint16_t dep_report_newly_enabled(om_machine* m, const demi_msg* msg) {
-  for (uint32_t i = 1; i < m->n_nodes; i++) {
-    if (m->node_parent[i] != m->parent_event) continue;
+  /* only the parent's children are compared (`parent.inNeighbors.find`, DepTracker.scala:94-101) */
+  for (uint32_t i = m->node_first_child[m->parent_event]; i; i = m->node_next_sibling[i]) {
     const demi_msg* c = &m->node_msg[i];
     if (c->src == msg->src && c->dst == msg->dst && c->type == msg->type &&
         c->p0 == msg->p0 && c->p1 == msg->p1) return (uint16_t)i;
@@ -149,6 +150,10 @@ static uint16_t dep_report_newly_enabled(om_machine* m, const demi_msg* msg) {
   m->node_msg[id] = *msg;
   m->node_msg[id].flags = 0;
   m->node_parent[id] = (uint16_t)m->parent_event;
+  m->node_first_child[id] = m->node_last_child[id] = m->node_next_sibling[id] = 0;
+  if (m->node_last_child[m->parent_event]) m->node_next_sibling[m->node_last_child[m->parent_event]] = (uint16_t)id;
+  else m->node_first_child[m->parent_event] = (uint16_t)id;
+  m->node_last_child[m->parent_event] = (uint16_t)id;
   return (uint16_t)id;
 }
 
@@ -230,6 +235,7 @@ static void send_external_messages(om_machine* m) {
 /* `!` inside receive(): Instrumenter.tell -> aroundDispatch -> event_produced,
  * synchronously and in program order (Instrumenter.scala:1098-1108). */
 void om_send(om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_frontier_mode()) { front_om_send(m, src, dst, type, p0, p1); return; }
   if (oracle_in_dpor_mode()) { dpor_om_send(m, src, dst, type, p0, p1); return; }
   if (oracle_in_sts_mode()) { sts_om_send(m, src, dst, type, p0, p1); return; }
   demi_msg msg; msg.src = (uint8_t)src; msg.dst = (uint8_t)dst; msg.type = type; msg.flags = 0;
@@ -240,6 +246,7 @@ void om_send(om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_
  * (ongoing=false) -> handleTick -> enqueue_timer -> removeCancellable
  * (Instrumenter.scala:1145-1200). */
 void om_schedule_once(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_frontier_mode()) { front_om_schedule(m, self, type, p0, p1, 0); return; }
   if (oracle_in_dpor_mode()) { dpor_om_schedule(m, self, type, p0, p1, 0); return; }
   if (oracle_in_sts_mode()) { sts_om_schedule(m, self, type, p0, p1, 0); return; }
   if (m->status) return;
@@ -248,6 +255,7 @@ void om_schedule_once(om_machine* m, int self, uint8_t type, uint32_t p0, uint32
 }
 /* scheduler.schedule (repeating): WeaveActor.aj:264-279, ongoing=true. */
 void om_schedule_repeating(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_frontier_mode()) { front_om_schedule(m, self, type, p0, p1, 1); return; }
   if (oracle_in_dpor_mode()) { dpor_om_schedule(m, self, type, p0, p1, 1); return; }
   if (oracle_in_sts_mode()) { sts_om_schedule(m, self, type, p0, p1, 1); return; }
   if (m->status) return;
@@ -261,6 +269,7 @@ void om_schedule_repeating(om_machine* m, int self, uint8_t type, uint32_t p0, u
  * matching ("deadLetters", rcv, msg) in pendingEvents.arr order
  * (FullyRandom.remove, RandomScheduler.scala:653-664). */
 void om_cancel_timer(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1) {
+  if (oracle_in_frontier_mode()) { front_om_cancel(m, self, type, p0, p1); return; }
   if (oracle_in_dpor_mode()) { dpor_om_cancel(m, self, type, p0, p1); return; }
   if (oracle_in_sts_mode()) { sts_om_cancel(m, self, type, p0, p1); return; }
   if (m->status) return;
@@ -435,6 +444,7 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
   m->n_nodes = 1;                       /* DepTracker.root, id 0 (DepTracker.scala:15-17) */
   memset(&m->node_msg[0], 0, sizeof(demi_msg));
   m->node_parent[0] = 0;
+  m->node_first_child[0] = m->node_last_child[0] = m->node_next_sibling[0] = 0;
   m->parent_event = 0;
   m->events = events; m->n_events = 0; m->trace_hash = 0;
   m->n_uniq = 0; m->nsched = 0; m->ext_idx = 0; m->ext = ext; m->n_ext = n_ext;

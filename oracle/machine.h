@@ -89,6 +89,8 @@ struct om_machine {
   /* DepTracker (DepTracker.scala:27-135): parent-pointer tree */
   demi_msg node_msg[OM_MAX_NODES];
   uint16_t node_parent[OM_MAX_NODES];
+  /* children of each node in creation (= id) order: what `inNeighbors` of the parent holds (DepTracker.scala:94-101) */
+  uint16_t node_first_child[OM_MAX_NODES], node_last_child[OM_MAX_NODES], node_next_sibling[OM_MAX_NODES];
   uint32_t n_nodes;
   uint32_t parent_event;       /* DepTracker.parentEvent */
   /* EventTrace.events (EventTrace.scala:20) */

@@ -44,6 +44,8 @@ def test_binding_layouts_match_the_header(native, tmp_path):
         "demi_dpor_result": native.DPOR_RESULT_DTYPE.itemsize, "demi_dpor_violation": native.DPOR_VIOL_DTYPE.itemsize,
         "demi_dpor_seed": C.sizeof(native.DporSeed), "demi_dpor_ex": C.sizeof(native.DporEx),
         "demi_incddmin_out": C.sizeof(native.IncDDMinOut), "demi_provenance_out": native.PROVENANCE_DTYPE.itemsize,
+        "demi_frontier_params": C.sizeof(native.FrontierParams), "demi_frontier_result": native.FRONTIER_RESULT_DTYPE.itemsize,
+        "demi_frontier_entry": native.FRONTIER_ENTRY_DTYPE.itemsize,
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "demi_b200.h"\nint main(void) {\n' +
