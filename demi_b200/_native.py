@@ -112,7 +112,7 @@ class FrontierParams(C.Structure):
     _fields_ = [("max_messages", C.c_int32), ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32),
                 ("width", C.c_uint32), ("max_interleavings", C.c_uint64), ("explored_slots", C.c_uint64),
                 ("pool_cap", C.c_uint64), ("trace_cap", C.c_uint32), ("rounds_per_exchange", C.c_uint32),
-                ("steal_max", C.c_uint32), ("reserved", C.c_uint32)]
+                ("steal_max", C.c_uint32), ("flags", C.c_uint32)]
 
 
 FRONTIER_RESULT_DTYPE = np.dtype([
@@ -126,6 +126,7 @@ FRONTIER_ENTRY_DTYPE = np.dtype([("id", "<u8"), ("src", "u1"), ("dst", "u1"), ("
                                  ("parent_pos", "<u2"), ("pad2", "<u2")])
 assert FRONTIER_RESULT_DTYPE.itemsize == 144 and C.sizeof(FrontierParams) == 56 and FRONTIER_ENTRY_DTYPE.itemsize == 16
 COMM_ID_BYTES = 128
+FR_NO_HISTORY = 1
 
 _lib = None
 

@@ -117,6 +117,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   for (void* b : h->dpor_buf) cudaFree(b);
   cudaFree(h->ext_sends_dev); cudaFree(h->lane_pend); cudaFree(h->ovf_list); cudaFree(h->ovf_count); cudaFree(h->fifo_scratch);
   demi_replay_free(h);
+  demi_frontier_free(h);
   demi_comm_free(h);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
   if (h->pinned) cudaFreeHost(h->pinned);

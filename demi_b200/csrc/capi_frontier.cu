@@ -121,6 +121,7 @@ constexpr int SCAN_WPB = 4;
 
 struct FrRun { std::vector<unsigned long long> lo, hi; };      // per branch: the not yet dequeued part of the run, [lo, hi) in the queue array
 
+struct FrGeom;
 struct FrState {
   demi_handle* h = nullptr; FrComm* comm = nullptr; const FrVariant* v = nullptr;
   demi_frontier_params F{}; uint32_t T1 = 0, W = 0, cap_pend = 0, rcap = 0, win_cap = 0, s_slots = 0, rec_u4 = 0;
@@ -157,7 +158,16 @@ struct FrState {
   ~FrState() { for (void* q : allocs) cudaFree(q); for (auto& e : ev) if (e) cudaEventDestroy(e); }
 };
 
-int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext) {
+// device buffers are kept in the handle between calls with the same geometry (a search of a few hundred
+// interleavings takes a millisecond; allocating its tables takes longer)
+struct FrGeom { int model, world; demi_frontier_params F; uint32_t n_sends, ext_cap; };
+bool fr_same_geom(const FrGeom& a, const FrGeom& b, uint32_t n_ext) {
+  return a.model == b.model && a.world == b.world && a.F.max_messages == b.F.max_messages && a.F.width == b.F.width &&
+         a.F.max_interleavings == b.F.max_interleavings && a.F.explored_slots == b.F.explored_slots && a.F.pool_cap == b.F.pool_cap &&
+         a.F.trace_cap == b.F.trace_cap && a.F.steal_max == b.F.steal_max && a.n_sends == b.n_sends && n_ext <= a.ext_cap;
+}
+
+int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool reuse) {
   demi_handle* h = st.h;
   const demi_frontier_params& F = st.F;
   st.T1 = (uint32_t)F.max_messages + 2;
@@ -174,6 +184,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext) {
   const int world = st.comm ? st.comm->world : 1;
   st.cap_exec = F.max_interleavings + st.W + 1;
   int32_t rc;
+  if (!reuse) {
 #define DA(p, n) if ((rc = st.dalloc(&st.p, (size_t)(n))) != DEMI_OK) return rc;
   DA(tr, (size_t)F.trace_cap * st.T1) DA(tr_meta, F.trace_cap) DA(E, F.explored_slots) DA(pool, F.pool_cap)
   DA(sel, std::max<uint32_t>(st.W, F.steal_max)) DA(out_hash, st.cap_exec) DA(out_viol, st.cap_exec)
@@ -188,13 +199,16 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext) {
     DA(gather_dev, (size_t)world * std::max(world, 4))
   }
   DA(hist, st.T1)
-  DA(ext_dev, std::max<uint32_t>(n_ext, 1))
+  DA(ext_dev, std::max<uint32_t>(n_ext, 64))
 #undef DA
-  CUDA_TRY(h, cudaMemsetAsync(st.E, 0, F.explored_slots * 8, st.s));
+  for (auto& e : st.ev) CUDA_TRY(h, cudaEventCreate(&e));
+  }
+  st.runs.clear(); st.pool_top = st.pool_live = st.n_exec = 0; st.n_slots = 0;
+  memset(&st.R, 0, sizeof(st.R));
+  if (!(F.flags & DEMI_FR_NO_HISTORY)) CUDA_TRY(h, cudaMemsetAsync(st.E, 0, F.explored_slots * 8, st.s));
   CUDA_TRY(h, cudaMemsetAsync(st.ctr, 0, FRC_N * 8, st.s));
   CUDA_TRY(h, cudaMemsetAsync(st.info, 0, sizeof(FrInfo), st.s));
   if (n_ext) CUDA_TRY(h, cudaMemcpyAsync(st.ext_dev, ext, n_ext * sizeof(demi_ext_event), cudaMemcpyHostToDevice, st.s));
-  for (auto& e : st.ev) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaFuncSetAttribute(st.v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.v->smem));
   const size_t scan_smem = (size_t)SCAN_WPB * fr_scan_words(st.T1) * 4, cnt_smem = (size_t)SCAN_WPB * fr_cnt_words(st.T1) * 4;
   CUDA_TRY(h, cudaFuncSetAttribute(fr_scan_kernel<SCAN_WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
@@ -203,7 +217,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext) {
   st.brq.assign(st.T1, {}); st.branch_live.assign(st.T1, 0);
   FrArgs& A = st.A;
   A.model_flags = h->cfg.model_flags; A.blocked_mask = h->cfg.blocked_mask; A.ignore_timers = h->cfg.ignore_timers;
-  A.max_messages = F.max_messages; A.looking_for = F.looking_for;
+  A.max_messages = F.max_messages; A.looking_for = F.looking_for; A.no_history = (F.flags & DEMI_FR_NO_HISTORY) ? 1u : 0u;
   A.ext = st.ext_dev; A.n_ext = n_ext; A.T1 = st.T1;
   A.tr = st.tr; A.tr_meta = st.tr_meta; A.E = st.E; A.e_slots = F.explored_slots;
   A.sel = st.sel; A.out_hash = st.out_hash; A.out_viol = st.out_viol;
@@ -240,6 +254,7 @@ int32_t fr_select_window(FrState& st, const std::vector<FrSeg>& segs, uint32_t w
   S.skey = st.skey; S.sidx = st.sidx; S.s_slots = st.s_slots;
   S.blockcnt = st.blockcnt; S.n_blocks = (win_n + 255) / 256;
   S.sel = dst; S.sel_base = dst_base; S.quota = quota; S.info = st.info; S.ctr = st.ctr;
+  S.no_history = (st.F.flags & DEMI_FR_NO_HISTORY) ? 1u : 0u;
   fr_sel_probe_kernel<<<S.n_blocks, 256, 0, st.s>>>(S);
   fr_sel_winner_kernel<<<S.n_blocks, 256, 0, st.s>>>(S);
   fr_sel_blockscan_kernel<<<1, 1024, 0, st.s>>>(S);
@@ -456,6 +471,8 @@ int32_t fr_exchange(FrState& st, const std::vector<unsigned long long>& have_in,
   return DEMI_OK;
 }
 
+struct FrCache { FrGeom geom; FrState st; };
+
 int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint64_t cap_hashes) {
   demi_handle* h = st.h;
   const demi_frontier_params& F = st.F;
@@ -529,6 +546,13 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
 }
 }  // namespace
 
+void demi_frontier_free(demi_handle* h) {
+  if (!h->frontier) return;
+  cudaSetDevice(h->cfg.device);
+  delete (FrCache*)h->frontier;
+  h->frontier = nullptr;
+}
+
 extern "C" int32_t demi_dpor_frontier(demi_handle* h, const demi_ext_event* ext, uint32_t n_ext,
                                       const demi_frontier_params* params, demi_frontier_result* result,
                                       demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint64_t cap_hashes) {
@@ -548,13 +572,20 @@ extern "C" int32_t demi_dpor_frontier(demi_handle* h, const demi_ext_event* ext,
   FrComm* cm = (FrComm*)h->comm;
   if (cm && cm->world > 1 && !F.steal_max) return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: steal_max must be positive on %d ranks", cm->world);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  FrState st;
+  uint32_t n_sends = 0;
+  for (uint32_t i = 0; i < n_ext; i++) if (ext[i].kind == DEMI_EXT_SEND) n_sends++;
+  FrGeom g{h->cfg.model, (cm && cm->world > 1) ? cm->world : 1, F, n_sends, std::max<uint32_t>(n_ext, 64)};
+  FrCache* cache = (FrCache*)h->frontier;
+  bool reuse = cache && fr_same_geom(cache->geom, g, n_ext);
+  if (!reuse) { delete cache; cache = new FrCache(); cache->geom = g; h->frontier = cache; }
+  FrState& st = cache->st;
   st.h = h; st.comm = (cm && cm->world > 1) ? cm : nullptr; st.F = F;
   st.v = pick_frv(h->cfg.model);
   if (!st.v) return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: no kernel for model %d", h->cfg.model);
   memset(result, 0, sizeof(*result));
   h->perf.kernel_launches = 0;
-  int32_t rc = fr_setup(st, ext, n_ext);
+  int32_t rc = fr_setup(st, ext, n_ext, reuse);
+  if (rc != DEMI_OK) { delete cache; h->frontier = nullptr; return rc; }
   if (rc == DEMI_OK) rc = fr_run(st, viol, cap_viol, hashes, cap_hashes);
   *result = st.R;
   if (rc != DEMI_OK) return rc;

@@ -62,9 +62,11 @@ struct demi_handle {
   unsigned long long* rp_counters = nullptr;
   // ---- communicator (capi_frontier.cu): NCCL inside the library
   void* comm = nullptr;
+  void* frontier = nullptr;      // cached K3F buffers
 };
 void demi_replay_free(demi_handle* h);
 void demi_comm_free(demi_handle* h);
+void demi_frontier_free(demi_handle* h);
 
 inline int32_t ensure_bytes(demi_handle* h, void** p, size_t* cap, size_t need);
 

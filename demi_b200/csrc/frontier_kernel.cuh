@@ -46,6 +46,7 @@ struct FrArgs {
   unsigned long long* E; unsigned long long e_slots;   // explored ordered pairs (open addressing, 0 = empty)
   const ulonglong2* sel; uint32_t n_sel;         // this round's backtrack points (ord, pair key); n_sel == 0 && root: first run
   uint32_t first_slot; uint32_t root;
+  uint32_t no_history;                           // trackHistory = false: the explored set is neither written nor read
   unsigned long long* out_hash; uint32_t* out_viol;    // per executed interleaving, index exec_base + j
   unsigned long long exec_base;
   uint4* pendA; uint32_t* pendP1; uint32_t* pendNX; uint32_t cap_pend;
@@ -398,7 +399,7 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
       const unsigned m = __ballot_sync(FULL_MASK, race);
       if (race) {
         rec[nr + __popc(m & ((1u << lane) - 1u))] = fr_rec(li, ei, br);
-        if (fr_e_insert(A.E, A.e_slots, demi_fr_pair_key(ids[ei], ids[li]), A.ctr)) new_pairs++;   // :1071-1073
+        if (!A.no_history && fr_e_insert(A.E, A.e_slots, demi_fr_pair_key(ids[ei], ids[li]), A.ctr)) new_pairs++;   // :1071-1073
       }
       nr += __popc(m);
     }
@@ -437,7 +438,7 @@ fr_count_kernel(const __grid_constant__ FrArgs A) {
     uint32_t r = rec[k];
     const uint32_t li = r & 0x3FFu, ei = (r >> 10) & 0x3FFu, br = (r >> 20) & 0x3FFu;
     // a point whose pair is explored would be dropped when dequeued (:1156-1160): not enqueued
-    if (!fr_e_has(A.E, A.e_slots, demi_fr_pair_key(ids[li], ids[ei]))) { rec[k] = r | (1u << 30); atomicAdd(&cnt[br], 1u); }
+    if (A.no_history || !fr_e_has(A.E, A.e_slots, demi_fr_pair_key(ids[li], ids[ei]))) { rec[k] = r | (1u << 30); atomicAdd(&cnt[br], 1u); }
   }
   __syncwarp();
   for (uint32_t i = lane; i < T1; i += 32) A.counts[(size_t)i * A.n_sel + j] = cnt[i];
@@ -527,6 +528,7 @@ struct FrSelArgs {
   uint32_t* blockcnt; uint32_t n_blocks;
   ulonglong2* sel; uint32_t sel_base; uint32_t quota;
   FrInfo* info; unsigned long long* ctr;
+  uint32_t no_history;
 };
 __device__ __forceinline__ uint32_t fr_s_slot(unsigned long long key, uint32_t slots) {
   return (uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 33) & (slots - 1);
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(256) fr_sel_probe_kernel(const __grid_constant
   const FrSeg sg = S.segs[lo];
   const ulonglong2 k = S.pool[sg.src + (i - sg.dst)];
   S.win[i] = k;
+  if (S.no_history) { S.flag[i] = 2; return; }                                // every point runs
   const bool alive = !fr_e_has(S.E, S.e_slots, k.y);
   S.flag[i] = alive ? 1 : 0;
   if (alive) {
@@ -557,7 +560,8 @@ __global__ void __launch_bounds__(256) fr_sel_winner_kernel(const __grid_constan
   __syncthreads();
   const uint32_t i = blockIdx.x * 256 + threadIdx.x;
   bool win = false;
-  if (i < S.win_n && S.flag[i]) {
+  if (i < S.win_n && S.flag[i] == 2) win = true;
+  else if (i < S.win_n && S.flag[i]) {
     const unsigned long long pk = S.win[i].y;
     uint32_t s = fr_s_slot(pk, S.s_slots);
     while (S.skey[s] != pk) s = (s + 1) & (S.s_slots - 1);
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(256) fr_sel_assign_kernel(const __grid_constan
   const uint32_t q = total < S.quota ? total : S.quota;
   if (rank >= q) return;
   const ulonglong2 k = S.win[i];
-  if (fr_e_insert(S.E, S.e_slots, k.y, S.ctr)) atomicAdd(&S.ctr[FRC_EXPLORED], 1ull);
+  if (!S.no_history && fr_e_insert(S.E, S.e_slots, k.y, S.ctr)) atomicAdd(&S.ctr[FRC_EXPLORED], 1ull);
   S.sel[S.sel_base + rank] = k;
   if (rank == q - 1 && total > S.quota) S.info->cut = i + 1;
 }

@@ -273,11 +273,12 @@ class Engine(object):
     # ---- frontier ("wide") DPOR: one DPORwHeuristics.test explored as a frontier of backtrack points
     @staticmethod
     def frontier_params(max_messages, max_interleavings, width, looking_for=0, stop_if_found=False,
-                        explored_slots=1 << 22, pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096):
+                        explored_slots=1 << 22, pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096,
+                        flags=0):
         if trace_cap is None:
             trace_cap = int(max_interleavings) + 8 * steal_max + 16
         return N.FrontierParams(max_messages, looking_for or 0, 1 if stop_if_found else 0, width, max_interleavings,
-                                explored_slots, pool_cap, trace_cap, rounds_per_exchange, steal_max, 0)
+                                explored_slots, pool_cap, trace_cap, rounds_per_exchange, steal_max, flags)
 
     def comm_init(self, unique_id, rank, world):
         """Join the library's NCCL communicator (demi_comm_init); unique_id = the 128 bytes rank 0 made."""

@@ -406,8 +406,10 @@ typedef struct demi_frontier_params {
   uint32_t trace_cap;             /* per rank: trace slots (executed + imported)                         */
   uint32_t rounds_per_exchange;   /* steal period in rounds (ignored on one rank)                        */
   uint32_t steal_max;             /* most records one rank sends to one other rank per exchange          */
-  uint32_t reserved;
+  uint32_t flags;                 /* DEMI_FR_*                                                            */
 } demi_frontier_params;
+#define DEMI_FR_NO_HISTORY 0x1u   /* trackHistory = false (DPORwHeuristics.scala:86): no ExploredTacker, every backtrack
+                                     point is replayed; only a budget ends the search                                 */
 typedef struct demi_frontier_result {   /* per rank */
   uint64_t interleavings;         /* executions performed on this rank                                   */
   uint64_t violations;

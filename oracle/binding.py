@@ -361,7 +361,7 @@ class FrontierParams(C.Structure):
     _fields_ = [("max_messages", C.c_int32), ("looking_for", C.c_uint32), ("stop_if_found", C.c_uint32),
                 ("width", C.c_uint32), ("max_interleavings", C.c_uint64), ("explored_slots", C.c_uint64),
                 ("pool_cap", C.c_uint64), ("trace_cap", C.c_uint32), ("rounds_per_exchange", C.c_uint32),
-                ("steal_max", C.c_uint32), ("reserved", C.c_uint32)]
+                ("steal_max", C.c_uint32), ("flags", C.c_uint32)]
 
 
 FRONTIER_RESULT_DTYPE = np.dtype([
@@ -375,11 +375,11 @@ assert FRONTIER_RESULT_DTYPE.itemsize == 144 and C.sizeof(FrontierParams) == 56
 
 
 def frontier_params(max_messages, max_interleavings, width, looking_for=0, stop_if_found=0, explored_slots=1 << 22,
-                    pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096):
+                    pool_cap=1 << 22, trace_cap=None, rounds_per_exchange=1, steal_max=4096, flags=0):
     if trace_cap is None:
         trace_cap = int(max_interleavings) + 8 * steal_max + 16
     return FrontierParams(max_messages, looking_for, stop_if_found, width, max_interleavings, explored_slots,
-                          pool_cap, trace_cap, rounds_per_exchange, steal_max, 0)
+                          pool_cap, trace_cap, rounds_per_exchange, steal_max, flags)
 
 
 def dpor_frontier(model, ext, F, n_ranks=1, model_flags=0, blocked_mask=0, ignore_timers=0, cap_viol=4096):

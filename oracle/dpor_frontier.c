@@ -28,7 +28,7 @@ typedef struct { uint64_t id; demi_msg msg; uint16_t ppos; } fpend;  /* a pendin
 
 typedef struct {
   /* explored ordered pairs */
-  uint64_t* E; uint64_t e_slots, n_E;
+  uint64_t* E; uint64_t e_slots, n_E; int no_history;     /* trackHistory = false (:86): the set stays empty */
   /* trace store */
   demi_frontier_entry* tr; uint32_t* tr_len; uint32_t* tr_branch; uint32_t n_slots, cap_slots, T1;
   /* backtrack queue, ascending ord */
@@ -56,11 +56,13 @@ int oracle_in_frontier_mode(void) { return g_fx != 0; }
 
 /* --------------------------------------------------------- explored set */
 static int e_has(const frank* r, uint64_t key) {
+  if (r->no_history) return 0;
   uint64_t s = demi_fr_explored_slot(key, r->e_slots);
   while (r->E[s]) { if (r->E[s] == key) return 1; s = (s + 1) & (r->e_slots - 1); }
   return 0;
 }
 static void e_add(frank* r, uint64_t key) {
+  if (r->no_history) return;
   uint64_t s = demi_fr_explored_slot(key, r->e_slots);
   while (r->E[s]) { if (r->E[s] == key) return; s = (s + 1) & (r->e_slots - 1); }
   if (r->n_E * 2 >= r->e_slots) { r->R.status = DEMI_DS_EXPLORED_OVF; return; }
@@ -329,7 +331,7 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
   fkey* sbuf = (fkey*)malloc(sizeof(fkey) * (2 * (size_t)F->steal_max + 2));
   for (uint32_t q = 0; q < n_ranks; q++) {
     frank* r = &R[q];
-    r->e_slots = F->explored_slots; r->E = (uint64_t*)calloc(r->e_slots, 8);
+    r->e_slots = F->explored_slots; r->E = (uint64_t*)calloc(r->e_slots, 8); r->no_history = (F->flags & DEMI_FR_NO_HISTORY) != 0;
     r->T1 = T1; r->cap_slots = F->trace_cap;
     r->tr = (demi_frontier_entry*)malloc(sizeof(demi_frontier_entry) * (size_t)r->cap_slots * T1);
     r->tr_len = (uint32_t*)calloc(r->cap_slots, 4); r->tr_branch = (uint32_t*)calloc(r->cap_slots, 4);

@@ -28,7 +28,7 @@ def check(model, prog, flags, maxm, maxi, width, oracle, **kw):
     eng = D.Engine(D.SchedulerConfig(model, model_flags=flags))
     F = eng.frontier_params(maxm, maxi, width, **kw)
     r, viol, hashes = eng.dpor_frontier(prog, F)
-    OF = oracle.frontier_params(maxm, maxi, width, **{k: v for k, v in kw.items() if k in ("explored_slots", "pool_cap", "stop_if_found", "looking_for")})
+    OF = oracle.frontier_params(maxm, maxi, width, **{k: v for k, v in kw.items() if k in ("explored_slots", "pool_cap", "stop_if_found", "looking_for", "flags")})
     rc, ores, oviol, ohashes = oracle.dpor_frontier(model, D.pack_externals(prog), OF, 1, model_flags=flags)
     assert rc == 0
     for f in FIELDS:
@@ -42,8 +42,18 @@ def check(model, prog, flags, maxm, maxi, width, oracle, **kw):
 def test_frontier_matches_oracle_raft_budgeted(oracle, width):
     rng = np.random.default_rng(3)
     for prog in raft_programs(3, rng):
-        r, _, _ = check(N.MODEL_RAFT5, prog, 3, 60, 700, width, oracle, explored_slots=1 << 20, pool_cap=1 << 21)
+        r, _, _ = check(N.MODEL_RAFT5, prog, 3, 60, 150, width, oracle, explored_slots=1 << 20, pool_cap=1 << 21)
         assert r["status"] == 0 and r["budget_exhausted"] == 1
+        r, _, _ = check(N.MODEL_RAFT5, prog, 3, 100, 5000, width, oracle, explored_slots=1 << 20, pool_cap=1 << 22)
+        assert r["status"] == 0 and r["exhausted"] == 1 and r["interleavings"] > 300
+
+
+@pytest.mark.parametrize("width", [1, 16, 512])
+def test_frontier_without_history_matches_oracle(oracle, width):
+    """trackHistory = false (DPORwHeuristics.scala:86): every backtrack point is replayed; only the budget ends it."""
+    prog = D.raft5_program(client_cmds=2)[:-1]
+    r, _, hashes = check(N.MODEL_RAFT5, prog, 3, 50, 1200, width, oracle, pool_cap=1 << 22, flags=N.FR_NO_HISTORY)
+    assert r["budget_exhausted"] == 1 and r["explored_pairs"] == 0 and r["keys_dropped"] == 0
 
 
 def test_frontier_width1_is_the_reference_order(oracle):

@@ -10,7 +10,9 @@ def main():
     budget = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
     eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=3))
     prog = D.raft5_program(client_cmds=2)[:-1]
-    F = eng.frontier_params(100, budget, width, explored_slots=1 << 29, pool_cap=1 << 29, trace_cap=budget + width + 16)
+    flags = N.FR_NO_HISTORY if (len(sys.argv) > 3 and sys.argv[3] == "nohist") else 0
+    F = eng.frontier_params(100, budget, width, explored_slots=1 << 24, pool_cap=(1 << 30) if flags else (1 << 24),
+                            trace_cap=budget + width + 16, flags=flags)
     for rep in range(2):
         t = time.perf_counter()
         r, viol, hashes = eng.dpor_frontier(prog, F, cap_viol=1 << 20, want_hashes=False)
