@@ -30,6 +30,8 @@ struct SeedHost {
 int32_t build_seed(demi_handle* h, const demi_dpor_seed* seed, SeedHost& out) {
   if (!seed->events || !seed->dep_parent || !seed->n_nodes) return fail(h, DEMI_ERR_INVALID, "demi_dpor_seed: events and dep_parent are required");
   if (seed->n_nodes > (1u << 16)) return fail(h, DEMI_ERR_INVALID, "demi_dpor_seed: node ids are 16-bit");
+  { int32_t vrc = demi_check_events(h, "demi_dpor_seed", seed->events, seed->n_events, seed->n_nodes); if (vrc != DEMI_OK) return vrc;
+    vrc = demi_check_parents(h, "demi_dpor_seed", seed->dep_parent, seed->n_nodes); if (vrc != DEMI_OK) return vrc; }
   out.nodes.assign(seed->n_nodes, make_uint4(0, 0, 0, 0));
   out.orig_index.assign(seed->n_nodes, -1);
   out.trace.assign(1, 0u);
@@ -257,6 +259,7 @@ extern "C" int32_t demi_incremental_ddmin(demi_handle* h, const demi_ext_event* 
   for (uint32_t i = 0; i < n_externals; i++)
     if (externals[i].kind != DEMI_EXT_START && externals[i].kind != DEMI_EXT_SEND)
       return fail(h, DEMI_ERR_INVALID, "demi_incremental_ddmin: external %u: DPOR accepts Start and Send only", i);
+  { int32_t vrc = demi_check_externals(h, "demi_incremental_ddmin", externals, n_externals); if (vrc != DEMI_OK) return vrc; }
   SeedHost sh;
   if (seed) { int32_t rc = build_seed(h, seed, sh); if (rc != DEMI_OK) return rc; }
   memset(out, 0, sizeof(*out));

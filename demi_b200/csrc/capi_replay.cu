@@ -44,6 +44,8 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
     return fail(h, DEMI_ERR_INVALID, "demi_set_trace: empty trace or externals");   // assume(!original_trace.isEmpty)
   if (n_externals > 4096) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: more than 4096 external events");
   if (n_events >= (1u << 31)) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: trace too long");
+  { int32_t vrc = demi_check_events(h, "demi_set_trace", events, n_events, 0); if (vrc != DEMI_OK) return vrc;
+    vrc = demi_check_externals(h, "demi_set_trace", externals, n_externals); if (vrc != DEMI_OK) return vrc; }
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const uint32_t ext_mask = demi_external_type_mask(h->cfg.model);
   // FIFO correspondence of external MsgSends and original Sends (EventTrace.scala:385-386, :419-436)

@@ -80,6 +80,46 @@ inline int32_t fail(demi_handle* h, int32_t code, const char* fmt, ...) {
   return fail((h), DEMI_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 
+// ---- validation of caller-supplied records (JNI hands over JVM buffers): every actor index, node id and parent
+// pointer is range-checked before any host table or kernel indexes with it.
+inline int demi_model_actors(int model) { return model == DEMI_MODEL_PINGPONG3 ? 3 : model == DEMI_MODEL_RAFT5 ? 5 : 32; }
+inline int32_t demi_check_externals(demi_handle* h, const char* who, const demi_ext_event* ev, uint32_t n) {
+  const uint32_t na = (uint32_t)demi_model_actors(h->cfg.model);
+  for (uint32_t i = 0; i < n; i++) {
+    const demi_ext_event& e = ev[i];
+    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION) return fail(h, DEMI_ERR_INVALID, "%s: external %u has unknown kind %u", who, i, (unsigned)e.kind);
+    const bool needs_a = e.kind != DEMI_EXT_WAIT_QUIESCENCE;
+    const bool needs_b = e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION;
+    if ((needs_a && e.a >= na) || (needs_b && e.b >= na)) return fail(h, DEMI_ERR_INVALID, "%s: external %u names an unknown actor", who, i);
+  }
+  return DEMI_OK;
+}
+// n_nodes == 0: node ids are not checked (traces recorded by STSScheduler carry node = 0)
+inline int32_t demi_check_events(demi_handle* h, const char* who, const demi_event* ev, uint32_t n, uint32_t n_nodes) {
+  const uint32_t na = (uint32_t)demi_model_actors(h->cfg.model);
+  for (uint32_t i = 0; i < n; i++) {
+    const demi_event& e = ev[i];
+    bool ok = true;
+    switch (e.kind) {
+      case DEMI_EV_MSG_SEND:  ok = (e.src < na || e.src == DEMI_DEADLETTERS || e.src == DEMI_TIMER_SND) && e.dst < na; break;
+      case DEMI_EV_MSG_EVENT: ok = (e.src < na || e.src == DEMI_DEADLETTERS || e.src == DEMI_TIMER_SND) && e.dst < na; break;
+      case DEMI_EV_SPAWN: case DEMI_EV_KILL: ok = e.dst < na; break;
+      case DEMI_EV_PARTITION: case DEMI_EV_UNPARTITION: ok = e.src < na && e.dst < na; break;
+      case DEMI_EV_BEGIN_WAIT_QUIESCENCE: case DEMI_EV_QUIESCENCE: break;
+      default: return fail(h, DEMI_ERR_INVALID, "%s: event %u has unknown kind %u", who, i, (unsigned)e.kind);
+    }
+    if (!ok) return fail(h, DEMI_ERR_INVALID, "%s: event %u names an unknown actor (src %u, dst %u)", who, i, (unsigned)e.src, (unsigned)e.dst);
+    if (n_nodes && (e.kind == DEMI_EV_MSG_SEND || e.kind == DEMI_EV_MSG_EVENT) && e.node >= n_nodes)
+      return fail(h, DEMI_ERR_INVALID, "%s: event %u names node %u outside the tree of %u", who, i, (unsigned)e.node, n_nodes);
+  }
+  return DEMI_OK;
+}
+inline int32_t demi_check_parents(demi_handle* h, const char* who, const uint16_t* dep_parent, uint32_t n_nodes) {
+  for (uint32_t v = 1; v < n_nodes; v++)
+    if (dep_parent[v] >= v) return fail(h, DEMI_ERR_INVALID, "%s: node %u has parent %u (a parent is created before its children)", who, v, (unsigned)dep_parent[v]);
+  return DEMI_OK;
+}
+
 inline int32_t ensure_bytes(demi_handle* h, void** p, size_t* cap, size_t need) {
   if (*cap >= need) return DEMI_OK;
   cudaFree(*p); *p = nullptr; *cap = 0;

@@ -101,3 +101,30 @@ def test_external_event_packing_roundtrip():
     assert back == prog                                # UniqueExternalEvent equality is by id
     assert (D.pack_externals(back) == arr).all()
     assert len({e._id for e in prog}) == len(prog)
+
+
+def test_record_validation_rejects_out_of_range_indices(native):
+    """Caller-supplied trace records (JNI passes JVM buffers) are range-checked before any table is indexed:
+    actor indices, node ids and parent pointers.  The checks run before the device is touched."""
+    import numpy as np
+    L = native.lib()
+    if L.demi_device_count() <= 0:
+        pytest.skip("needs a handle (CUDA device)")
+    import demi_b200 as D
+    eng = D.Engine(D.SchedulerConfig(native.MODEL_RAFT5))
+    ev = np.zeros(2, dtype=native.EVENT_DTYPE)
+    ev[0] = (native.EV_MSG_SEND, 0, 200, 1, 0, 0, 1, 1)          # dst 200 is not an actor
+    ev[1] = (native.EV_MSG_EVENT, 0, 1, 1, 0, 0, 1, 1)
+    ext = D.pack_externals(D.raft5_program())
+    with pytest.raises(D.DemiError) as ei:
+        eng.set_trace(ev, ext)
+    assert ei.value.code == native.ERR_INVALID and "unknown actor" in str(ei.value)
+    ev[0]["dst"] = 1
+    ev[0]["node"] = 9                                             # outside a 2-node tree
+    with pytest.raises(D.DemiError) as ei:
+        eng.provenance(ev, np.array([0, 0], dtype=np.uint16), 1)
+    assert "outside the tree" in str(ei.value)
+    ev[0]["node"] = 1
+    with pytest.raises(D.DemiError) as ei:
+        eng.provenance(ev, np.array([0, 1], dtype=np.uint16), 1)  # node 1 is its own parent
+    assert "parent" in str(ei.value)

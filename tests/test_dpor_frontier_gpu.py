@@ -25,6 +25,8 @@ def raft_programs(n, rng):
 
 
 def check(model, prog, flags, maxm, maxi, width, oracle, **kw):
+    if "fr_flags" in kw:
+        kw["flags"] = kw.pop("fr_flags")
     eng = D.Engine(D.SchedulerConfig(model, model_flags=flags))
     F = eng.frontier_params(maxm, maxi, width, **kw)
     r, viol, hashes = eng.dpor_frontier(prog, F)
@@ -52,7 +54,7 @@ def test_frontier_matches_oracle_raft_budgeted(oracle, width):
 def test_frontier_without_history_matches_oracle(oracle, width):
     """trackHistory = false (DPORwHeuristics.scala:86): every backtrack point is replayed; only the budget ends it."""
     prog = D.raft5_program(client_cmds=2)[:-1]
-    r, _, hashes = check(N.MODEL_RAFT5, prog, 3, 50, 1200, width, oracle, pool_cap=1 << 22, flags=N.FR_NO_HISTORY)
+    r, _, hashes = check(N.MODEL_RAFT5, prog, 3, 50, 1200, width, oracle, pool_cap=1 << 22, fr_flags=N.FR_NO_HISTORY)
     assert r["budget_exhausted"] == 1 and r["explored_pairs"] == 0 and r["keys_dropped"] == 0
 
 
