@@ -526,6 +526,11 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
     }
   }
   // results
+  {
+    unsigned long long ctr[FRC_N];                          // a steal round marks the points it hands over
+    CUDA_TRY(h, cudaMemcpy(ctr, st.ctr, sizeof(ctr), cudaMemcpyDeviceToHost));
+    st.R.explored_pairs = ctr[FRC_EXPLORED];
+  }
   st.R.pool_left = st.pool_live; st.R.trace_slots = st.n_slots;
   st.R.exhausted = (uint32_t)exhausted; st.R.budget_exhausted = (uint32_t)budget;
   if (st.n_exec) {
