@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — schedule prefixes/sec on the BASELINE.json north-star workload.
+"""bench.py — schedule prefixes/sec on the BASELINE.json north-star workload, plus the secondary configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-secondary]
 
-Workload (BASELINE.json configs[1]): 5-actor Raft model (seeded double-vote bug),
-RandomScheduler/FullyRandom fuzz, maxMessages=50, invariant every 5 deliveries,
-10^7 prefixes per step per GPU (weak scaling: rank r, step s explores its own
-seed range).  One "step" = one pass of the hot path over one batch of prefixes.
+Headline (BASELINE.json configs[1]): 5-actor Raft model (seeded double-vote bug), RandomScheduler/FullyRandom fuzz,
+maxMessages=50, invariant every 5 deliveries, 10^7 prefixes per step per GPU (weak scaling: rank r, step s explores
+its own seed range).  One "step" = one pass of the hot path over one batch of prefixes.
 
   value : prefixes/s, results stay in HBM (demi_fuzz_batch_dev), CUDA-event timed
-  e2e   : prefixes/s through the reference-facing C-ABI call demi_fuzz_batch with
-          HOST buffers (external program H2D + all result records D2H per step)
-  roofline     : algorithmic HBM bytes of the fuzz kernel vs the measured copy peak
-  cpu_baseline : the CPU oracle (C restatement of the reference's JVM scheduler)
-                 on all host cores, bounded sample of the same workload
+  e2e   : prefixes/s through the reference-facing C-ABI call demi_fuzz_batch with HOST buffers
+          (external program H2D + all result records D2H per step)
+  roofline     : algorithmic HBM bytes of the fuzz kernel vs the measured copy peak; the profile-derived figures
+                 (DRAM traffic, issue-slot utilisation) come from profiles/k1_profile.json and are dropped when that
+                 capture was taken from another build of the kernels
+  cpu_baseline : the CPU oracle (C restatement of the reference's JVM scheduler) on all host cores, bounded sample
+  secondary    : configs[2] (one DPORwHeuristics search as a frontier, with the in-library NCCL steal round at N > 1),
+                 configs[3] (DDMin / STSSched replays over a 2000-event trace), configs[4] (bcast32 + state-hash
+                 dedup) — measured after, and outside, the headline's timed region (tools/secondary.py)
 
-`--impl reference` times the CPU oracle alone (the reference itself needs a
-JVM + sbt + Akka + the akka-raft application, none of which exist here).
+`--impl reference` times the CPU oracle alone on the SAME batch definition (the reference itself needs a JVM + sbt +
+Akka + the akka-raft application, none of which exist here).
 """
 import argparse
 import json
@@ -34,11 +37,9 @@ MAX_MESSAGES = 50
 INTERVAL = 5
 MODEL_FLAGS = 1            # Raft5 BUG_DOUBLE_VOTE: gives a non-empty, stable violating set
 RESULT_BYTES = 32          # sizeof(demi_fuzz_result): the algorithmic HBM bytes per prefix
-# dram__bytes_read.sum + dram__bytes_write.sum of fuzz_lane_kernel per prefix, from the one
-# `ncu --set full` capture in profiles/r1_ncu_summary.md (v3, 4e6 prefixes: 2.18 GB)
-NCU_DRAM_BYTES_PER_PREFIX = 502.0
 PREFIXES_PER_STEP = 10_000_000
 METRIC = "schedule prefixes/sec (5-actor Raft, depth 50)"
+K1_PROFILE = os.path.join(ROOT, "profiles", "k1_profile.json")
 
 
 def workload_config(n_per_step, n_gpus):
@@ -119,8 +120,25 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+def k1_profile(build_id):
+    """Profile-derived figures of the headline kernel (tools/profile_k1.py writes the file from one `ncu --set full`
+    capture).  They describe ONE build: if the library was built from other sources they are reported as stale and
+    not used — loudly, on stderr and in the JSON line."""
+    if not os.path.exists(K1_PROFILE):
+        return None, "no profiles/k1_profile.json"
+    try:
+        p = json.load(open(K1_PROFILE))
+    except Exception as e:
+        return None, "unreadable profile: %s" % e
+    if p.get("build_id") != build_id:
+        msg = "profiles/k1_profile.json was captured from build %s, the library is build %s" % (p.get("build_id"), build_id)
+        sys.stderr.write("bench.py: STALE PROFILE — %s; its figures are not reported (re-run tools/profile_k1.py)\n" % msg)
+        return None, msg
+    return p, None
+
+
 def run_reference(args):
-    """CPU arm: the oracle on all host cores, bounded sample per step."""
+    """CPU arm: the oracle on all host cores, the same batch definition as the GPU arm (same_config)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -129,9 +147,9 @@ def run_reference(args):
     from oracle import binding as O
     ext = events.pack_externals(events.raft5_program())
     cores = host_cores()
-    n = 125_000 * cores        # ~1 s of work per step at ~1.2e5 prefixes/s/core
-    for w in range(args.warmup):
-        O.fuzz_batch(MODEL_RAFT5, ext, 1 + w * n, n, MAX_MESSAGES, INTERVAL, model_flags=MODEL_FLAGS, threads=cores)
+    n = args.prefixes
+    for w in range(args.warmup):                 # warm-up only touches the caches: a small batch is enough
+        O.fuzz_batch(MODEL_RAFT5, ext, 1 + w * 100_000, 100_000, MAX_MESSAGES, INTERVAL, model_flags=MODEL_FLAGS, threads=cores)
     t0 = time.perf_counter()
     for s in range(args.steps):
         O.fuzz_batch(MODEL_RAFT5, ext, 1 + (args.warmup + s) * n, n, MAX_MESSAGES, INTERVAL,
@@ -143,9 +161,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": workload_config(n, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "prefixes/s", "cores": cores, "kind": "port",
-                         "sample": "%d prefixes per step x %d steps (C oracle, %d pthreads); the JVM reference "
-                                   "cannot run here (no JDK/sbt/Akka/akka-raft)" % (n, args.steps, cores)},
+        "cpu_baseline": {"value": value, "per_core": value / cores, "unit": "prefixes/s", "cores": cores, "kind": "port",
+                         "sample": "%d prefixes per step x %d steps (C oracle -O3 -march=native, %d pthreads); the JVM "
+                                   "reference cannot run here (no JDK/sbt/Akka/akka-raft)" % (n, args.steps, cores)},
         "e2e": {"value": value, "unit": "prefixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -161,6 +179,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--prefixes", type=int, default=PREFIXES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -211,11 +230,12 @@ def main():
     if rank == 0:
         sampler.start()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    total_viol = total_steps = 0
+    launches = 0
     barrier()
     evs[0].record(stream)
     for s in range(K):
         eng.fuzz_batch_dev(seed_of(W + s), n, MAX_MESSAGES, INTERVAL, results_dev.data_ptr(), stream.cuda_stream)
+        launches += int(eng.stats().kernel_launches)           # counted by the library per batch call
         evs[s + 1].record(stream)
     barrier()
     total_ms = evs[0].elapsed_time(evs[K])
@@ -252,10 +272,14 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    line = None
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
         k_ms = sum(kernel_ms) / len(kernel_ms)
         achieved = n * RESULT_BYTES / (k_ms * 1e-3) / 1e9
+        build_id = D._native.lib().demi_version().decode().split("build ")[-1]
+        prof, stale = k1_profile(build_id)
+        lane = not os.environ.get("DEMI_DISABLE_LANE_ENGINE")
         line = {
             "metric": METRIC, "value": value, "unit": "prefixes/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -265,17 +289,22 @@ def main():
             "e2e": {"value": e2e_value, "unit": "prefixes/s", "h2d_bytes_per_step": int(ext.nbytes),
                     "d2h_bytes_per_step": n * RESULT_BYTES + 16, "steps": e2e_steps,
                     "violations_last_step_rank0": last_viol},
-            "gpu_launches": 2 * K,
+            "gpu_launches": launches,
+            "build_id": build_id,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PREFIX * n, "peak_kind": peak_kind,
-                         "kernel": "fuzz_lane_kernel<Raft5,256,96> (+ fuzz_kernel<Raft5,256,32> for deferred prefixes)", "algorithmic_bytes_per_prefix": RESULT_BYTES,
-                         "kernel_ms": k_ms,
-                         "issue_slot_utilisation": 0.680, "warp_instructions_per_prefix": 3472,
-                         "note": "on-chip-state fuzz regime (SURVEY §8d R1): the only algorithmic HBM traffic is "
-                                 "the 32 B result record, so the kernel is issue-slot bound, not HBM bound "
-                                 "(smsp__issue_active 68.0 % of peak, profiles/r1_ncu_summary.md, v4 capture); `traffic` is the ncu "
-                                 "DRAM bytes per launch scaled from the 4e6-prefix capture (pending-array lines "
-                                 "evicted from L2)"},
+                         "frac": achieved / peak, "peak_kind": peak_kind,
+                         "traffic": (prof["dram_bytes_per_prefix"] * n) if prof else None,
+                         "kernel": ("fuzz_lane_kernel<Raft5,256,96> (+ fuzz_kernel<Raft5,256,32> for deferred prefixes)"
+                                    if lane else "fuzz_kernel<Raft5,256,32> (warp engine; lane engine disabled)"),
+                         "algorithmic_bytes_per_prefix": RESULT_BYTES, "kernel_ms": k_ms,
+                         "from_profile": ({k: prof[k] for k in ("capture", "build_id", "dram_bytes_per_prefix",
+                                                               "issue_slot_utilisation", "warp_instructions_per_prefix",
+                                                               "active_lanes_per_instruction", "prefixes") if k in prof}
+                                          if prof else None),
+                         "profile_stale": stale,
+                         "note": "on-chip-state fuzz regime (SURVEY §8d R1): the only algorithmic HBM traffic is the "
+                                 "32 B result record, so the kernel is issue-slot bound, not HBM bound; `traffic` and "
+                                 "`from_profile` are per-launch figures scaled from the ncu capture named there"},
             "clocks": sampler.summary(),
         }
         line["cpu_baseline"] = None                 # timed at N=1 only (rank 0)
@@ -289,12 +318,24 @@ def main():
             reps = 0
             while time.perf_counter() - t0 < 2.5 and reps < 40:
                 O.fuzz_batch(MODEL_RAFT5, ext, seed_of(W) + reps * ncpu, ncpu, MAX_MESSAGES, INTERVAL,
-                                    model_flags=MODEL_FLAGS, threads=cores)
+                             model_flags=MODEL_FLAGS, threads=cores)
                 reps += 1
             cdt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ncpu * reps / cdt, "unit": "prefixes/s", "cores": cores, "kind": "port",
-                                    "sample": "%d prefixes of the same workload (C oracle, %d pthreads, %.1f s)"
-                                              % (ncpu * reps, cores, cdt)}
+            line["cpu_baseline"] = {"value": ncpu * reps / cdt, "per_core": ncpu * reps / cdt / cores, "unit": "prefixes/s",
+                                    "cores": cores, "kind": "port",
+                                    "sample": "%d prefixes of the same workload (C oracle -O3 -march=native, %d pthreads, "
+                                              "%.1f s)" % (ncpu * reps, cores, cdt)}
+
+    # ------------------------------------------------ secondary configs (outside the headline's timed region)
+    if not args.no_secondary:
+        from tools import secondary
+        try:
+            sec = secondary.run_all(eng, rank, world, local_rank, results_dev, n, host_cores(), with_cpu=not args.no_cpu_baseline)
+        except Exception as e:                      # a failing secondary leg must not take the headline with it
+            sec = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -38,12 +38,24 @@ def _sources(root, exts):
     return out
 
 
+def source_id():
+    """Hash of every source the engine library is built from: compiled into the library (demi_version) and
+    recorded in profiles/*.json, so a profile taken from another build is recognised as stale."""
+    import hashlib
+    h = hashlib.sha1()
+    srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
+    for s in sorted(srcs):
+        h.update(os.path.relpath(s, ROOT).encode())
+        h.update(open(s, "rb").read())
+    return h.hexdigest()[:12]
+
+
 def build_engine(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
     if not force and _newer(LIB, srcs):
         return LIB
     cus = sorted(s for s in srcs if s.endswith(".cu"))
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-DDEMI_BUILD_ID=\"%s\"" % source_id()] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus
     subprocess.check_call(cmd, cwd=ROOT)
     return LIB
 

@@ -1,18 +1,76 @@
-"""Driver for the ncu capture of the K1 lane kernel: two 4e6-prefix launches of the bench workload."""
+"""Regenerate profiles/k1_profile.json: the profile-derived figures bench.py reports for the headline kernel.
+
+  (on the GPU box)  python tools/profile_k1.py            # runs ncu on tools/profile_k1.py --workload, parses the capture
+
+One `ncu --set full --clock-control none` capture of fuzz_lane_kernel over PREFIXES prefixes of the bench workload.
+The JSON records the build id of the library it profiled; bench.py refuses figures from another build."""
+import csv
+import io
+import json
 import os
+import subprocess
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PREFIXES = 4_000_000
+OUT = os.path.join(ROOT, "profiles", "k1_profile.json")
+REP = os.path.join(ROOT, "gpurun_out", "k1_profile")
 
-import demi_b200 as D
-from demi_b200 import _native as N
 
-eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
-eng.set_externals(D.raft5_program())
-n = 4_000_000
-out = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
-for rep in range(2):
-    eng.fuzz_batch_dev(1 + rep * n, n, 50, 5, out.data_ptr())
-torch.cuda.synchronize()
-print("done")
+def workload():
+    import demi_b200 as D
+    import torch
+    eng = D.Engine(D.SchedulerConfig(2, model_flags=1))
+    eng.set_externals(D.pack_externals(D.raft5_program()))
+    out = torch.empty(PREFIXES * 32, dtype=torch.uint8, device="cuda")
+    for s in range(3):
+        eng.fuzz_batch_dev(1 + s * PREFIXES, PREFIXES, 50, 5, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+
+
+def metric(rows, name):
+    for r in rows:
+        if r.get("Metric Name") == name:
+            return float(r["Metric Value"].replace(",", ""))
+    return None
+
+
+def main():
+    if "--workload" in sys.argv:
+        return workload()
+    os.makedirs(os.path.dirname(REP), exist_ok=True)
+    subprocess.check_call(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:fuzz_lane_kernel",
+                           "-s", "2", "-c", "1", "-f", "-o", REP, sys.executable, os.path.abspath(__file__), "--workload"])
+    raw = subprocess.run(["ncu", "-i", REP + ".ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rd = list(csv.reader(io.StringIO(raw)))
+    hdr, vals = rd[0], rd[-1]
+    m = dict(zip(hdr, vals))
+
+    def g(name):
+        v = m.get(name)
+        return float(v.replace(",", "")) if v not in (None, "") else None
+    from demi_b200 import _native as N
+    build_id = N.lib().demi_version().decode().split("build ")[-1]
+    inst = g("smsp__inst_executed.sum")
+    tinst = g("smsp__thread_inst_executed.sum")
+    dram = (g("dram__bytes_read.sum") or 0) + (g("dram__bytes_write.sum") or 0)
+    prof = {
+        "capture": "ncu --set full --clock-control none, fuzz_lane_kernel<Raft5,256,96>, %d prefixes (3rd launch)" % PREFIXES,
+        "build_id": build_id, "prefixes": PREFIXES,
+        "duration_ms": (g("gpu__time_duration.sum") or 0) / 1e6,
+        "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
+        "dram_bytes_per_prefix": dram / PREFIXES,
+        "warp_instructions_per_prefix": inst / PREFIXES if inst else None,
+        "active_lanes_per_instruction": (tinst / inst) if inst and tinst else None,
+        "issue_slot_utilisation": (g("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0) / 100.0,
+        "registers_per_thread": g("launch__registers_per_thread"),
+        "achieved_occupancy_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "l1_hit_rate_pct": g("l1tex__t_sector_hit_rate.pct"),
+    }
+    json.dump(prof, open(OUT, "w"), indent=1)
+    print(json.dumps(prof))
+
+
+if __name__ == "__main__":
+    main()
