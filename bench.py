@@ -120,7 +120,7 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
-def k1_profile(build_id):
+def k1_profile(k1_id):
     """Profile-derived figures of the headline kernel (tools/profile_k1.py writes the file from one `ncu --set full`
     capture).  They describe ONE build: if the library was built from other sources they are reported as stale and
     not used — loudly, on stderr and in the JSON line."""
@@ -130,8 +130,8 @@ def k1_profile(build_id):
         p = json.load(open(K1_PROFILE))
     except Exception as e:
         return None, "unreadable profile: %s" % e
-    if p.get("build_id") != build_id:
-        msg = "profiles/k1_profile.json was captured from build %s, the library is build %s" % (p.get("build_id"), build_id)
+    if p.get("k1_id") != k1_id:
+        msg = "profiles/k1_profile.json was captured from kernel sources %s, the library was built from %s" % (p.get("k1_id"), k1_id)
         sys.stderr.write("bench.py: STALE PROFILE — %s; its figures are not reported (re-run tools/profile_k1.py)\n" % msg)
         return None, msg
     return p, None
@@ -277,8 +277,9 @@ def main():
         peak, peak_kind = measured_peak_hbm()
         k_ms = sum(kernel_ms) / len(kernel_ms)
         achieved = n * RESULT_BYTES / (k_ms * 1e-3) / 1e9
-        build_id = D._native.lib().demi_version().decode().split("build ")[-1]
-        prof, stale = k1_profile(build_id)
+        ver = D._native.lib().demi_version().decode()
+        build_id, k1_id = ver.split("build ")[-1].split(" ")[0], ver.split(" k1 ")[-1]
+        prof, stale = k1_profile(k1_id)
         lane = not os.environ.get("DEMI_DISABLE_LANE_ENGINE")
         line = {
             "metric": METRIC, "value": value, "unit": "prefixes/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -290,14 +291,14 @@ def main():
                     "d2h_bytes_per_step": n * RESULT_BYTES + 16, "steps": e2e_steps,
                     "violations_last_step_rank0": last_viol},
             "gpu_launches": launches,
-            "build_id": build_id,
+            "build_id": build_id, "k1_id": k1_id,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_kind": peak_kind,
                          "traffic": (prof["dram_bytes_per_prefix"] * n) if prof else None,
                          "kernel": ("fuzz_lane_kernel<Raft5,256,96> (+ fuzz_kernel<Raft5,256,32> for deferred prefixes)"
                                     if lane else "fuzz_kernel<Raft5,256,32> (warp engine; lane engine disabled)"),
                          "algorithmic_bytes_per_prefix": RESULT_BYTES, "kernel_ms": k_ms,
-                         "from_profile": ({k: prof[k] for k in ("capture", "build_id", "dram_bytes_per_prefix",
+                         "from_profile": ({k: prof[k] for k in ("capture", "k1_id", "dram_bytes_per_prefix",
                                                                "issue_slot_utilisation", "warp_instructions_per_prefix",
                                                                "active_lanes_per_instruction", "prefixes") if k in prof}
                                           if prof else None),

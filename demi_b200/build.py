@@ -50,12 +50,27 @@ def source_id():
     return h.hexdigest()[:12]
 
 
+K1_SOURCES = ["demi_b200/csrc/lane_kernel.cuh", "demi_b200/csrc/machine.cuh", "demi_b200/csrc/fuzz_kernel.cuh",
+              "demi_b200/csrc/models/models.cuh", "include/demi_limits.h"]
+
+
+def k1_source_id():
+    """Hash of the sources of the headline kernel alone (fuzz_lane_kernel / fuzz_kernel): what profiles/k1_profile.json
+    is tied to, so work on the other kernels does not invalidate that capture."""
+    import hashlib
+    h = hashlib.sha1()
+    for s in K1_SOURCES:
+        h.update(s.encode())
+        h.update(open(os.path.join(ROOT, s), "rb").read())
+    return h.hexdigest()[:12]
+
+
 def build_engine(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
     if not force and _newer(LIB, srcs):
         return LIB
     cus = sorted(s for s in srcs if s.endswith(".cu"))
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-DDEMI_BUILD_ID=\"%s\"" % source_id()] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-DDEMI_BUILD_ID=\"%s\"" % source_id(), "-DDEMI_K1_ID=\"%s\"" % k1_source_id()] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus
     subprocess.check_call(cmd, cwd=ROOT)
     return LIB
 

@@ -24,3 +24,12 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_k1_profile_describes_the_current_kernel_sources():
+    """bench.py reports profile-derived figures (DRAM traffic, issue-slot utilisation) only from a capture of the
+    kernel sources it was built from; a stale committed profile fails here instead of going unnoticed."""
+    from demi_b200 import build
+    prof = json.load(open(os.path.join(ROOT, "profiles", "k1_profile.json")))
+    assert prof["k1_id"] == build.k1_source_id(), "re-run tools/profile_k1.py on the GPU box and commit profiles/k1_profile.json"
+    assert prof["dram_bytes_per_prefix"] > 0 and 0 < prof["issue_slot_utilisation"] <= 1
