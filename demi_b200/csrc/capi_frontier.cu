@@ -389,7 +389,8 @@ int32_t fr_execute_and_scan(FrState& st, uint32_t n_sel, bool root) {
 }
 
 // one steal exchange; `have` = every rank's queue length (all-gathered).  The plan is a pure function of the all-gathered lengths, so every rank computes the same one.
-int32_t fr_exchange(FrState& st, const std::vector<unsigned long long>& have_in, unsigned long long total_pool) {
+int32_t fr_exchange(FrState& st, const std::vector<unsigned long long>& have_in, unsigned long long total_pool,
+                    std::vector<unsigned long long>& have_after) {
   demi_handle* h = st.h; NcclApi* nc = nccl_api(); FrComm* cm = st.comm;
   const int G = cm->world, me = cm->rank;
   const unsigned long long S = st.F.rounds_per_exchange ? st.F.rounds_per_exchange : 1;
@@ -438,6 +439,13 @@ int32_t fr_exchange(FrState& st, const std::vector<unsigned long long>& have_in,
   NCCL_TRY(h, nc->AllGather(st.gather_dev + (size_t)me * G, st.gather_dev, G, ncclUint64, cm->comm, st.s));
   CUDA_TRY(h, cudaMemcpyAsync(mat.data(), st.gather_dev, (size_t)G * G * 8, cudaMemcpyDeviceToHost, st.s));
   CUDA_TRY(h, cudaStreamSynchronize(st.s));
+  // every rank's queue length after the exchange: a donor loses what was planned (explored points are dropped on the
+  // way out), a receiver gains what really arrived
+  have_after = have_in;
+  for (int don = 0; don < G; don++) for (int rcv = 0; rcv < G; rcv++) {
+    have_after[don] -= planned[(size_t)don * G + rcv];
+    have_after[rcv] += mat[(size_t)don * G + rcv];
+  }
   std::vector<size_t> recv_off(G, 0);
   size_t roff = 0;
   for (int don = 0; don < G; don++) { recv_off[don] = roff; roff += (size_t)mat[(size_t)don * G + me]; }
@@ -502,15 +510,21 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
     if (F.stop_if_found && found) break;                                      // :1147
     if (executed >= F.max_interleavings) { budget = 1; break; }
     if (!total_pool) { exhausted = 1; break; }
+    std::vector<unsigned long long> have_after = have;
     if (G > 1) {
       const auto t0 = std::chrono::steady_clock::now();
-      if ((rc = fr_exchange(st, have, total_pool)) != DEMI_OK) return rc;
+      if ((rc = fr_exchange(st, have, total_pool, have_after)) != DEMI_OK) return rc;
       st.R.exchange_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (st.R.status) continue;                                              // reported at the next exchange point
     }
-    // ---- S rounds; this rank may execute its share of what is left of the budget
-    const unsigned long long remaining = F.max_interleavings - executed;
-    unsigned long long allow = remaining / G + ((unsigned long long)me < remaining % G ? 1 : 0);
+    // ---- S rounds.  What is left of the budget goes to the ranks in rank order, each taking what its queue (as every
+    // rank knows it after the exchange) could use in S rounds — so the budget follows the work
+    unsigned long long left = F.max_interleavings - executed, allow = 0;
+    for (int q = 0; q <= me; q++) {
+      const unsigned long long cap = std::min<unsigned long long>((unsigned long long)S * F.width, have_after[q]);
+      allow = std::min(cap, left);
+      left -= allow;
+    }
     for (uint32_t r = 0; r < S && allow && st.pool_live && !st.R.status; r++) {
       const uint32_t quota = (uint32_t)std::min<unsigned long long>(allow, st.W);
       uint32_t n_sel = 0;

@@ -422,11 +422,15 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
       for (uint32_t q = 0; q < n_ranks; q++) any_status |= R[q].R.status != 0;
       if (any_status) break;
     }
-    /* ---- S rounds per rank; rank q may execute its share of what is left of the budget */
-    const uint64_t remaining = F->max_interleavings - executed;
+    /* ---- S rounds per rank.  What is left of the budget goes to the ranks in rank order, each taking what its queue
+     * (as every rank knows it after the exchange) could use in S rounds — so the budget follows the work */
+    uint64_t left = F->max_interleavings - executed;
     for (uint32_t q = 0; q < n_ranks; q++) {
       frank* r = &R[q];
-      uint64_t allow = remaining / n_ranks + (q < remaining % n_ranks ? 1 : 0);
+      uint64_t cap = (uint64_t)S * F->width;
+      if (cap > r->n_pool) cap = r->n_pool;
+      uint64_t allow = cap < left ? cap : left;
+      left -= allow;
       for (uint32_t s = 0; s < S && allow && r->n_pool && !r->R.status; s++) {
         uint32_t quota = allow < F->width ? (uint32_t)allow : F->width;
         const uint64_t before = r->R.interleavings;

@@ -76,10 +76,12 @@ def test_exhaustive_set_parity_and_multi_rank_coverage(oracle):
 def test_multi_rank_runs_are_deterministic_and_respect_the_budget(oracle):
     prog = D.raft5_program(client_cmds=2)[:-1]
     ext = D.pack_externals(prog)
-    F = oracle.frontier_params(60, 3000, 32, explored_slots=1 << 20, pool_cap=1 << 21, rounds_per_exchange=2, steal_max=64)
-    a = oracle.dpor_frontier(N.MODEL_RAFT5, ext, F, 4, model_flags=3)
-    b = oracle.dpor_frontier(N.MODEL_RAFT5, ext, F, 4, model_flags=3)
-    assert a[0] == 0 and (a[1] == b[1]).all()
-    assert all((x == y).all() for x, y in zip(a[3], b[3]))
-    assert a[1]["interleavings"].sum() == 3000 and (a[1]["budget_exhausted"] == 1).all()
-    assert (a[1]["interleavings"] > 0).all()                                    # every rank got work
+    for flags, budget in [(0, 300), (N.FR_NO_HISTORY, 3000)]:               # trackHistory = true / false
+        F = oracle.frontier_params(60, budget, 32, explored_slots=1 << 20, pool_cap=1 << 22, rounds_per_exchange=2, steal_max=64,
+                                   flags=flags)
+        a = oracle.dpor_frontier(N.MODEL_RAFT5, ext, F, 4, model_flags=3)
+        b = oracle.dpor_frontier(N.MODEL_RAFT5, ext, F, 4, model_flags=3)
+        assert a[0] == 0 and (a[1] == b[1]).all()
+        assert all((x == y).all() for x, y in zip(a[3], b[3]))
+        assert a[1]["interleavings"].sum() == budget and (a[1]["budget_exhausted"] == 1).all()
+        assert (a[1]["interleavings"] > 0).all()                                # every rank got work
