@@ -104,7 +104,7 @@ EXPORTS = [
     "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
     "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
     "demi_dpor_frontier", "demi_dpor_frontier_multi", "demi_comm_unique_id", "demi_comm_init", "demi_comm_rank",
-    "demi_create_multi",
+    "demi_create_multi", "demi_conjoin_atoms",
 ]
 
 
@@ -206,6 +206,8 @@ def lib():
     L.demi_comm_rank.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.demi_create_multi.restype = C.c_int32
     L.demi_create_multi.argtypes = [C.POINTER(Config), vp, C.c_int32, vp]
+    L.demi_conjoin_atoms.restype = C.c_int32
+    L.demi_conjoin_atoms.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.demi_stats.restype = C.c_int32
     L.demi_stats.argtypes = [vp, C.POINTER(Perf)]
     _lib = L

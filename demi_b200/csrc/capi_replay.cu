@@ -76,6 +76,7 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
   h->trace_host.assign(events, events + n_events);
   h->trace_ext_host.assign(externals, externals + n_externals);
   h->send_ext_index_host = sidx;
+  h->conjoined.assign(n_externals, -1);                       // a new EventDag has no conjoined atoms
   h->trace_n_uniq = max_uniq + 1;
   h->trace_n_send_events = n_send_events;
   h->trace_n_ext_sends = (uint32_t)sidx.size();
@@ -97,6 +98,18 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
 static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* skips_dev, uint32_t n_masks, uint32_t mask_words,
                              uint32_t looking_for, uint32_t flags, void* out_dev, void* stream,
                              demi_event* rec_dev, uint32_t rec_cap, uint32_t* rec_count_dev);
+
+extern "C" int32_t demi_conjoin_atoms(demi_handle* h, uint32_t e1, uint32_t e2) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (h->trace_ext_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
+  const uint32_t n = (uint32_t)h->trace_ext_host.size();
+  if (e1 >= n || e2 >= n) return fail(h, DEMI_ERR_INVALID, "No such external event: %u", e1 >= n ? e1 : e2);   // :168-173
+  if (e1 == e2) return fail(h, DEMI_ERR_INVALID, "demi_conjoin_atoms: an event cannot be conjoined with itself");
+  if (h->conjoined[e1] >= 0 || h->conjoined[e2] >= 0)                          // the asserts at :174-175
+    return fail(h, DEMI_ERR_STATE, "demi_conjoin_atoms: external %u is already conjoined", h->conjoined[e1] >= 0 ? e1 : e2);
+  h->conjoined[e1] = (int32_t)e2; h->conjoined[e2] = (int32_t)e1;
+  return DEMI_OK;
+}
 
 extern "C" int32_t demi_replay_batch_dev(demi_handle* h, const void* masks_dev, uint32_t n_masks, uint32_t mask_words,
                                          uint32_t looking_for, uint32_t flags, void* out_dev, void* stream) {
@@ -295,6 +308,7 @@ extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t fla
   StsDDMinDriver d;
   d.h = h; d.looking_for = looking_for; d.flags = flags; d.mw = mask_words; d.n_ext = n_ext;
   d.ext = h->trace_ext_host.data();
+  d.conjoined = &h->conjoined;
   // STSSched ignores WaitQuiescence: drop them from the DAG (RunnerUtils.scala:678-684)
   Mask dag(mask_words, 0), zero(mask_words, 0);
   for (uint32_t i = 0; i < n_ext; i++) if (d.ext[i].kind != DEMI_EXT_WAIT_QUIESCENCE) DDMinDriver::setbit(dag, i);

@@ -34,12 +34,24 @@ struct DDMinDriver {
   static Mask unite(const Mask& a, const Mask& b) { Mask r(a.size()); for (size_t i = 0; i < a.size(); i++) r[i] = a[i] | b[i]; return r; }
 
   // UnmodifiedEventDag.get_atomic_events (minification/Util.scala:197-265)
+  // UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178): partner index per external, -1 = none
+  const std::vector<int32_t>* conjoined = nullptr;
+  bool is_conjoined(uint32_t i) const { return conjoined && i < conjoined->size() && (*conjoined)[i] >= 0; }
   bool atomic_events(const Mask& dag, std::vector<Atom>& atoms) const {
     std::vector<int32_t> last_start(DEMI_MAX_ACTORS, -1);
     std::map<std::pair<int, int>, int32_t> last_part;
     atoms.clear();
+    // "First deal with explicitly conjoined atoms" (:210-219); both halves must be present (:211).  The reference
+    // takes HashSet.head as the atom's first element; canonically the lower original index.
+    for (uint32_t i = 0; i < n_ext; i++) {
+      if (!bit(dag, i) || !is_conjoined(i)) continue;
+      const uint32_t p = (uint32_t)(*conjoined)[i];
+      if (p >= n_ext || !bit(dag, p)) return false;
+      if (p > i) atoms.push_back({i, p});
+    }
     for (uint32_t i = 0; i < n_ext; i++) {
       if (!bit(dag, i)) continue;
+      if (is_conjoined(i)) continue;                              // filterNot(_conjoinedAtoms contains ...) :222
       const demi_ext_event& e = ext[i];
       switch (e.kind) {
         case DEMI_EXT_KILL:

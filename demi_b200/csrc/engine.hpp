@@ -51,6 +51,7 @@ struct demi_handle {
   std::vector<demi_event> trace_host;
   std::vector<demi_ext_event> trace_ext_host;
   std::vector<uint16_t> send_ext_index_host;
+  std::vector<int32_t> conjoined;          // UnmodifiedEventDag._conjoinedAtoms over trace_ext_host (demi_conjoin_atoms)
   void* trace_dev = nullptr; void* trace_ext_dev = nullptr;
   uint16_t* ev_ordinal_dev = nullptr; uint16_t* send_ext_index_dev = nullptr;
   uint32_t trace_n_uniq = 0, trace_n_send_events = 0, trace_n_ext_sends = 0;

@@ -174,6 +174,10 @@ class Engine(object):
                                                    sizes.ctypes.data, cap_events, C.byref(out)))
         return ev[:out.n_events].copy(), sizes[:out.n_internal_sizes].copy(), out
 
+    def conjoin_atoms(self, e1, e2):
+        """UnmodifiedEventDag.conjoinAtoms: externals e1, e2 (indices into the trace's externals) form one atom."""
+        self._check(N.lib().demi_conjoin_atoms(self._h, e1, e2))
+
     def ddmin(self, looking_for, flags=0, check_unmodified=True, cap_iterations=1 << 16):
         mw = self.mask_words()
         mcs = np.zeros(mw, dtype=np.uint64)
@@ -386,18 +390,7 @@ def events_of(externals, mask):
     return [e for i, e in enumerate(externals) if (int(mask[i // 64]) >> (i % 64)) & 1]
 
 
-class MinimizationStats(object):
-    """The counters of minification/Minimizer.scala:30-237 that DDMin drives."""
-
-    def __init__(self):
-        self.total_replays = 0
-        self.iteration_size = []
-
-    def increment_replays(self, n=1):
-        self.total_replays += n
-
-    def record_iteration_size(self, n):
-        self.iteration_size.append(n)
+from .minimization_stats import MinimizationStats  # noqa: E402  (minification/Minimizer.scala:30-237)
 
 
 class STSScheduler(object):
@@ -466,11 +459,19 @@ class DDMin(object):
         self._stats = stats or MinimizationStats()
         self.last = None
 
+    def conjoinAtoms(self, e1, e2):
+        """UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178) on the dag DDMin minimizes."""
+        ext = self.oracle.original_externals
+        for e in (e1, e2):
+            if e not in ext:
+                raise ValueError("No such external event:%r" % (e,))
+        self.oracle.engine.conjoin_atoms(ext.index(e1), ext.index(e2))
+
     def minimize(self, violation_fingerprint):
         """Returns the MCS as a list of ExternalEvents (WaitQuiescence dropped, RunnerUtils.scala:678-684)."""
         mcs, iters, out = self.oracle.engine.ddmin(violation_fingerprint, self.oracle.flags, self.checkUnmodifed)
+        self._stats.record_series(iters)
         self._stats.total_replays = out.total_replays
-        self._stats.iteration_size = [int(x) for x in iters]
         self.last = out
         return events_of(self.oracle.original_externals, mcs)
 
@@ -649,7 +650,7 @@ class STSSchedMinimizer(object):
     def minimize(self):
         self.engine.set_trace(self.verified_mcs, pack_externals(self.mcs))
         trace, sizes, out = self.engine.internal_minimize(self.violation, flags=self.flags)
+        self._stats.record_series(sizes, internal=True)
         self._stats.total_replays += out.total_replays
-        self._stats.internal_sizes = [int(x) for x in sizes]
         self.last = out
         return self._stats, trace

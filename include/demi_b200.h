@@ -275,6 +275,10 @@ typedef struct demi_ddmin_out {
   uint32_t verified;            /* verify_mcs: 1 if the MCS still reproduces (DeltaDebugging.scala:64-71) */
   uint32_t reserved[2];
 } demi_ddmin_out;
+/* UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178; RunnerUtils.scala:321): externals e1 and e2 of
+ * the trace given to demi_set_trace (indices into its externals) form one atomic event — DDMin keeps or removes them
+ * together.  demi_set_trace starts a new EventDag without conjoined atoms. */
+int32_t demi_conjoin_atoms(demi_handle* h, uint32_t e1, uint32_t e2);
 int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t flags, int32_t check_unmodified,
                    uint64_t* mcs_mask, uint32_t mask_words,
                    uint32_t* iteration_sizes, uint32_t cap_iterations, demi_ddmin_out* out);

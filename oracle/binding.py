@@ -157,6 +157,23 @@ def project(model, events, ext, mask, filter_known_absents=False):
     return keep
 
 
+def set_conjoined(pairs, n_ext):
+    """UnmodifiedEventDag.conjoinAtoms for the next minimizations on this thread; pairs = [(i, j), ...]; [] clears."""
+    global _conj_keep
+    if not pairs:
+        lib().oracle_set_conjoined(None, C.c_uint32(0))
+        _conj_keep = None
+        return
+    partner = np.full(n_ext, -1, dtype=np.int32)
+    for i, j in pairs:
+        partner[i], partner[j] = j, i
+    _conj_keep = partner
+    lib().oracle_set_conjoined(C.c_void_p(partner.ctypes.data), C.c_uint32(n_ext))
+
+
+_conj_keep = None
+
+
 def ddmin_sts(model, events, ext, looking_for, flags=0, model_flags=0, check_unmodified=True, cap_iter=65536):
     ri = make_replay_input(model, events, ext)
     cfg = Config(0, model, model_flags, 0, 0)
@@ -172,6 +189,7 @@ def ddmin_sts(model, events, ext, looking_for, flags=0, model_flags=0, check_unm
 
 
 def ddmin_superset(ext, K, cap=65536):
+    """DDMin over `ext` with the monotone oracle "fails iff mask is a superset of K"; returns the test log too."""
     ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)
     mw = mask_words(len(ext))
     K = np.ascontiguousarray(K, dtype=np.uint64)

@@ -51,13 +51,27 @@ uint32_t oracle_split_first_len(uint32_t len, uint32_t ways, uint32_t which) {
  * Start..Kill and Partition..UnPartition, everything else single; sorted by the
  * original index of the first element.  Returns -1 on "Kill without preceding
  * Start" / "UnPartition without preceding Partition". */
+/* UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178): partner index per external, -1 = none.
+ * Thread-local test state: set before a minimization, cleared (n = 0) after it. */
+static __thread const int32_t* g_conj = 0;
+static __thread uint32_t g_n_conj = 0;
+void oracle_set_conjoined(const int32_t* partner, uint32_t n) { g_conj = n ? partner : 0; g_n_conj = n; }
+
 int oracle_atomic_events(const demi_ext_event* ext, uint32_t n_ext, const uint64_t* mask, atom_t* atoms) {
   int32_t last_start[DEMI_MAX_ACTORS];
   int32_t last_part[DEMI_MAX_ACTORS][DEMI_MAX_ACTORS];
   for (int a = 0; a < DEMI_MAX_ACTORS; a++) { last_start[a] = -1; for (int b = 0; b < DEMI_MAX_ACTORS; b++) last_part[a][b] = -1; }
   uint32_t n = 0;
+  /* "First deal with explicitly conjoined atoms" (:210-219): both halves must be present (the assert at :211);
+   * canonical head = the lower original index (the reference takes HashSet.head) */
+  for (uint32_t i = 0; i < n_ext && i < g_n_conj; i++) {
+    if (!bit(mask, i) || g_conj[i] < 0) continue;
+    if ((uint32_t)g_conj[i] >= n_ext || !bit(mask, (uint32_t)g_conj[i])) return -1;
+    if ((uint32_t)g_conj[i] > i) { atoms[n].first = i; atoms[n].second = (uint32_t)g_conj[i]; n++; }
+  }
   for (uint32_t i = 0; i < n_ext; i++) {
     if (!bit(mask, i)) continue;
+    if (i < g_n_conj && g_conj[i] >= 0) continue;               /* filterNot(_conjoinedAtoms contains ...) :222 */
     const demi_ext_event* e = &ext[i];
     switch (e->kind) {
       case DEMI_EXT_KILL:

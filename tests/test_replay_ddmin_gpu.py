@@ -169,3 +169,31 @@ def test_replay_large_batch_properties(oracle):
     assert (c == a[perm]).all()
     st = eng.stats()
     assert st.violations == int((c["violation"] != 0).sum())
+
+
+def test_ddmin_with_conjoined_atoms(oracle):
+    """UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178): two externals the caller ties together are
+    kept or removed as one atom; MCS and sequential stats still equal the oracle's."""
+    prog = D.raft5_program(client_cmds=14)
+    ext, ev, code = violating_trace(oracle, N.MODEL_RAFT5, prog, 1, 50, 5, which=1)
+    cfg = D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1)
+    sts = D.STSScheduler(cfg, ev, prog)
+    dd = D.DDMin(sts, checkUnmodifed=True)
+    pairs = [(11, 17), (12, 20)]
+    for i, j in pairs:
+        dd.conjoinAtoms(prog[i], prog[j])
+    with pytest.raises(D.DemiError):
+        dd.conjoinAtoms(prog[11], prog[13])                          # the assert at :174: already conjoined
+    mcs = dd.minimize(code)
+    oracle.set_conjoined(pairs, len(ext))
+    try:
+        rc, cmcs, total_replays, iters, verified = oracle.ddmin_sts(N.MODEL_RAFT5, ev, ext, code, model_flags=1)
+    finally:
+        oracle.set_conjoined([], len(ext))
+    assert rc == 0 and (D.mask_of(prog, mcs) == cmcs).all()
+    assert dd._stats.total_replays == total_replays and dd._stats.iteration_size == [int(x) for x in iters]
+    m = int(cmcs[0])
+    for i, j in pairs:
+        assert ((m >> i) & 1) == ((m >> j) & 1)
+    json_line = dd._stats.toJson()
+    assert '"iteration_size"' in json_line and '"total_replays": %d' % total_replays in json_line
