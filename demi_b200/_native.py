@@ -104,8 +104,21 @@ EXPORTS = [
     "demi_replay_batch_ex", "demi_replay_trace", "demi_internal_minimize",
     "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
     "demi_dpor_frontier", "demi_dpor_frontier_multi", "demi_comm_unique_id", "demi_comm_init", "demi_comm_rank",
-    "demi_create_multi", "demi_conjoin_atoms",
+    "demi_create_multi", "demi_conjoin_atoms", "demi_fuzzer_generate", "demi_experiment_save", "demi_experiment_load",
 ]
+
+
+class FuzzerConfig(C.Structure):
+    _fields_ = [("kill", C.c_double), ("send", C.c_double), ("wait_quiescence", C.c_double), ("partition", C.c_double),
+                ("unpartition", C.c_double), ("num_events", C.c_uint32), ("send_type", C.c_uint32)]
+
+
+class Experiment(C.Structure):
+    _fields_ = [("model", C.c_int32), ("model_flags", C.c_uint32), ("violation", C.c_uint32), ("reserved", C.c_uint32),
+                ("externals", C.c_void_p), ("n_externals", C.c_uint32), ("cap_externals", C.c_uint32),
+                ("events", C.c_void_p), ("n_events", C.c_uint32), ("cap_events", C.c_uint32),
+                ("dep_parent", C.c_void_p), ("n_nodes", C.c_uint32), ("cap_nodes", C.c_uint32),
+                ("mcs_mask", C.c_void_p), ("mask_words", C.c_uint32), ("cap_mask_words", C.c_uint32)]
 
 
 class FrontierParams(C.Structure):
@@ -206,6 +219,13 @@ def lib():
     L.demi_comm_rank.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.demi_create_multi.restype = C.c_int32
     L.demi_create_multi.argtypes = [C.POINTER(Config), vp, C.c_int32, vp]
+    L.demi_fuzzer_generate.restype = C.c_int32
+    L.demi_fuzzer_generate.argtypes = [C.POINTER(FuzzerConfig), C.c_int64, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32,
+                                       C.POINTER(C.c_uint32)]
+    L.demi_experiment_save.restype = C.c_int32
+    L.demi_experiment_save.argtypes = [C.c_char_p, C.POINTER(Experiment)]
+    L.demi_experiment_load.restype = C.c_int32
+    L.demi_experiment_load.argtypes = [C.c_char_p, C.POINTER(Experiment)]
     L.demi_conjoin_atoms.restype = C.c_int32
     L.demi_conjoin_atoms.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.demi_stats.restype = C.c_int32

@@ -510,6 +510,33 @@ int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* p, const ui
                              uint64_t* keep_masks, uint32_t mask_words, demi_provenance_out* out,
                              demi_fuzz_result* results);
 
+/* ------------------------------------------------- fuzz-test generation, persistence */
+/* Fuzzer(num_events, FuzzerWeights, message_gen, prefix, postfix).generateFuzzTest (fuzzing/Fuzzer.scala:24-194),
+ * seeded: the reference seeds the fuzzer and its RandomizedHashSets from the wall clock (:67-68; Util.scala:110), here
+ * all of them take `seed`.  message_gen = "Send(random alive actor, send_type, running counter)".  Host-only. */
+typedef struct demi_fuzzer_config {
+  double   kill, send, wait_quiescence, partition, unpartition;   /* FuzzerWeights (Fuzzer.scala:24-29)        */
+  uint32_t num_events;
+  uint32_t send_type;
+} demi_fuzzer_config;
+int32_t demi_fuzzer_generate(const demi_fuzzer_config* cfg, int64_t seed,
+                             const demi_ext_event* prefix, uint32_t n_prefix,
+                             const demi_ext_event* postfix, uint32_t n_postfix,
+                             demi_ext_event* out, uint32_t cap, uint32_t* n_out);
+/* The flat experiment directory that replaces ExperimentSerializer's Java object streams (Serialization.scala:57-74,
+ * :176-254): externals.bin (demi_ext_event[]), event_trace.bin (demi_event[]), dep_parent.bin (uint16[], optional),
+ * mcs.bin (uint64[] mask over the externals, optional), meta.json {model, model_flags, violation}.  Load: the counts
+ * are always filled in; DEMI_ERR_CAPACITY when a caller buffer is missing or too small. */
+typedef struct demi_experiment {
+  int32_t  model; uint32_t model_flags; uint32_t violation; uint32_t reserved;
+  demi_ext_event* externals; uint32_t n_externals, cap_externals;
+  demi_event*     events;    uint32_t n_events, cap_events;
+  uint16_t*       dep_parent; uint32_t n_nodes, cap_nodes;
+  uint64_t*       mcs_mask;  uint32_t mask_words, cap_mask_words;
+} demi_experiment;
+int32_t demi_experiment_save(const char* dir, const demi_experiment* e);
+int32_t demi_experiment_load(const char* dir, demi_experiment* e);
+
 /* ------------------------------------------------------------- statistics */
 int32_t demi_stats(const demi_handle* h, demi_perf* out);
 

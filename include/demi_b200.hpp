@@ -21,6 +21,7 @@
 // engine reports -> demi::Error (code + demi_last_error text).  There is no CPU fallback: without a
 // CUDA device the constructors throw demi::Error(DEMI_ERR_NO_DEVICE).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -63,10 +64,68 @@ struct SchedulerConfig {
   int32_t strategy = DEMI_RS_FULLY_RANDOM;      // RandomizationStrategy: FullyRandom | SrcDstFIFO
 };
 
+// MinimizationStats (minification/Minimizer.scala:30-237) with the reference's shape: one InnerStats per
+// <strategy, oracle> pair, the maps keyed by the replay number, and toJson() with the keys of minimization_stats.json.
 struct MinimizationStats {
-  uint32_t total_replays = 0;
+  struct InnerStats {
+    std::string name;
+    uint32_t total_replays = 0;
+    std::map<uint32_t, uint32_t> iterationSize, internalIterationSize, maxDistance;
+    std::map<std::string, double> stats;
+    explicit InnerStats(const std::string& n) : name(n) { reset(); }
+    void reset() {                                                       // :125-157 (total_replays is not reset, as written)
+      iterationSize.clear(); internalIterationSize.clear(); maxDistance.clear(); stats.clear();
+      for (const char* k : {"prune_duration_seconds", "prune_start_epoch", "prune_end_epoch", "replay_duration_seconds",
+                            "replay_end_epoch", "replay_start_epoch", "original_duration_seconds"}) stats[k] = -1.0;
+      for (const char* k : {"total_inputs", "total_events", "initial_verification_runs_needed", "minimized_deliveries",
+                            "minimized_externals", "minimized_timers"}) stats[k] = 0.0;
+    }
+    static std::string map_json(const std::map<uint32_t, uint32_t>& m) {
+      std::string o = "{"; bool first = true;
+      for (auto& kv : m) { o += (first ? "\"" : ", \"") + std::to_string(kv.first) + "\": " + std::to_string(kv.second); first = false; }
+      return o + "}";
+    }
+    std::string toJson() const {                                          // :207-217
+      std::string o = "{\"name\": \"" + name + "\", \"iteration_size\": " + map_json(iterationSize) +
+                      ", \"internal_iteration_size\": " + map_json(internalIterationSize) + ", \"total_replays\": " +
+                      std::to_string(total_replays) + ", \"maxDistance\": " + map_json(maxDistance);
+      for (auto& kv : stats) o += ", \"" + kv.first + "\": " + std::to_string(kv.second);
+      return o + "}";
+    }
+  };
+  std::string minimization_strategy, test_oracle;
+  std::vector<InnerStats> stats;
+  void updateStrategy(const std::string& strategy, const std::string& oracle) {   // :41-47
+    minimization_strategy = strategy; test_oracle = oracle;
+    stats.emplace_back("(" + strategy + "," + oracle + ")");
+  }
+  InnerStats& inner() { if (stats.empty()) updateStrategy(minimization_strategy, test_oracle); return stats.back(); }
+  void reset() { inner().reset(); }
+  void increment_replays(uint32_t n = 1) { inner().total_replays += n; }
+  void record_iteration_size(uint32_t n) { inner().iterationSize[inner().total_replays] = n; iteration_size.push_back(n); }
+  void record_internal_size(uint32_t n) { inner().internalIterationSize[inner().total_replays] = n; internal_size.push_back(n); }
+  void record_distance_increase(uint32_t d) { inner().maxDistance[d] = inner().total_replays; }
+  void recordDeliveryStats(uint32_t deliveries, uint32_t externals, uint32_t timers) {
+    inner().stats["minimized_deliveries"] = deliveries; inner().stats["minimized_externals"] = externals; inner().stats["minimized_timers"] = timers;
+  }
+  std::string toJson() const {                                            // :98-100
+    std::string o = "["; bool first = true;
+    for (auto& s : stats) { o += (first ? "" : ", ") + s.toJson(); first = false; }
+    return o + "]";
+  }
+  // the engine returns a minimization's whole record_*_size series; kept in recording order beside the maps
   std::vector<uint32_t> iteration_size, internal_size;
-  void increment_replays(uint32_t n = 1) { total_replays += n; }
+  uint32_t& total_replays_ref() { return inner().total_replays; }
+  // one record per test keyed by the replay number, the fencepost record on the last replay number again
+  void record_series(const uint32_t* sizes, size_t n, bool internal) {
+    InnerStats& in = inner();
+    const uint32_t base = in.total_replays;
+    for (size_t i = 0; i < n; i++) {
+      const uint32_t key = base + (uint32_t)std::min(i + 1, n > 1 ? n - 1 : (size_t)1);
+      (internal ? in.internalIterationSize : in.iterationSize)[key] = sizes[i];
+      (internal ? internal_size : iteration_size).push_back(sizes[i]);
+    }
+  }
 };
 
 // One demi_handle.
@@ -228,8 +287,9 @@ class DDMin {
     std::vector<uint32_t> iters(1 << 16);
     oracle.engine->check(demi_ddmin(oracle.engine->handle(), fp, oracle.flags, checkUnmodifed ? 1 : 0, mcs.data(),
                                     oracle.mask_words(), iters.data(), (uint32_t)iters.size(), &last));
-    _stats->total_replays = last.total_replays;
-    _stats->iteration_size.assign(iters.begin(), iters.begin() + last.n_iterations);
+    _stats->iteration_size.clear();
+    _stats->record_series(iters.data(), last.n_iterations, false);
+    _stats->total_replays_ref() = last.total_replays;
     return events_of(oracle.original_externals, mcs);
   }
   std::optional<EventTrace> verify_mcs(const ExternalEvents& mcs, ViolationFingerprint fp) { return oracle.test(mcs, fp); }
@@ -259,8 +319,9 @@ class STSSchedMinimizer {
                                          (uint32_t)sizes.size(), &last));
     out.resize(last.n_events);
     MinimizationStats s;
-    s.total_replays = last.total_replays;
-    s.internal_size.assign(sizes.begin(), sizes.begin() + last.n_internal_sizes);
+    s.total_replays_ref() = last.total_replays;
+    s.internal_size.clear();
+    s.record_series(sizes.data(), last.n_internal_sizes, true);
     return {s, out};
   }
   demi_intmin_out last{};

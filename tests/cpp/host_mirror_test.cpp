@@ -61,7 +61,7 @@ int main() {
   DDMin ddmin(sts, /*checkUnmodifed=*/true, &stats);
   ExternalEvents mcs = ddmin.minimize(fp);
   std::printf("DDMin: %zu -> %zu externals in %u sequential tests (%u executed)\n", prog.size() - 1, mcs.size(),
-              stats.total_replays, ddmin.last.replays_executed);
+              stats.total_replays_ref(), ddmin.last.replays_executed);
   CHECK(mcs.size() < prog.size());
   auto verified = ddmin.verify_mcs(mcs, fp);
   if (!verified) { mcs.assign(prog.begin(), prog.end() - 1); verified = sts.test(mcs, fp); }
@@ -73,12 +73,12 @@ int main() {
   STSSchedMinimizer im(mcs, *verified, fp, LeftToRightOneAtATime(), cfg);
   auto res = im.minimize();
   std::printf("internal minimization: %u -> %u deliveries in %u replays\n", im.last.deliveries_before,
-              im.last.deliveries_after, res.first.total_replays);
+              im.last.deliveries_after, res.first.total_replays_ref());
   CHECK(im.last.deliveries_after <= im.last.deliveries_before);
   STSSchedMinimizer fifo_min(mcs, *verified, fp, SrcDstFIFORemoval(), cfg);
   auto fres = fifo_min.minimize();
   std::printf("internal minimization (SrcDstFIFORemoval): %u -> %u deliveries in %u replays\n", fifo_min.last.deliveries_before,
-              fifo_min.last.deliveries_after, fres.first.total_replays);
+              fifo_min.last.deliveries_after, fres.first.total_replays_ref());
   CHECK(fifo_min.last.deliveries_after <= fifo_min.last.deliveries_before);
   ReplayScheduler final_check(cfg, res.second, mcs);
   CHECK(final_check.replay(fp).violation == fp);

@@ -46,6 +46,7 @@ def test_binding_layouts_match_the_header(native, tmp_path):
         "demi_incddmin_out": C.sizeof(native.IncDDMinOut), "demi_provenance_out": native.PROVENANCE_DTYPE.itemsize,
         "demi_frontier_params": C.sizeof(native.FrontierParams), "demi_frontier_result": native.FRONTIER_RESULT_DTYPE.itemsize,
         "demi_frontier_entry": native.FRONTIER_ENTRY_DTYPE.itemsize,
+        "demi_fuzzer_config": C.sizeof(native.FuzzerConfig), "demi_experiment": C.sizeof(native.Experiment),
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "demi_b200.h"\nint main(void) {\n' +
