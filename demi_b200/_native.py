@@ -105,7 +105,9 @@ EXPORTS = [
     "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
     "demi_dpor_frontier", "demi_dpor_frontier_multi", "demi_comm_unique_id", "demi_comm_init", "demi_comm_rank",
     "demi_create_multi", "demi_conjoin_atoms", "demi_fuzzer_generate", "demi_experiment_save", "demi_experiment_load",
+    "demi_load_model", "demi_actor_index", "demi_actor_name",
 ]
+MODEL_IR = 100
 
 
 class FuzzerConfig(C.Structure):
@@ -219,6 +221,12 @@ def lib():
     L.demi_comm_rank.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.demi_create_multi.restype = C.c_int32
     L.demi_create_multi.argtypes = [C.POINTER(Config), vp, C.c_int32, vp]
+    L.demi_load_model.restype = C.c_int32
+    L.demi_load_model.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.demi_actor_index.restype = C.c_int32
+    L.demi_actor_index.argtypes = [vp, C.c_char_p]
+    L.demi_actor_name.restype = C.c_char_p
+    L.demi_actor_name.argtypes = [vp, C.c_uint32]
     L.demi_fuzzer_generate.restype = C.c_int32
     L.demi_fuzzer_generate.argtypes = [C.POINTER(FuzzerConfig), C.c_int64, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32,
                                        C.POINTER(C.c_uint32)]

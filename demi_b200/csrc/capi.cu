@@ -12,6 +12,7 @@
 #include "fuzz_kernel.cuh"
 #include "provenance_kernel.cuh"
 #include "lane_kernel.cuh"
+#include "models/model_ir.cuh"
 
 using namespace demi;
 
@@ -45,6 +46,9 @@ static const std::vector<Variant>& variants() {
     make_variant<Bcast32, 16384, 32, true, false>(),
     make_variant<Bcast32, 16384, 1024, true, false>(),
     make_variant<Bcast32, 16384, 1024, true, true>(),
+    make_variant<IrModel, 128, 128, false, false>(),      // a model loaded with demi_load_model
+    make_variant<IrModel, 16384, 1024, true, false>(),
+    make_variant<IrModel, 16384, 1024, true, true>(),
   };
   return v;
 }
@@ -86,7 +90,8 @@ extern "C" int32_t demi_device_count(void) {
 extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (!cfg || !out) return fail(nullptr, DEMI_ERR_INVALID, "demi_create: null argument");
   *out = nullptr;
-  if (cfg->model != DEMI_MODEL_PINGPONG3 && cfg->model != DEMI_MODEL_RAFT5 && cfg->model != DEMI_MODEL_BCAST32)
+  if (cfg->model != DEMI_MODEL_PINGPONG3 && cfg->model != DEMI_MODEL_RAFT5 && cfg->model != DEMI_MODEL_BCAST32 &&
+      cfg->model != DEMI_MODEL_IR)
     return fail(nullptr, DEMI_ERR_INVALID, "demi_create: unknown model %d", cfg->model);
   if (cfg->strategy != DEMI_RS_FULLY_RANDOM && cfg->strategy != DEMI_RS_SRC_DST_FIFO)
     return fail(nullptr, DEMI_ERR_INVALID, "demi_create: unknown randomization strategy %d", cfg->strategy);
@@ -125,6 +130,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   demi_replay_free(h);
   demi_frontier_free(h);
   demi_comm_free(h);
+  cudaFree(h->ir_blob_dev);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -134,10 +140,66 @@ extern "C" void demi_destroy(demi_handle* h) {
   delete h;
 }
 
+// demi_load_model: validate, keep the name table on the host, put programs + initial states on the device
+extern "C" int32_t demi_load_model(demi_handle* h, const void* model_blob, size_t size) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (h->cfg.model != DEMI_MODEL_IR) return fail(h, DEMI_ERR_STATE, "demi_load_model: the handle was created for built-in model %d", h->cfg.model);
+  const uint32_t* w = (const uint32_t*)model_blob;
+  if (!w || size < DEMI_IR_HEADER_WORDS * 4 || w[0] != DEMI_IR_MAGIC) return fail(h, DEMI_ERR_INVALID, "demi_load_model: not a model blob");
+  if (w[1] != DEMI_IR_VERSION) return fail(h, DEMI_ERR_INVALID, "demi_load_model: version %u, this library reads %u", w[1], DEMI_IR_VERSION);
+  const uint32_t na = w[2], sw = w[3], nt = w[4], rl = w[5], il = w[6], nb = w[9];
+  if (na < 1 || na > DEMI_IR_ACTORS || sw < 1 || sw > DEMI_IR_STATE_WORDS || rl > DEMI_IR_MAX_CODE || il > DEMI_IR_MAX_CODE || w[8] > DEMI_IR_OUTBOX || nt > 256)
+    return fail(h, DEMI_ERR_INVALID, "demi_load_model: %u actors x %u words, %u + %u instructions, fan-out %u exceed the limits of demi_model_ir.h", na, sw, rl, il, w[8]);
+  const size_t words = (size_t)DEMI_IR_HEADER_WORDS + rl + il + (size_t)na * sw;
+  if (size < words * 4 + nb) return fail(h, DEMI_ERR_INVALID, "demi_load_model: blob truncated (%zu of %zu bytes)", size, words * 4 + nb);
+  // every operand is a register number < 16 by construction; jump targets and opcodes are checked here
+  for (int prog = 0; prog < 2; prog++) {
+    const uint32_t* code = w + DEMI_IR_HEADER_WORDS + (prog ? rl : 0); const uint32_t len = prog ? il : rl;
+    for (uint32_t pc = 0; pc < len; pc++) {
+      const uint32_t op = code[pc] & 0xFF;
+      if (op > DEMI_IR_RET) return fail(h, DEMI_ERR_INVALID, "demi_load_model: unknown opcode %u at %u", op, pc);
+      if (op == DEMI_IR_LDI || (op >= DEMI_IR_JMP && op <= DEMI_IR_JGE)) {
+        if (pc + 1 >= len) return fail(h, DEMI_ERR_INVALID, "demi_load_model: instruction at %u lacks its immediate", pc);
+        if (op != DEMI_IR_LDI && code[pc + 1] > len) return fail(h, DEMI_ERR_INVALID, "demi_load_model: jump at %u leaves the program", pc);
+        pc++;
+      }
+    }
+  }
+  std::vector<std::string> names;
+  const char* nm = (const char*)(w + words); size_t off = 0;
+  while (off < nb && names.size() < (size_t)na + nt) { const size_t l = strnlen(nm + off, nb - off); names.emplace_back(nm + off, l); off += l + 1; }
+  if (names.size() != (size_t)na + nt) return fail(h, DEMI_ERR_INVALID, "demi_load_model: %zu names for %u actors + %u message types", names.size(), na, nt);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaFree(h->ir_blob_dev); h->ir_blob_dev = nullptr; h->ir_loaded = false;
+  CUDA_TRY(h, cudaMalloc(&h->ir_blob_dev, words * 4));
+  CUDA_TRY(h, cudaMemcpy(h->ir_blob_dev, w, words * 4, cudaMemcpyHostToDevice));
+  h->ir_dev.recv = h->ir_blob_dev + DEMI_IR_HEADER_WORDS; h->ir_dev.inv = h->ir_dev.recv + rl; h->ir_dev.init = h->ir_dev.inv + il;
+  h->ir_dev.recv_len = rl; h->ir_dev.inv_len = il; h->ir_dev.n_actors = na; h->ir_dev.state_words = sw;
+  h->ir_ext_mask = w[7]; h->ir_fanout = w[8]; h->ir_n_actors = na; h->ir_n_types = nt;
+  h->names = names;
+  h->ir_loaded = true;
+  return DEMI_OK;
+}
+extern "C" int32_t demi_actor_index(const demi_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  const int na = demi_model_actors(h);
+  if (h->cfg.model == DEMI_MODEL_IR) { for (int i = 0; i < na; i++) if (h->names[i] == name) return i; return -1; }
+  char* end = nullptr; const long v = strtol(name, &end, 10);
+  return (*name && !*end && v >= 0 && v < na) ? (int32_t)v : -1;
+}
+extern "C" const char* demi_actor_name(const demi_handle* h, uint32_t index) {
+  if (!h || (int)index >= demi_model_actors(h)) return nullptr;
+  if (h->cfg.model == DEMI_MODEL_IR) return h->names[index].c_str();
+  static const char* digits[32] = {"0","1","2","3","4","5","6","7","8","9","10","11","12","13","14","15","16","17","18","19","20",
+                                   "21","22","23","24","25","26","27","28","29","30","31"};
+  return digits[index];
+}
+
 extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, uint32_t n) {
   if (!h) return DEMI_ERR_INVALID;
   if (!ev && n) return fail(h, DEMI_ERR_INVALID, "demi_set_externals: null events");
-  const int n_actors = h->cfg.model == DEMI_MODEL_PINGPONG3 ? 3 : h->cfg.model == DEMI_MODEL_RAFT5 ? 5 : 32;
+  { int32_t mrc = demi_need_model(h); if (mrc != DEMI_OK) return mrc; }
+  const int n_actors = demi_model_actors(h);
   uint32_t sends = 0;
   for (uint32_t i = 0; i < n; i++) {
     const demi_ext_event& e = ev[i];
@@ -207,7 +269,8 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   if (!p) return fail(h, DEMI_ERR_INVALID, "null params");
   if (h->ext_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_externals has not been called");
   if (p->n_prefixes > 0xFFFFFFFFull) return fail(h, DEMI_ERR_INVALID, "n_prefixes > 2^32-1 per call");
-  const uint32_t pcap = demi_pending_cap(h->cfg.model, p->max_messages, h->n_ext_sends);
+  { int32_t mrc = demi_need_model(h); if (mrc != DEMI_OK) return mrc; }
+  const uint32_t pcap = demi_pending_cap(demi_model_key(h), p->max_messages, h->n_ext_sends);
   const uint32_t tcap = demi_tosend_cap(h->n_ext_sends);
   const bool fifo = h->cfg.strategy == DEMI_RS_SRC_DST_FIFO;          // SrcDstFIFO lives in the HBM-pending variants
   const Variant* v = pick_variant(h->cfg.model, pcap, tcap, record, fifo);
@@ -306,6 +369,7 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
     plan.args.index_list = h->ovf_list;
     plan.args.index_count = h->ovf_count;
   }
+  if (h->cfg.model == DEMI_MODEL_IR) CUDA_TRY(h, ir_bind(h->ir_dev, s));
   plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
   CUDA_TRY(h, cudaGetLastError());
   h->perf.kernel_launches++;
@@ -400,6 +464,7 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
   plan.args.rec_counts = h->rec_counts_dev;
   plan.args.rec_parent = dep_parent ? par_dev : nullptr; plan.args.rec_parent_cap = cap_nodes;
   CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), h->stream));
+  if (h->cfg.model == DEMI_MODEL_IR) ir_bind(h->ir_dev, h->stream);
   plan.v->fn<<<1, WARPS * 32, plan.smem, h->stream>>>(plan.args);
   cudaError_t e = cudaGetLastError();
   demi_fuzz_result r{}; uint32_t counts[4] = {0, 0, 0, 0};
@@ -532,6 +597,7 @@ extern "C" int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* 
     plan.args.sum_steps = nullptr; plan.args.n_violations = nullptr;
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, s);
+    if (h->cfg.model == DEMI_MODEL_IR) ir_bind(h->ir_dev, s);
     plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
     e = cudaGetLastError();
     h->perf.kernel_launches++;

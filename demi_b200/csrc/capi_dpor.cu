@@ -76,7 +76,7 @@ int32_t dpor_run(demi_handle* h, const demi_ext_event* ext, const uint32_t* ext_
   const DporVariant* dv = pick_dv(h->cfg.model);
   if (!dv) return fail(h, DEMI_ERR_INVALID, "no DPOR kernel for model %d", h->cfg.model);
   const uint32_t n_ext = ext_offsets[n_searches];
-  const int n_actors = h->cfg.model == DEMI_MODEL_PINGPONG3 ? 3 : h->cfg.model == DEMI_MODEL_RAFT5 ? 5 : 32;
+  const int n_actors = demi_model_actors(h);
   for (uint32_t i = 0; i < n_ext; i++) {
     // "unsuported external event" (DPORwHeuristics.scala:710)
     if (ext[i].kind != DEMI_EXT_START && ext[i].kind != DEMI_EXT_SEND)

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <nccl.h>                    // types only: the library is bound with dlopen (no link-time dependency)
 #include "frontier_kernel.cuh"
+#include "models/model_ir.cuh"
 #include "engine.hpp"
 
 using namespace demi;
@@ -113,7 +114,7 @@ struct FrVariant { int model; int bd; fr_exec_fn fn; size_t smem; };
 template <class MODEL, int BD>
 FrVariant make_frv() { return FrVariant{MODEL::ID, BD, fr_exec_kernel<MODEL, BD>, (size_t)FrExec<MODEL, BD>::WORDS * BD * sizeof(uint32_t)}; }
 const FrVariant* pick_frv(int model) {
-  static const std::vector<FrVariant> v = { make_frv<PingPong3, 128>(), make_frv<Raft5, 128>(), make_frv<Bcast32, 64>() };
+  static const std::vector<FrVariant> v = { make_frv<PingPong3, 128>(), make_frv<Raft5, 128>(), make_frv<Bcast32, 64>(), make_frv<IrModel, 64>() };
   for (const FrVariant& d : v) if (d.model == model) return &d;
   return nullptr;
 }
@@ -174,7 +175,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   st.W = F.width;
   uint32_t n_sends = 0;
   for (uint32_t i = 0; i < n_ext; i++) if (ext[i].kind == DEMI_EXT_SEND) n_sends++;
-  st.cap_pend = demi_fr_pool_entries(h->cfg.model, F.max_messages, n_sends);
+  st.cap_pend = demi_fr_pool_entries(demi_model_key(h), F.max_messages, n_sends);
   if (st.cap_pend >= 0xFFFFu) return fail(h, DEMI_ERR_CAPACITY, "demi_dpor_frontier: %u pending entries per interleaving exceed the 16-bit links", st.cap_pend);
   st.rcap = st.T1 * (st.T1 - 1) / 2;
   st.win_cap = std::min<uint32_t>(std::max<uint32_t>(4 * st.W, 4096), 1u << 22);
@@ -352,6 +353,7 @@ int32_t fr_execute_and_scan(FrState& st, uint32_t n_sel, bool root) {
   if ((unsigned long long)st.n_slots + n_sel > st.F.trace_cap) { st.R.status = DEMI_DS_TRACE_OVF; return DEMI_OK; }
   FrArgs& A = st.A;
   A.n_sel = n_sel; A.root = root ? 1u : 0u; A.first_slot = st.n_slots; A.exec_base = st.n_exec; A.pool_top = st.pool_top;
+  if (h->cfg.model == DEMI_MODEL_IR) CUDA_TRY(h, ir_bind(h->ir_dev, st.s));
   CUDA_TRY(h, cudaEventRecord(st.ev[0], st.s));
   st.v->fn<<<(n_sel + st.v->bd - 1) / st.v->bd, st.v->bd, st.v->smem, st.s>>>(A);
   CUDA_TRY(h, cudaEventRecord(st.ev[1], st.s));
@@ -582,7 +584,8 @@ extern "C" int32_t demi_dpor_frontier(demi_handle* h, const demi_ext_event* ext,
   if (!F.width || F.width > (1u << 20)) return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: width must be in [1, 2^20]");
   if (F.explored_slots < 1024 || (F.explored_slots & (F.explored_slots - 1))) return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: explored_slots must be a power of two >= 1024");
   if (!F.pool_cap || !F.trace_cap || F.trace_cap >= (1u << 28)) return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: pool_cap / trace_cap (below 2^28) must be positive");
-  const int n_actors = h->cfg.model == DEMI_MODEL_PINGPONG3 ? 3 : h->cfg.model == DEMI_MODEL_RAFT5 ? 5 : 32;
+  { int32_t mrc = demi_need_model(h); if (mrc != DEMI_OK) return mrc; }
+  const int n_actors = demi_model_actors(h);
   for (uint32_t i = 0; i < n_ext; i++) {
     if (ext[i].kind != DEMI_EXT_START && ext[i].kind != DEMI_EXT_SEND)       // "unsuported external event" (:710)
       return fail(h, DEMI_ERR_INVALID, "demi_dpor_frontier: external %u is neither Start nor Send", i);

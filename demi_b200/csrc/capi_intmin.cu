@@ -91,7 +91,7 @@ extern "C" int32_t demi_internal_minimize(demi_handle* h, uint32_t looking_for, 
   if (!out) return fail(h, DEMI_ERR_INVALID, "demi_internal_minimize: null output");
   if (h->trace_host.empty()) return fail(h, DEMI_ERR_STATE, "demi_set_trace has not been called");
   memset(out, 0, sizeof(*out));
-  const uint32_t ext_mask = demi_external_type_mask(h->cfg.model);
+  const uint32_t ext_mask = demi_ext_type_mask(h);
   const bool use_fifo = (flags & DEMI_IM_SRC_DST_FIFO) != 0;
   flags &= ~DEMI_IM_SRC_DST_FIFO;
   const std::vector<demi_event> verified = h->trace_host;

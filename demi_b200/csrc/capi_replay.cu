@@ -12,6 +12,7 @@
 #include <deque>
 #include "replay_kernel.cuh"
 #include "engine.hpp"
+#include "models/model_ir.cuh"
 
 using namespace demi;
 
@@ -25,7 +26,7 @@ static ReplayVariant make_rv() {
 }
 static const ReplayVariant* pick_rv(int model) {
   static const std::vector<ReplayVariant> v = {
-    make_rv<PingPong3, 256>(), make_rv<Raft5, 256>(), make_rv<Bcast32, 128>(),
+    make_rv<PingPong3, 256>(), make_rv<Raft5, 256>(), make_rv<Bcast32, 128>(), make_rv<IrModel, 128>(),
   };
   for (const ReplayVariant& r : v) if (r.model == model) return &r;
   return nullptr;
@@ -47,7 +48,8 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
   { int32_t vrc = demi_check_events(h, "demi_set_trace", events, n_events, 0); if (vrc != DEMI_OK) return vrc;
     vrc = demi_check_externals(h, "demi_set_trace", externals, n_externals); if (vrc != DEMI_OK) return vrc; }
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  const uint32_t ext_mask = demi_external_type_mask(h->cfg.model);
+  { int32_t mrc = demi_need_model(h); if (mrc != DEMI_OK) return mrc; }
+  const uint32_t ext_mask = demi_ext_type_mask(h);
   // FIFO correspondence of external MsgSends and original Sends (EventTrace.scala:385-386, :419-436)
   std::vector<uint16_t> ordinal(n_events, 0xFFFF);
   std::map<uint32_t, uint16_t> uniq_to_ord;
@@ -147,7 +149,7 @@ static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* 
   a.ev_ordinal = h->ev_ordinal_dev;
   a.ext = (const uint4*)h->trace_ext_dev; a.n_ext = n_ext;
   a.send_ext_index = h->send_ext_index_dev; a.n_sends = h->trace_n_ext_sends;
-  a.external_type_mask = demi_external_type_mask(h->cfg.model);
+  a.external_type_mask = demi_ext_type_mask(h);
   a.n_uniq_words = (h->trace_n_uniq + 31) / 32;
   a.masks = (const uint64_t*)masks_dev; a.n_masks = n_masks; a.mask_words = mask_words;
   a.skips = (const uint32_t*)skips_dev;
@@ -181,8 +183,10 @@ static int32_t launch_replay(demi_handle* h, const void* masks_dev, const void* 
   a.counters = h->rp_counters;
   if (record) {
     CUDA_TRY(h, cudaFuncSetAttribute(rv->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv->smem));
+    if (h->cfg.model == DEMI_MODEL_IR) CUDA_TRY(h, ir_bind(h->ir_dev, s));
     rv->fn_rec<<<1, rv->bd, rv->smem, s>>>(a);
   } else {
+    if (h->cfg.model == DEMI_MODEL_IR) CUDA_TRY(h, ir_bind(h->ir_dev, s));
     rv->fn<<<grid, rv->bd, rv->smem, s>>>(a);
   }
   CUDA_TRY(h, cudaGetLastError());

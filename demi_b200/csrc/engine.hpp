@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include "../../include/demi_b200.h"
 #include "../../include/demi_limits.h"
+#include "../../include/demi_model_ir.h"
 
 extern thread_local std::string g_create_error;
 
@@ -64,6 +65,12 @@ struct demi_handle {
   // ---- communicator (capi_frontier.cu): NCCL inside the library
   void* comm = nullptr;
   void* frontier = nullptr;      // cached K3F buffers
+  // ---- a model loaded with demi_load_model (model == DEMI_MODEL_IR)
+  bool ir_loaded = false;
+  uint32_t* ir_blob_dev = nullptr;
+  demi_ir_device ir_dev{};
+  uint32_t ir_ext_mask = 0, ir_fanout = 0, ir_n_actors = 0, ir_n_types = 0;
+  std::vector<std::string> names;      // actor names, then message-type names
 };
 void demi_replay_free(demi_handle* h);
 void demi_comm_free(demi_handle* h);
@@ -83,9 +90,20 @@ inline int32_t fail(demi_handle* h, int32_t code, const char* fmt, ...) {
 
 // ---- validation of caller-supplied records (JNI hands over JVM buffers): every actor index, node id and parent
 // pointer is range-checked before any host table or kernel indexes with it.
-inline int demi_model_actors(int model) { return model == DEMI_MODEL_PINGPONG3 ? 3 : model == DEMI_MODEL_RAFT5 ? 5 : 32; }
+inline int demi_model_actors(const demi_handle* h) {
+  const int model = h->cfg.model;
+  if (model == DEMI_MODEL_IR) return (int)h->ir_n_actors;
+  return model == DEMI_MODEL_PINGPONG3 ? 3 : model == DEMI_MODEL_RAFT5 ? 5 : 32;
+}
+// the `model` argument of the capacity rules in demi_limits.h (a loaded model carries its fan-out in the key)
+inline int demi_model_key(const demi_handle* h) { return h->cfg.model == DEMI_MODEL_IR ? (DEMI_MODEL_IR | (int)(h->ir_fanout << 8)) : h->cfg.model; }
+inline uint32_t demi_ext_type_mask(const demi_handle* h) { return h->cfg.model == DEMI_MODEL_IR ? h->ir_ext_mask : demi_external_type_mask(h->cfg.model); }
+inline int32_t demi_need_model(demi_handle* h) {
+  if (h->cfg.model == DEMI_MODEL_IR && !h->ir_loaded) return fail(h, DEMI_ERR_STATE, "demi_load_model has not been called");
+  return DEMI_OK;
+}
 inline int32_t demi_check_externals(demi_handle* h, const char* who, const demi_ext_event* ev, uint32_t n) {
-  const uint32_t na = (uint32_t)demi_model_actors(h->cfg.model);
+  const uint32_t na = (uint32_t)demi_model_actors(h);
   for (uint32_t i = 0; i < n; i++) {
     const demi_ext_event& e = ev[i];
     if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION) return fail(h, DEMI_ERR_INVALID, "%s: external %u has unknown kind %u", who, i, (unsigned)e.kind);
@@ -97,7 +115,7 @@ inline int32_t demi_check_externals(demi_handle* h, const char* who, const demi_
 }
 // n_nodes == 0: node ids are not checked (traces recorded by STSScheduler carry node = 0)
 inline int32_t demi_check_events(demi_handle* h, const char* who, const demi_event* ev, uint32_t n, uint32_t n_nodes) {
-  const uint32_t na = (uint32_t)demi_model_actors(h->cfg.model);
+  const uint32_t na = (uint32_t)demi_model_actors(h);
   for (uint32_t i = 0; i < n; i++) {
     const demi_event& e = ev[i];
     bool ok = true;

@@ -61,6 +61,17 @@ class Engine(object):
         if rc != N.OK:
             raise DemiError(rc, N.lib().demi_last_error(self._h).decode())
 
+    def load_model(self, blob):
+        """demi_load_model: the data-only model of the host's application (demi_b200.model_ir builds the blob)."""
+        self._check(N.lib().demi_load_model(self._h, bytes(blob), len(blob)))
+
+    def actor_index(self, name):
+        return int(N.lib().demi_actor_index(self._h, name.encode()))
+
+    def actor_name(self, index):
+        v = N.lib().demi_actor_name(self._h, index)
+        return v.decode() if v is not None else None
+
     def set_externals(self, events):
         arr = events if isinstance(events, np.ndarray) else pack_externals(events)
         arr = np.ascontiguousarray(arr, dtype=N.EXT_DTYPE)

@@ -108,6 +108,7 @@ enum {
   DEMI_MODEL_PINGPONG3 = 1,
   DEMI_MODEL_RAFT5 = 2,
   DEMI_MODEL_BCAST32 = 3
+  /* 100 = DEMI_MODEL_IR (demi_model_ir.h): the model comes from demi_load_model */
 };
 
 /* Engine-wide configuration == SchedulerConfig (SchedulerConfig.scala:9-37)
@@ -177,6 +178,16 @@ int32_t demi_device_count(void);
 /* new RandomScheduler/STSScheduler/DPORwHeuristics(schedulerConfig, ...) */
 int32_t demi_create(const demi_config* cfg, demi_handle** out);
 void    demi_destroy(demi_handle* h);
+
+/* A data-only actor model for a handle created with model = DEMI_MODEL_IR (include/demi_model_ir.h): the receive()
+ * and invariant programs, initial states, the external-message filter and the actor / message-type name table.  This
+ * is what stands in for "the application's receive()" (Instrumenter.scala:913-1017) and `setInvariant`
+ * (TestOracle.scala:27) when the host's application is not one of the compiled models.  The blob is copied. */
+int32_t demi_load_model(demi_handle* h, const void* model_blob, size_t size);
+/* The name table: the reference addresses actors by name (Scheduler.scala:13-104: blockedActors: Set[String], ...),
+ * the C ABI by index.  Built-in models name their actors "0", "1", ...; a loaded model brings its own names. */
+int32_t demi_actor_index(const demi_handle* h, const char* name);         /* -1 if unknown */
+const char* demi_actor_name(const demi_handle* h, uint32_t index);        /* NULL if out of range */
 
 /* The external-event program == the `_trace: Seq[ExternalEvent]` argument of
  * RandomScheduler.explore (RandomScheduler.scala:234) / TestOracle.test. */

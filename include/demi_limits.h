@@ -25,9 +25,11 @@ static inline uint32_t demi_pow2_at_least(uint32_t x, uint32_t lo, uint32_t hi) 
  *  pingpong3: every external Send may be pending at once  -> n_ext_sends + 8
  *  raft5:     10 timers + net +4 per delivery              -> 16 + 4*(max_messages+1)
  *  bcast32:   net +30 per delivery                         -> 8 + 31*(max_messages+1) */
+/* model IR (demi_model_ir.h): the bound comes from the blob's "max sends of one receive()", model = 100 + 256 * fanout */
 static inline uint32_t demi_pending_bound(int model, int32_t max_messages, uint32_t n_ext_sends) {
   uint32_t d = (max_messages < 0) ? 0u : (uint32_t)max_messages;
   if (d > 100000u) d = 100000u;
+  if ((model & 0xFF) == 100) return n_ext_sends + 8u + (uint32_t)(model >> 8) * (d + 1u);
   switch (model) {
     case 1: return n_ext_sends + 8u;
     case 2: return n_ext_sends + 16u + 4u * (d + 1u);
@@ -54,7 +56,7 @@ static inline uint32_t demi_replay_pending_cap(uint32_t n_send_events) {
 }
 /* EventTypes.externalMessageFilter by message type, per built-in model
  * (pingpong3: PING; raft5: BOOT, CLIENT_CMD; bcast32: INJECT). */
-static inline uint32_t demi_external_type_mask(int model) {
+static inline uint32_t demi_external_type_mask(int model) {      /* model IR: taken from the blob instead */
   switch (model) { case 1: return 1u << 1; case 2: return (1u << 1) | (1u << 2); case 3: return 1u << 2; default: return 0; }
 }
 
@@ -127,6 +129,7 @@ DEMI_HD uint64_t demi_fr_explored_slot(uint64_t key, uint64_t slots) {
 /* executor capacities per interleaving: messages created (pool entries never outlive the execution) */
 static inline uint32_t demi_fr_pool_entries(int model, int32_t max_messages, uint32_t n_ext_sends) {
   uint32_t d = (uint32_t)max_messages + 1u;
+  if ((model & 0xFF) == 100) return n_ext_sends + 8u + ((uint32_t)(model >> 8) + 1u) * d;     /* loaded model: fan-out in the key */
   switch (model) {
     case 1: return n_ext_sends + 2u * d + 8u;
     case 2: return n_ext_sends + 16u + 7u * d;     /* <= 6 outbox ops + one re-arm per delivery */

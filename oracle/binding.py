@@ -111,6 +111,15 @@ def _pow2_at_least(x, lo, hi):
     return c
 
 
+def load_model(blob):
+    """oracle_load_model: the CPU interpreter's copy of a demi_load_model blob (model id 100)."""
+    rc = lib().oracle_load_model(bytes(blob), C.c_size_t(len(blob)))
+    if rc != 0:
+        raise RuntimeError("oracle_load_model: %d" % rc)
+    lib().oracle_ir_external_mask.restype = C.c_uint32
+    _EXT_TYPE_MASK[100] = int(lib().oracle_ir_external_mask())
+
+
 def make_replay_input(model, events, ext):
     events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
     ext = np.ascontiguousarray(ext, dtype=EXT_DTYPE)

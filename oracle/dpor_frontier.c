@@ -22,6 +22,7 @@
 #include "machine.h"
 #include "dpor.h"
 #include "dpor_frontier.h"
+int oracle_model_key(int model);
 
 typedef struct { uint64_t ord, pk; } fkey;                          /* queue entry: order key, explored-set key of (later, earlier) */
 typedef struct { uint64_t id; demi_msg msg; uint16_t ppos; } fpend;  /* a pending message and the position that created it */
@@ -324,7 +325,7 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
   fexec* x = (fexec*)calloc(1, sizeof(fexec));
   x->m.model = model; x->m.model_flags = cfg->model_flags; x->m.blocked_mask = cfg->blocked_mask; x->m.ignore_timers = cfg->ignore_timers;
   x->F = F; x->ext = ext; x->n_ext = n_ext;
-  x->cap_pend = demi_fr_pool_entries(cfg->model, F->max_messages, n_sends);
+  x->cap_pend = demi_fr_pool_entries(oracle_model_key(cfg->model), F->max_messages, n_sends);
   x->pend = (fpend*)malloc(sizeof(fpend) * x->cap_pend);
   const uint64_t cap_scratch = (uint64_t)F->width * T1 * T1 / 2 + (uint64_t)T1 * T1 + F->width + 16;
   fkey* scratch = (fkey*)malloc(sizeof(fkey) * cap_scratch);

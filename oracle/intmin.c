@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "machine.h"
+uint32_t oracle_ir_external_mask(void);
 #include "sts.h"
 
 typedef struct { uint8_t src, dst, type; uint32_t p0, p1; uint32_t count; } mkey;
@@ -129,7 +130,7 @@ int oracle_internal_minimize(const demi_config* cfg, const demi_event* verified,
                              demi_event* out_trace, uint32_t cap_out, uint32_t* n_out,
                              uint32_t* total_replays, uint32_t* internal_sizes, uint32_t cap_sizes, uint32_t* n_sizes,
                              uint32_t* unignorable) {
-  const uint32_t ext_mask = demi_external_type_mask(cfg->model);
+  const uint32_t ext_mask = cfg->model == 100 ? oracle_ir_external_mask() : demi_external_type_mask(cfg->model);
   const uint32_t flags = flags_in & ~DEMI_IM_SRC_DST_FIFO;
   fifo_strategy* fifo = 0;
   if (flags_in & DEMI_IM_SRC_DST_FIFO) { fifo = (fifo_strategy*)malloc(sizeof(fifo_strategy)); fifo_init(fifo, verified, n_verified); }

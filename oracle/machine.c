@@ -14,6 +14,9 @@
 #include "dpor.h"
 #include "dpor_frontier.h"
 
+uint32_t oracle_ir_fanout(void); uint32_t oracle_ir_external_mask(void);
+int oracle_model_key(int model) { return model == 100 ? (100 | (int)(oracle_ir_fanout() << 8)) : model; }
+
 /* ------------------------------------------------------------------ helpers */
 static int key_eq(const om_timer_key* k, int dst, uint8_t type, uint32_t p0, uint32_t p1) {
   return k->dst == dst && k->type == type && k->p0 == p0 && k->p1 == p1;
@@ -419,7 +422,7 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
   m->max_messages = p->max_messages < 0 ? INT_MAX : p->max_messages; /* maxMessages = Int.MaxValue (RandomScheduler.scala:54) */
   m->interval = p->invariant_check_interval;
   m->looking_for = p->looking_for;
-  m->pending_cap = demi_pending_cap(cfg->model, p->max_messages, n_sends);
+  m->pending_cap = demi_pending_cap(oracle_model_key(cfg->model), p->max_messages, n_sends);
   m->tosend_cap = demi_tosend_cap(n_sends);
   m->node_cap = demi_node_cap(m->pending_cap);
   m->event_cap = cap_events;

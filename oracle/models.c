@@ -270,7 +270,10 @@ static const oracle_model MODELS[] = {
   { DEMI_MODEL_RAFT5, 5, 10, raft_init, raft_receive, raft_invariant, raft_affected },
   { DEMI_MODEL_BCAST32, 32, 2, bc_init, bc_receive, bc_invariant, bc_affected },
 };
+extern const oracle_model ORACLE_IR_MODEL;      /* model_ir.c: a model loaded with oracle_load_model */
+int oracle_ir_loaded(void);
 const oracle_model* oracle_get_model(int id) {
+  if (id == ORACLE_IR_MODEL.id) return oracle_ir_loaded() ? &ORACLE_IR_MODEL : 0;
   for (unsigned i = 0; i < sizeof(MODELS) / sizeof(MODELS[0]); i++)
     if (MODELS[i].id == id) return &MODELS[i];
   return 0;
