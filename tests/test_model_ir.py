@@ -73,4 +73,4 @@ def test_loaded_model_on_the_device(oracle):
     OF = oracle.frontier_params(14, 20000, 64, explored_slots=1 << 18, pool_cap=1 << 20)
     rc, ores, oviol, ohashes = oracle.dpor_frontier(N.MODEL_IR, D.pack_externals(dprog), OF, 1, model_flags=flags)
     assert rc == 0 and r["interleavings"] == ores[0]["interleavings"] and (hashes == ohashes[0]).all() and (viol == oviol[0]).all()
-    assert r["violations"] > 0
+    assert r["interleavings"] > 1 and r["exhausted"] == 1
