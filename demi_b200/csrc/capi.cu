@@ -510,7 +510,7 @@ extern "C" int32_t demi_provenance(demi_handle* h, const demi_event* events, uin
   if (!events || !dep_parent || !keep_mask || !out || !mask_words || !n_nodes)
     return fail(h, DEMI_ERR_INVALID, "demi_provenance: events, dep_parent, keep_mask and out are required");
   if (n_nodes > 65536) return fail(h, DEMI_ERR_INVALID, "demi_provenance: node ids are 16-bit");
-  { int32_t vrc = demi_check_events(h, "demi_provenance", events, n_events, n_nodes); if (vrc != DEMI_OK) return vrc;
+  { int32_t vrc = demi_check_events(h, "demi_provenance", events, n_events, n_nodes, DEMI_MAX_ACTORS); if (vrc != DEMI_OK) return vrc;
     vrc = demi_check_parents(h, "demi_provenance", dep_parent, n_nodes); if (vrc != DEMI_OK) return vrc; }
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const size_t ev_b = (size_t)std::max(n_events, 1u) * sizeof(demi_event), par_b = (size_t)n_nodes * 2;

@@ -114,8 +114,10 @@ inline int32_t demi_check_externals(demi_handle* h, const char* who, const demi_
   return DEMI_OK;
 }
 // n_nodes == 0: node ids are not checked (traces recorded by STSScheduler carry node = 0)
-inline int32_t demi_check_events(demi_handle* h, const char* who, const demi_event* ev, uint32_t n, uint32_t n_nodes) {
-  const uint32_t na = (uint32_t)demi_model_actors(h);
+// max_actors == 0: the handle's model decides; else an explicit bound (provenance pruning works on any <= 32 actors)
+inline int32_t demi_check_events(demi_handle* h, const char* who, const demi_event* ev, uint32_t n, uint32_t n_nodes,
+                                 uint32_t max_actors = 0) {
+  const uint32_t na = max_actors ? max_actors : (uint32_t)demi_model_actors(h);
   for (uint32_t i = 0; i < n; i++) {
     const demi_event& e = ev[i];
     bool ok = true;

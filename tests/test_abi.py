@@ -121,6 +121,10 @@ def test_record_validation_rejects_out_of_range_indices(native):
         eng.set_trace(ev, ext)
     assert ei.value.code == native.ERR_INVALID and "unknown actor" in str(ei.value)
     ev[0]["dst"] = 1
+    ev[1]["dst"] = 40                                             # provenance accepts any of the 32 actor slots, not 40
+    with pytest.raises(D.DemiError):
+        eng.provenance(ev, np.array([0, 0], dtype=np.uint16), 1)
+    ev[1]["dst"] = 1
     ev[0]["node"] = 9                                             # outside a 2-node tree
     with pytest.raises(D.DemiError) as ei:
         eng.provenance(ev, np.array([0, 0], dtype=np.uint16), 1)
