@@ -313,6 +313,7 @@ extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t fla
   d.h = h; d.looking_for = looking_for; d.flags = flags; d.mw = mask_words; d.n_ext = n_ext;
   d.ext = h->trace_ext_host.data();
   d.conjoined = &h->conjoined;
+  d.wide_cap = (size_t)h->sm_count * 768;                                // one wave of replay_lane_kernel
   // STSSched ignores WaitQuiescence: drop them from the DAG (RunnerUtils.scala:678-684)
   Mask dag(mask_words, 0), zero(mask_words, 0);
   for (uint32_t i = 0; i < n_ext; i++) if (d.ext[i].kind != DEMI_EXT_WAIT_QUIESCENCE) DDMinDriver::setbit(dag, i);

@@ -27,6 +27,37 @@ struct DDMinDriver {
   // interference siblings waiting on the recursion stack: (dag, remainder)
   std::vector<std::pair<Mask, Mask>> pending_siblings;
   static constexpr size_t BATCH_TARGET = 4096;
+  // wide speculation (STSSched replays are cheap and a test's latency, not its cost, is what a minimisation waits
+  // for): on a miss, the closure of the decision tree below the current frame is evaluated level by level up to
+  // `wide_cap` tests — about one full wave of the replay kernel — so a whole DDMin run is one or two launches
+  size_t wide_cap = 0;
+  struct HalfCache { Mask hv[2]; size_t na; bool ok; };
+  std::map<Mask, HalfCache> half_cache;        // halves() depends on the dag alone; a run meets ~2n distinct dags
+  const HalfCache& halves_of(const Mask& dag) {
+    auto it = half_cache.find(dag);
+    if (it != half_cache.end()) return it->second;
+    HalfCache c; c.ok = halves(dag, c.hv, c.na);
+    return half_cache.emplace(dag, std::move(c)).first->second;
+  }
+  void expand_wide(const std::vector<std::pair<Mask, Mask>>& roots, std::vector<Mask>& want) {
+    std::vector<std::pair<Mask, Mask>> cur = roots, next;
+    while (!cur.empty() && want.size() < wide_cap) {
+      next.clear();
+      for (const auto& f : cur) {
+        const HalfCache& c = halves_of(f.first);
+        if (!c.ok || c.na <= 1) continue;
+        Mask t0 = unite(c.hv[0], f.second), t1 = unite(c.hv[1], f.second);
+        if (!memo.count(t0)) want.push_back(t0);
+        if (!memo.count(t1)) want.push_back(t1);
+        next.emplace_back(c.hv[0], f.second);                      // left half violates
+        next.emplace_back(c.hv[1], f.second);                      // right half violates
+        next.emplace_back(c.hv[0], t1);                            // interference: remainder grows by the sibling
+        next.emplace_back(c.hv[1], t0);
+      }
+      if (want.size() + 2 * next.size() > 2 * wide_cap) break;      // the next level would not fit a wave
+      cur.swap(next);
+    }
+  }
 
   static bool bit(const Mask& m, uint32_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
   static void setbit(Mask& m, uint32_t i) { m[i >> 6] |= 1ull << (i & 63); }
@@ -128,11 +159,18 @@ struct DDMinDriver {
     if (it == memo.end()) {
       std::vector<Mask> want;
       want.push_back(m);
+      if (wide_cap) {
+        std::vector<std::pair<Mask, Mask>> roots;
+        roots.emplace_back(cur_dag, cur_rem);
+        for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend(); ++it2) roots.push_back(*it2);
+        expand_wide(roots, want);
+      } else {
       // depth: 4^d frames * 2 tests; stay near BATCH_TARGET
       int depth = 5;
       expand(cur_dag, cur_rem, depth, want);
       for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend() && want.size() < BATCH_TARGET; ++it2)
         expand(it2->first, it2->second, 3, want);
+      }
       evaluate(want);
       if (error != DEMI_OK) return false;
       it = memo.find(m);
