@@ -284,6 +284,16 @@ namespace {
 
 // STSSched as DDMin's TestOracle: a batch of masks = one replay launch
 struct StsDDMinDriver : DDMinDriver {
+  int32_t evaluate_flat(const uint64_t* masks, size_t n, signed char* out) override {   // the arena slice goes to the kernel as is
+    std::vector<demi_replay_result> res(n);
+    int32_t rc = demi_replay_batch(h, masks, (uint32_t)n, mw, looking_for, flags, res.data());
+    if (rc != DEMI_OK) return rc;
+    for (size_t i = 0; i < n; i++) {
+      if (res[i].status != 0) return fail(h, DEMI_ERR_CAPACITY, "demi_ddmin: a replay reported status %u", (unsigned)res[i].status);
+      out[i] = res[i].violation != 0;
+    }
+    return DEMI_OK;
+  }
   int32_t evaluate_batch(const std::vector<Mask>& want, std::vector<char>& out) override {
     std::vector<uint64_t> flat(want.size() * mw);
     for (size_t i = 0; i < want.size(); i++) std::copy(want[i].begin(), want[i].end(), flat.begin() + i * mw);

@@ -4,6 +4,7 @@
 // STSSched replays (capi_replay.cu) or resumable DPOR instances (capi_dpor.cu).
 #pragma once
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <vector>
 #include "engine.hpp"
@@ -27,36 +28,107 @@ struct DDMinDriver {
   // interference siblings waiting on the recursion stack: (dag, remainder)
   std::vector<std::pair<Mask, Mask>> pending_siblings;
   static constexpr size_t BATCH_TARGET = 4096;
-  // wide speculation (STSSched replays are cheap and a test's latency, not its cost, is what a minimisation waits
-  // for): on a miss, the closure of the decision tree below the current frame is evaluated level by level up to
-  // `wide_cap` tests — about one full wave of the replay kernel — so a whole DDMin run is one or two launches
+  // ---- wide speculation.  STSSched replays are cheap and a test's latency, not its cost, is what a minimisation
+  // waits for: on a miss, the closure of the decision tree below the current frame is evaluated level by level up to
+  // `wide_cap` tests — about one full wave of the replay kernel — so a whole DDMin run is one or two launches.  The
+  // host side must then not cost more than the launch: masks live in one flat arena (a batch is a contiguous slice of
+  // it, handed to the kernel as is), the memo is an open-addressing table over that arena with exact comparison, and
+  // halves() is cached per dag (it depends on the dag alone; a run meets ~2n distinct dags).
   size_t wide_cap = 0;
-  struct HalfCache { Mask hv[2]; size_t na; bool ok; };
-  std::map<Mask, HalfCache> half_cache;        // halves() depends on the dag alone; a run meets ~2n distinct dags
-  const HalfCache& halves_of(const Mask& dag) {
-    auto it = half_cache.find(dag);
-    if (it != half_cache.end()) return it->second;
-    HalfCache c; c.ok = halves(dag, c.hv, c.na);
-    return half_cache.emplace(dag, std::move(c)).first->second;
-  }
-  void expand_wide(const std::vector<std::pair<Mask, Mask>>& roots, std::vector<Mask>& want) {
-    std::vector<std::pair<Mask, Mask>> cur = roots, next;
-    while (!cur.empty() && want.size() < wide_cap) {
-      next.clear();
-      for (const auto& f : cur) {
-        const HalfCache& c = halves_of(f.first);
-        if (!c.ok || c.na <= 1) continue;
-        Mask t0 = unite(c.hv[0], f.second), t1 = unite(c.hv[1], f.second);
-        if (!memo.count(t0)) want.push_back(t0);
-        if (!memo.count(t1)) want.push_back(t1);
-        next.emplace_back(c.hv[0], f.second);                      // left half violates
-        next.emplace_back(c.hv[1], f.second);                      // right half violates
-        next.emplace_back(c.hv[0], t1);                            // interference: remainder grows by the sibling
-        next.emplace_back(c.hv[1], t0);
+  struct WideTable {
+    uint32_t mw = 0;
+    std::vector<uint64_t> arena; std::vector<signed char> res; std::vector<int32_t> slots;
+    void init(uint32_t w) { mw = w; arena.clear(); res.clear(); slots.assign(1u << 12, -1); }
+    size_t size() const { return res.size(); }
+    static uint64_t hash(const uint64_t* m, uint32_t w) {
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (uint32_t i = 0; i < w; i++) { h ^= m[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xD6E8FEB86659FD93ull; }
+      return h ^ (h >> 32);
+    }
+    int32_t find(const uint64_t* m) const {
+      const size_t mask = slots.size() - 1;
+      for (size_t s = hash(m, mw) & mask;; s = (s + 1) & mask) {
+        const int32_t i = slots[s];
+        if (i < 0) return -1;
+        if (!memcmp(&arena[(size_t)i * mw], m, mw * 8)) return i;
       }
-      if (want.size() + 2 * next.size() > 2 * wide_cap) break;      // the next level would not fit a wave
+    }
+    int32_t insert(const uint64_t* m) {                       // index of m; a new entry has res = -1 (not evaluated)
+      int32_t i = find(m);
+      if (i >= 0) return i;
+      if ((res.size() + 1) * 2 > slots.size()) {
+        std::vector<int32_t> ns(slots.size() * 2, -1);
+        const size_t mask = ns.size() - 1;
+        for (size_t k = 0; k < res.size(); k++) { size_t s = hash(&arena[k * mw], mw) & mask; while (ns[s] >= 0) s = (s + 1) & mask; ns[s] = (int32_t)k; }
+        slots.swap(ns);
+      }
+      i = (int32_t)res.size();
+      arena.insert(arena.end(), m, m + mw); res.push_back(-1);
+      const size_t mask = slots.size() - 1;
+      size_t s = hash(m, mw) & mask; while (slots[s] >= 0) s = (s + 1) & mask; slots[s] = i;
+      return i;
+    }
+  } wt;
+  struct DagNode { Mask dag, hv[2]; int32_t child[2]; size_t na; bool ok; };
+  std::vector<DagNode> dag_nodes; std::map<Mask, int32_t> dag_index;
+  int32_t dag_of(const Mask& dag) {
+    auto it = dag_index.find(dag);
+    if (it != dag_index.end()) return it->second;
+    DagNode n; n.dag = dag; n.child[0] = n.child[1] = -1; n.ok = halves(dag, n.hv, n.na);
+    dag_nodes.push_back(std::move(n));
+    return dag_index[dag] = (int32_t)dag_nodes.size() - 1;
+  }
+  int32_t child_of(int32_t d, int k) {
+    if (dag_nodes[d].child[k] < 0) { const int32_t c = dag_of(dag_nodes[d].hv[k]); dag_nodes[d].child[k] = c; }
+    return dag_nodes[d].child[k];
+  }
+  // the oracle over a flat slice of masks (default: through evaluate_batch)
+  virtual int32_t evaluate_flat(const uint64_t* masks, size_t n, signed char* out) {
+    std::vector<Mask> want(n, Mask(mw)); std::vector<char> r(n, 0);
+    for (size_t i = 0; i < n; i++) std::copy(masks + i * mw, masks + (i + 1) * mw, want[i].begin());
+    int32_t rc = evaluate_batch(want, r);
+    for (size_t i = 0; i < n; i++) out[i] = r[i];
+    return rc;
+  }
+  struct Frame { int32_t dag; uint32_t rem; };                  // rem: index into rem_arena
+  std::vector<uint64_t> rem_arena;
+  // evaluates m and, level by level, the tests the recursion below (dag, rem) — and the waiting siblings — can ask for
+  void speculate_wide(const Mask& m, const Mask& cur_dag, const Mask& cur_rem) {
+    const size_t first_new = wt.size();
+    wt.insert(m.data());
+    rem_arena.clear();
+    std::vector<Frame> cur, next;
+    auto add_root = [&](const Mask& dag, const Mask& rem) {
+      cur.push_back(Frame{dag_of(dag), (uint32_t)(rem_arena.size() / mw)});
+      rem_arena.insert(rem_arena.end(), rem.begin(), rem.end());
+    };
+    add_root(cur_dag, cur_rem);
+    for (auto it = pending_siblings.rbegin(); it != pending_siblings.rend(); ++it) add_root(it->first, it->second);
+    std::vector<uint64_t> t0(mw), t1(mw);
+    while (!cur.empty() && wt.size() - first_new < wide_cap) {
+      next.clear();
+      for (const Frame f : cur) {
+        const DagNode& n = dag_nodes[f.dag];
+        if (!n.ok || n.na <= 1) continue;
+        for (uint32_t w = 0; w < mw; w++) { const uint64_t r = rem_arena[(size_t)f.rem * mw + w]; t0[w] = n.hv[0][w] | r; t1[w] = n.hv[1][w] | r; }
+        wt.insert(t0.data()); wt.insert(t1.data());
+        const int32_t c0 = child_of(f.dag, 0), c1 = child_of(f.dag, 1);
+        const uint32_t r0 = (uint32_t)(rem_arena.size() / mw);
+        rem_arena.insert(rem_arena.end(), t1.begin(), t1.end());      // interference: the remainder grows by the sibling half
+        rem_arena.insert(rem_arena.end(), t0.begin(), t0.end());
+        next.push_back(Frame{c0, f.rem}); next.push_back(Frame{c1, f.rem});   // a half violates
+        next.push_back(Frame{c0, r0}); next.push_back(Frame{c1, r0 + 1});
+      }
+      if (wt.size() - first_new + 2 * next.size() > 2 * wide_cap) break;     // the next level would not fit a wave
       cur.swap(next);
     }
+    // entries inserted earlier but never evaluated cannot exist: every insert above is evaluated right here
+    const size_t n_new = wt.size() - first_new;
+    if (!n_new) return;
+    int32_t rc = evaluate_flat(&wt.arena[first_new * mw], n_new, &wt.res[first_new]);
+    if (rc != DEMI_OK) { error = rc; return; }
+    replays_executed += (uint32_t)n_new;
+    batches++;
   }
 
   static bool bit(const Mask& m, uint32_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
@@ -155,22 +227,22 @@ struct DDMinDriver {
 
   // TestOracle.test for the sequential walk
   bool test(const Mask& m, const Mask& cur_dag, const Mask& cur_rem) {
+    if (wide_cap) {
+      if (wt.mw != mw) wt.init(mw);
+      int32_t i = wt.find(m.data());
+      if (i < 0) { speculate_wide(m, cur_dag, cur_rem); if (error != DEMI_OK) return false; i = wt.find(m.data()); }
+      consumed(m);
+      return wt.res[i] > 0;
+    }
     auto it = memo.find(m);
     if (it == memo.end()) {
       std::vector<Mask> want;
       want.push_back(m);
-      if (wide_cap) {
-        std::vector<std::pair<Mask, Mask>> roots;
-        roots.emplace_back(cur_dag, cur_rem);
-        for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend(); ++it2) roots.push_back(*it2);
-        expand_wide(roots, want);
-      } else {
       // depth: 4^d frames * 2 tests; stay near BATCH_TARGET
       int depth = 5;
       expand(cur_dag, cur_rem, depth, want);
       for (auto it2 = pending_siblings.rbegin(); it2 != pending_siblings.rend() && want.size() < BATCH_TARGET; ++it2)
         expand(it2->first, it2->second, 3, want);
-      }
       evaluate(want);
       if (error != DEMI_OK) return false;
       it = memo.find(m);
