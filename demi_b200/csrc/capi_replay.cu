@@ -323,7 +323,9 @@ extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t fla
   d.h = h; d.looking_for = looking_for; d.flags = flags; d.mw = mask_words; d.n_ext = n_ext;
   d.ext = h->trace_ext_host.data();
   d.conjoined = &h->conjoined;
-  d.wide_cap = (size_t)h->sm_count * 768;                                // one wave of replay_lane_kernel
+  // tests per speculative batch: a launch costs ~3 ms of latency whatever its size (one test walks the whole trace),
+  // building a batch ~0.2 us per test on the host; ~6000 tests = five to six levels of the decision tree per launch
+  d.wide_cap = getenv("DEMI_DDMIN_WIDE") ? (size_t)atol(getenv("DEMI_DDMIN_WIDE")) : 6000;
   // STSSched ignores WaitQuiescence: drop them from the DAG (RunnerUtils.scala:678-684)
   Mask dag(mask_words, 0), zero(mask_words, 0);
   for (uint32_t i = 0; i < n_ext; i++) if (d.ext[i].kind != DEMI_EXT_WAIT_QUIESCENCE) DDMinDriver::setbit(dag, i);
@@ -344,6 +346,7 @@ extern "C" int32_t demi_ddmin(demi_handle* h, uint32_t looking_for, uint32_t fla
   bool verified = d.test(mcs, mcs, zero);
   if (d.error != DEMI_OK) return d.error;
   out->mcs_size = DDMinDriver::popcount(mcs);
+  out->reserved[0] = (uint32_t)d.spec_us; out->reserved[1] = (uint32_t)d.eval_us;    // host microseconds: building batches / evaluating them
   out->total_replays = d.total_replays;
   out->n_iterations = (uint32_t)d.iteration_sizes.size();
   out->replays_executed = d.replays_executed;

@@ -4,6 +4,7 @@
 // STSSched replays (capi_replay.cu) or resumable DPOR instances (capi_dpor.cu).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -38,7 +39,7 @@ struct DDMinDriver {
   struct WideTable {
     uint32_t mw = 0;
     std::vector<uint64_t> arena; std::vector<signed char> res; std::vector<int32_t> slots;
-    void init(uint32_t w) { mw = w; arena.clear(); res.clear(); slots.assign(1u << 12, -1); }
+    void init(uint32_t w) { mw = w; arena.clear(); res.clear(); slots.assign(1u << 15, -1); arena.reserve((size_t)w << 15); res.reserve(1u << 15); }
     size_t size() const { return res.size(); }
     static uint64_t hash(const uint64_t* m, uint32_t w) {
       uint64_t h = 0x9E3779B97F4A7C15ull;
@@ -93,7 +94,9 @@ struct DDMinDriver {
   struct Frame { int32_t dag; uint32_t rem; };                  // rem: index into rem_arena
   std::vector<uint64_t> rem_arena;
   // evaluates m and, level by level, the tests the recursion below (dag, rem) — and the waiting siblings — can ask for
+  uint64_t spec_us = 0, eval_us = 0;                            // host time building batches / waiting for them
   void speculate_wide(const Mask& m, const Mask& cur_dag, const Mask& cur_rem) {
+    const auto tq0 = std::chrono::steady_clock::now();
     const size_t first_new = wt.size();
     wt.insert(m.data());
     rem_arena.clear();
@@ -125,7 +128,11 @@ struct DDMinDriver {
     // entries inserted earlier but never evaluated cannot exist: every insert above is evaluated right here
     const size_t n_new = wt.size() - first_new;
     if (!n_new) return;
+    const auto tq1 = std::chrono::steady_clock::now();
     int32_t rc = evaluate_flat(&wt.arena[first_new * mw], n_new, &wt.res[first_new]);
+    const auto tq2 = std::chrono::steady_clock::now();
+    spec_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(tq1 - tq0).count();
+    eval_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(tq2 - tq1).count();
     if (rc != DEMI_OK) { error = rc; return; }
     replays_executed += (uint32_t)n_new;
     batches++;

@@ -269,8 +269,14 @@ struct ReplayMachine {
     bool diverged = false;
     const uint32_t n_ev = A->n_events;
 
+    // the walk is one dependent chain per test; the next event and its ordinal are fetched a step ahead so that their
+    // L2 latency overlaps the current event's work
+    uint4 e_next = n_ev ? __ldg(A->events) : make_uint4(0, 0, 0, 0);
+    uint32_t ord_next = n_ev ? __ldg(A->ev_ordinal) : 0xFFFFu;
     for (uint32_t i = 0; i < n_ev && !status && !diverged; i++) {
-      const uint4 e = __ldg(A->events + i);
+      const uint4 e = e_next;
+      const uint32_t ord_cur = ord_next;
+      if (i + 1 < n_ev) { e_next = __ldg(A->events + i + 1); ord_next = __ldg(A->ev_ordinal + i + 1); }
       const uint32_t kind = e.x & 0xFF, src = (e.x >> 8) & 0xFF, dst = (e.x >> 16) & 0xFF, type = e.x >> 24;
       const uint32_t uniq = e.w & 0xFFFF;
       const bool is_msg = kind == DEMI_EV_MSG_SEND || kind == DEMI_EV_MSG_EVENT;
@@ -297,7 +303,7 @@ struct ReplayMachine {
       }
       // ---- pass 2: filterSends (EventTrace.scala:425-446), FIFO-ordinal form
       if (k && is_msg) {
-        uint32_t ord = __ldg(A->ev_ordinal + i);
+        const uint32_t ord = ord_cur;
         if (ord < A->n_sends && !in_mask(__ldg(A->send_ext_index + ord))) k = false;
       }
       // ---- pass 3: filterKnownAbsentInternals (EventTrace.scala:501-532), as written
