@@ -1,0 +1,548 @@
+"""A second, independently written restatement of the reference's RandomScheduler path — in Python, object for object as
+the Scala reads (actor names are strings, messages are tuples, the structures are the reference's own: RandomizedHashSet,
+DepTracker, EventOrchestrator, the ExternalEventInjector queue, Instrumenter's timer maps) — plus DDMin.ddmin2.
+
+It shares NOTHING with oracle/*.c or include/*.h: no headers, no hash functions, no capacity rules; the actors are
+written a third time from DESIGN.md §3.  tests/test_micro_oracle.py cross-checks it against liboracle.so event by
+event on 10^4 seeds, so an error in the C oracle's reading of the Scala has to be made twice, independently, to pass.
+Test infrastructure only.
+
+Reference (src/main/scala/verification/): schedulers/RandomScheduler.scala:226-321, :352-485, :525-559, :635-697;
+schedulers/Util.scala:110-185, :470-489; DepTracker.scala:82-135; schedulers/EventOrchestrator.scala:132-241, :314-351;
+schedulers/ExternalEventInjector.scala:258-365, :367-441, :541-580, :601-610; Instrumenter.scala:159-168, :1000-1016,
+:1090-1096, :1145-1200; minification/DeltaDebugging.scala:27-109; minification/Util.scala:9-37, :197-265.
+"""
+
+DEADLETTERS = "deadLetters"
+
+
+class JavaRandom(object):                       # java.util.Random, Java SE specification
+    def __init__(self, seed):
+        self.seed = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def _next(self, bits):
+        self.seed = (self.seed * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        r = self.seed >> (48 - bits)
+        return r - (1 << 32) if r >= (1 << 31) and bits == 32 else r
+
+    def nextInt(self, bound):
+        r = self._next(31)
+        m = bound - 1
+        if (bound & m) == 0:
+            return (bound * r) >> 31
+        u = r
+        while True:
+            r = u % bound
+            if u - r + m <= 0x7FFFFFFF:          # no int overflow
+                return r
+            u = self._next(31)
+
+
+class RandomizedHashSet(object):                # schedulers/Util.scala:110-185
+    def __init__(self, seed):
+        self.arr = []                            # ArrayBuffer[(E, Int)]
+        self.hash = {}                           # (E, counter) -> index
+        self.rand = JavaRandom(seed)
+
+    def insert(self, value):
+        c = 0
+        while (id(value), c) in self.hash:       # the uniqueness counter only matters for equal tuples
+            c += 1
+        t = (value, c)
+        self.hash[(id(value), c)] = len(self.arr)
+        self.arr.append(t)
+
+    def remove(self, t):
+        i = self.hash[(id(t[0]), t[1])]
+        d = self.arr[-1]
+        self.arr[i] = d
+        self.hash[(id(d[0]), d[1])] = i
+        self.arr.pop()                           # arr.dropRight(1)
+        del self.hash[(id(t[0]), t[1])]
+
+    def removeRandomElement(self):
+        idx = self.rand.nextInt(len(self.arr))
+        v = self.arr[idx]
+        self.remove(v)
+        return v[0]
+
+    def isEmpty(self):
+        return not self.arr
+
+
+class Unique(object):
+    def __init__(self, event, uid):
+        self.event, self.id = event, uid
+
+
+class DepTracker(object):                        # DepTracker.scala:27-135
+    def __init__(self):
+        self.root = Unique(("null", "null", None), 0)
+        self.next_id = 1
+        self.parent_of = {0: 0}
+        self.children = {0: []}                  # inNeighbors of a node, in creation order
+        self.parentEvent = self.root
+        self.lastQuiescence = self.root          # noopWaitQuiescence: the root stands for every quiescence (:139-150)
+
+    def _getMessage(self, snd, rcv, msg):        # :82-109
+        for c in self.children[self.parentEvent.id]:
+            s, r, m = c.event
+            if s == snd and r == rcv and m == msg:
+                return c, False
+        u = Unique((snd, rcv, msg), self.next_id)
+        self.next_id += 1
+        return u, True
+
+    def reportNewlyEnabled(self, snd, rcv, msg):  # :126-130 with addNodeAndEdge :111-116
+        child, new = self._getMessage(snd, rcv, msg)
+        if new:
+            self.parent_of[child.id] = self.parentEvent.id
+            self.children[self.parentEvent.id].append(child)
+            self.children[child.id] = []
+        return child
+
+    def reportNewlyEnabledExternal(self, snd, rcv, msg):   # :119-122
+        self.parentEvent = self.lastQuiescence
+        return self.reportNewlyEnabled(snd, rcv, msg)
+
+    def reportNewlyDelivered(self, u):           # :132-135
+        self.parentEvent = u
+
+
+class Execution(object):
+    """One RandomScheduler.explore(trace) with max_executions = 1, FullyRandom(seed), checkpointing off."""
+
+    def __init__(self, actors, externals, seed, max_messages, invariant_check_interval, invariant, external_filter,
+                 blocked=(), looking_for=None):
+        self.actors = actors                     # name -> actor object with receive(ctx, sender, msg)
+        self.externals = externals               # [("Start", name) | ("Kill", name) | ("Send", name, msg) | ("Partition", a, b) | ...]
+        self.pendingEvents = RandomizedHashSet(seed)
+        self.maxMessages = max_messages if max_messages >= 0 else 0x7FFFFFFF
+        self.interval = invariant_check_interval
+        self.invariant = invariant
+        self.is_external = external_filter
+        self.blockedActors = set(blocked)
+        self.lookingFor = looking_for
+        self.depTracker = DepTracker()
+        # ExternalEventInjector
+        self.messagesToSend = []                 # (sender or None, receiver, msg)
+        self.enqueuedExternalMessages = []       # MultiSet
+        # RandomScheduler
+        self.justScheduledTimers = set()
+        self.timersToResend = []
+        self.messagesScheduledSoFar = 0
+        self.violationFound = None
+        # EventOrchestrator
+        self.events = []                         # the EventTrace
+        self.traceIdx = 0
+        self.killed, self.inaccessible, self.partitioned = set(), set(actors), set()   # populateActorSystem isolates everyone
+        # Instrumenter
+        self.timerToCancellable = {}             # (rcv, msg) -> ongoing?
+        self.timersCancelledThisStep = set()
+        self.uniq_counter = 0
+        self.max_pending = 0
+
+    # ---- EventOrchestrator
+    def crosses_partition(self, snd, rcv):       # :345-351
+        if snd == rcv and snd not in self.killed:
+            return False
+        return ((snd, rcv) in self.partitioned or (rcv, snd) in self.partitioned or rcv in self.inaccessible or
+                snd in self.inaccessible)
+
+    def inject_until_quiescence(self):           # :132-189
+        loop = True
+        while loop and self.traceIdx < len(self.externals):
+            e = self.externals[self.traceIdx]
+            if e[0] == "Start":
+                self.events.append(("Spawn", e[1]))
+                self.inaccessible.discard(e[1]); self.killed.discard(e[1])
+                self.blockedActors.discard(e[1])
+            elif e[0] == "Kill":
+                self.events.append(("Kill", e[1]))
+                self.killed.add(e[1]); self.inaccessible.add(e[1])
+            elif e[0] == "Send":
+                self.enqueuedExternalMessages.append(e[2])           # enqueue_message :258-268
+                self.messagesToSend.append((None, e[1], e[2]))
+            elif e[0] == "Partition":
+                self.events.append(("Partition", e[1], e[2])); self.partitioned.add((e[1], e[2]))
+            elif e[0] == "UnPartition":
+                self.events.append(("UnPartition", e[1], e[2])); self.partitioned.discard((e[1], e[2]))
+            elif e[0] == "WaitQuiescence":
+                self.events.append(("BeginWaitQuiescence",))
+                loop = False
+            self.traceIdx += 1
+
+    # ---- Instrumenter: `!`, timers
+    def tell(self, sender, rcv, msg):            # aroundDispatch :1033-1108
+        if (rcv, msg) in self.timersCancelledThisStep:               # :1090-1096
+            self.timersCancelledThisStep.discard((rcv, msg))
+            return
+        self.event_produced(sender, rcv, msg)
+
+    def registerCancellable(self, ongoing, rcv, msg):                # :1145-1174
+        if (rcv, msg) in self.timerToCancellable:
+            return                                                   # "Non-unique timer"
+        self.timerToCancellable[(rcv, msg)] = ongoing
+        self.handleTick(rcv, msg)
+
+    def handleTick(self, rcv, msg):              # :1185-1200
+        ongoing = self.timerToCancellable[(rcv, msg)]
+        self.enqueue_timer(rcv, msg)
+        if not ongoing:
+            del self.timerToCancellable[(rcv, msg)]                  # removeCancellable
+
+    def cancelTimer(self, rcv, msg):             # :159-168
+        self.timersCancelledThisStep.add((rcv, msg))
+        self.timerToCancellable.pop((rcv, msg), None)
+        self.notify_timer_cancel(rcv, msg)
+
+    # ---- RandomScheduler
+    def event_produced(self, snd, rcv, msg):     # :274-321
+        self.uniq_counter += 1
+        uniq = self.uniq_counter
+        is_timer = False
+        if msg in self.enqueuedExternalMessages:                     # handle_event_produced :504-507
+            unique = self.depTracker.reportNewlyEnabledExternal(snd, rcv, msg)
+            self.pendingEvents.insert((uniq, unique, snd, rcv, msg))
+        else:
+            if snd == DEADLETTERS:
+                is_timer = True
+            unique = self.depTracker.reportNewlyEnabled(snd, rcv, msg)
+            if not self.crosses_partition(snd, rcv):
+                self.pendingEvents.insert((uniq, unique, snd, rcv, msg))
+        self.max_pending = max(self.max_pending, len(self.pendingEvents.arr))
+        self.events.append(("MsgSend", "Timer" if is_timer else snd, rcv, msg, uniq, unique.id))
+
+    def handle_timer(self, rcv, msg):            # ExternalEventInjector :282-297
+        self.messagesToSend.append((None, rcv, msg))
+
+    def enqueue_timer(self, rcv, msg):           # :549-559
+        if (rcv, msg) in self.justScheduledTimers:
+            self.timersToResend.append((rcv, msg))
+            return
+        self.handle_timer(rcv, msg)
+
+    def notify_timer_cancel(self, rcv, msg):     # :525-534 + handle_timer_cancel (ExternalEventInjector :601-610)
+        for i, (s, r, m) in enumerate(self.messagesToSend):
+            if r == rcv and m == msg:
+                del self.messagesToSend[i]
+                return
+        for t in self.pendingEvents.arr:         # FullyRandom.remove :653-664
+            _, _, s, r, m = t[0]
+            if s == DEADLETTERS and r == rcv and m == msg:
+                self.pendingEvents.remove(t)
+                return
+
+    def send_external_messages(self):            # ExternalEventInjector :306-365
+        queue, self.messagesToSend = self.messagesToSend, []
+        for sender, rcv, msg in queue:
+            self.tell(DEADLETTERS if sender is None else sender, rcv, msg)
+
+    def violationMatches(self, v):               # :138-154
+        if v is None:
+            return None
+        if self.lookingFor is None or v == self.lookingFor:
+            return v
+        return None
+
+    def schedule_new_message(self):              # :352-485
+        if self.violationFound is not None:
+            return None
+        if self.messagesScheduledSoFar > self.maxMessages:
+            self.traceIdx = len(self.externals)                      # finish_early
+            return None
+        if self.interval > 0 and self.messagesScheduledSoFar % self.interval == 0 and self.messagesScheduledSoFar != 0:
+            # lastCheckpoint stays 0 without checkpointing, so the guard `lastCheckpoint != n` is `n != 0`
+            self.violationFound = self.violationMatches(self.invariant(self.actors))
+            if self.violationFound is not None:
+                return None
+        self.send_external_messages()
+        if self.pendingEvents.isEmpty():                             # find_non_blocked_message (Util.scala:470-489)
+            return None
+        blocked = []
+        e = self.pendingEvents.removeRandomElement()
+        while e[3] in self.blockedActors:
+            blocked.append(e)
+            if self.pendingEvents.isEmpty():
+                for b in blocked:
+                    self.pendingEvents.insert(b)
+                return None
+            e = self.pendingEvents.removeRandomElement()
+        for b in blocked:
+            self.pendingEvents.insert(b)
+        uniq, unique, snd, rcv, msg = e
+        self.messagesScheduledSoFar += 1
+        self.events.append(("MsgEvent", snd, rcv, msg, uniq, unique.id))
+        self.depTracker.reportNewlyDelivered(unique)
+        if (rcv, msg) in self.timerToCancellable:                    # updateRepeatingTimer :405-421
+            self.justScheduledTimers.add((rcv, msg))
+        else:
+            for r, t in self.timersToResend:
+                self.handle_timer(r, t)
+            self.timersToResend = []
+            self.justScheduledTimers.clear()
+        return e
+
+    def dispatch_new_message(self, e):           # Instrumenter :913-1017
+        _, _, snd, rcv, msg = e
+        if self.timerToCancellable.get((rcv, msg)):                  # a repeating timer is re-armed right after the hand-off
+            self.handleTick(rcv, msg)
+        self.actors[rcv].receive(Context(self, rcv), snd, msg)
+
+    def run(self):
+        while True:                              # execute_trace / advanceTrace / handle_quiescence
+            self.inject_until_quiescence()
+            while True:
+                e = self.schedule_new_message()
+                if e is None:
+                    break
+                self.dispatch_new_message(e)
+            if self.violationFound is not None:  # notify_quiescence :487-500
+                break
+            if self.traceIdx < len(self.externals):
+                self.events.append(("Quiescence",))
+                continue
+            break
+        if self.violationFound is None and self.messagesScheduledSoFar <= self.maxMessages:   # explore :256 + checkIfBugFound
+            self.violationFound = self.violationMatches(self.invariant(self.actors))
+        return self.violationFound
+
+
+class Context(object):
+    """What an actor can do inside receive(): `!`, scheduleOnce, schedule, cancel."""
+
+    def __init__(self, ex, name):
+        self.ex, self.name = ex, name
+
+    def send(self, dst, msg):
+        self.ex.tell(self.name, dst, msg)
+
+    def schedule_repeating(self, msg):
+        self.ex.registerCancellable(True, self.name, msg)
+
+    def schedule_once(self, msg):
+        self.ex.registerCancellable(False, self.name, msg)
+
+    def cancel(self, msg):
+        self.ex.cancelTimer(self.name, msg)
+
+
+# ---------------------------------------------------------------- the applications, a third time
+class PingPongActor(object):
+    def __init__(self, idx):
+        self.idx, self.pings, self.pongs = idx, 0, 0
+
+    def receive(self, ctx, sender, msg):
+        t, p0, _ = msg
+        if t == 1:
+            self.pings += 1
+            ctx.send(str((self.idx + 1) % 3), (2, p0, 0))
+        elif t == 2:
+            self.pongs += 1
+
+
+BOOT, CLIENT_CMD, ELECTION_TICK, REQUEST_VOTE, VOTE_REPLY, HEARTBEAT_TICK, APPEND_ENTRIES, APPEND_REPLY = range(1, 9)
+INIT, FOLLOWER, CANDIDATE, LEADER = range(4)
+
+
+class RaftActor(object):
+    """Raft Fig. 2, 5 nodes, tick timers, log capacity 8, one entry per AppendEntries, leader no-op on election."""
+
+    def __init__(self, idx, flags):
+        self.idx, self.flags = idx, flags
+        self.role, self.term, self.voted, self.votes, self.heard, self.commit = INIT, 0, None, set(), False, 0
+        self.log = []                            # [(term, value)]
+        self.next, self.match = [0] * 5, [0] * 5
+
+    def step_down(self, ctx, t):
+        if self.role == LEADER:
+            ctx.cancel((HEARTBEAT_TICK, 0, 0))
+        if t > self.term:
+            self.term, self.voted = t, None
+        self.role, self.votes = FOLLOWER, set()
+
+    def send_append(self, ctx, j):
+        prev = self.next[j]
+        pt = self.log[prev - 1][0] if prev else 0
+        has = 1 if prev < len(self.log) else 0
+        et, ev = self.log[prev] if has else (0, 0)
+        ctx.send(str(j), (APPEND_ENTRIES, self.term | (prev << 8) | (pt << 16) | (self.commit << 24), has | (et << 8) | (ev << 16)))
+
+    def receive(self, ctx, sender, msg):
+        ty, p0, p1 = msg
+        src = int(sender) if sender.isdigit() else None
+        last_idx = len(self.log)
+        last_term = self.log[-1][0] if self.log else 0
+        t = p0 & 0xFF
+        if ty not in (BOOT, CLIENT_CMD) and self.role == INIT:
+            return
+        if ty == BOOT:
+            if self.role == INIT:
+                self.role = FOLLOWER
+                ctx.schedule_repeating((ELECTION_TICK, 0, 0))
+        elif ty == CLIENT_CMD:
+            if self.role == LEADER and len(self.log) < 8:
+                self.log.append((self.term, p0 & 0x7F))
+        elif ty == ELECTION_TICK:
+            if self.role == LEADER:
+                return
+            if self.heard:
+                self.heard = False
+                return
+            if self.term == 255:
+                return
+            self.term += 1
+            self.role, self.voted, self.votes = CANDIDATE, self.idx, {self.idx}
+            for j in range(5):
+                if j != self.idx:
+                    ctx.send(str(j), (REQUEST_VOTE, self.term | (last_idx << 8) | (last_term << 16), 0))
+        elif ty == REQUEST_VOTE:
+            li, lt = (p0 >> 8) & 0xFF, (p0 >> 16) & 0xFF
+            if t > self.term:
+                self.step_down(ctx, t)
+            up_to_date = lt > last_term or (lt == last_term and li >= last_idx)
+            can_vote = self.voted is None or self.voted == src or (self.flags & 1)
+            grant = 1 if (t == self.term and can_vote and up_to_date) else 0
+            if grant:
+                self.voted, self.heard = src, True
+            ctx.send(str(src), (VOTE_REPLY, self.term | (grant << 8), 0))
+        elif ty == VOTE_REPLY:
+            if t > self.term:
+                self.step_down(ctx, t)
+                return
+            if self.role == CANDIDATE and t == self.term and (p0 >> 8) & 1:
+                self.votes.add(src)
+                if len(self.votes) >= 3:
+                    self.role = LEADER
+                    self.next, self.match = [len(self.log)] * 5, [0] * 5
+                    if len(self.log) < 8:
+                        self.log.append((self.term, 0x80 | self.idx))
+                    for j in range(5):
+                        if j != self.idx:
+                            self.send_append(ctx, j)
+                    ctx.schedule_repeating((HEARTBEAT_TICK, 0, 0))
+        elif ty == HEARTBEAT_TICK:
+            if self.role == LEADER:
+                for j in range(5):
+                    if j != self.idx:
+                        self.send_append(ctx, j)
+        elif ty == APPEND_ENTRIES:
+            prev, pt, lc = (p0 >> 8) & 0xFF, (p0 >> 16) & 0xFF, (p0 >> 24) & 0xFF
+            has, et, ev = p1 & 1, (p1 >> 8) & 0xFF, (p1 >> 16) & 0xFF
+            if t < self.term:
+                ctx.send(str(src), (APPEND_REPLY, self.term, 0))
+                return
+            if t > self.term or self.role != FOLLOWER:
+                self.step_down(ctx, t)
+            self.heard = True
+            ok = prev <= len(self.log) and (prev == 0 or self.log[prev - 1][0] == pt)
+            if not ok:
+                ctx.send(str(src), (APPEND_REPLY, self.term, 0))
+                return
+            mi = prev
+            if has:
+                if len(self.log) > prev and self.log[prev][0] != et:
+                    del self.log[prev:]
+                if len(self.log) == prev and prev < 8:
+                    self.log.append((et, ev))
+                if len(self.log) > prev:
+                    mi = prev + 1
+            self.commit = max(self.commit, min(lc, mi))
+            ctx.send(str(src), (APPEND_REPLY, self.term | (1 << 8) | (mi << 16), 0))
+        elif ty == APPEND_REPLY:
+            ok, mi = (p0 >> 8) & 1, (p0 >> 16) & 0xFF
+            if t > self.term:
+                self.step_down(ctx, t)
+                return
+            if self.role != LEADER or t != self.term:
+                return
+            if ok:
+                self.match[src] = max(self.match[src], mi)
+                self.next[src] = max(self.next[src], mi)
+                for i in range(len(self.log), self.commit, -1):
+                    if self.log[i - 1][0] != self.term and not (self.flags & 2):
+                        continue
+                    if 1 + sum(1 for k in range(5) if k != self.idx and self.match[k] >= i) >= 3:
+                        self.commit = i
+                        break
+            elif self.next[src] > 0:
+                self.next[src] -= 1
+
+
+def raft_invariant(actors):
+    """1: two leaders in one term; 2: committed prefixes disagree (1 wins; else the first pair in (i, j) order)."""
+    a = [actors[str(i)] for i in range(5)]
+    code = None
+    for i in range(5):
+        for j in range(i + 1, 5):
+            if a[i].role == LEADER and a[j].role == LEADER and a[i].term == a[j].term:
+                return 1
+            if code is None:
+                c = min(a[i].commit, a[j].commit)
+                if a[i].log[:c] != a[j].log[:c]:
+                    code = 2
+    return code
+
+
+def pingpong_invariant(flags):
+    return lambda actors: 7 if (flags & 1) and actors["0"].pongs >= (flags >> 8) else None
+
+
+# ---------------------------------------------------------------- DDMin (minification/DeltaDebugging.scala, Util.scala)
+def split_list(l, split_ways):                   # minification/Util.scala:9-37
+    if split_ways < 1:
+        raise ValueError("Split ways must be greater than 0")
+    splits, split_interval = [], len(l) // split_ways
+    remainder = len(l) % split_ways
+    start_idx = 0
+    while len(splits) < split_ways:
+        split_idx = start_idx + split_interval
+        if remainder > 0:                        # the first `remainder` chunks get one extra element
+            split_idx += 1
+            remainder -= 1
+        splits.append(l[start_idx:split_idx])
+        start_idx = split_idx
+    return splits
+
+
+def atomic_events(events):                       # UnmodifiedEventDag.get_atomic_events, minification/Util.scala:197-265
+    prev, atomics = {}, []
+    for idx, e in events:
+        if e[0] == "Kill":
+            atomics.append([prev.pop(e[1]), (idx, e)])
+        elif e[0] == "Partition":
+            prev[(e[1], e[2])] = (idx, e)
+        elif e[0] == "Start":
+            prev[e[1]] = (idx, e)
+        elif e[0] == "UnPartition":
+            atomics.append([prev.pop((e[1], e[2])), (idx, e)])
+        else:
+            atomics.append([(idx, e)])
+    for v in prev.values():
+        atomics.append([v])
+    return sorted(atomics, key=lambda a: a[0][0])
+
+
+class DDMin(object):                             # minification/DeltaDebugging.scala:7-109
+    def __init__(self, test):
+        self.test, self.total_replays, self.tests = test, 0, []
+
+    def minimize(self, events):
+        return self.ddmin2(list(enumerate(events)), [])
+
+    def ddmin2(self, dag, remainder):
+        atoms = atomic_events(dag)
+        if len(atoms) <= 1:
+            return dag
+        keep = split_list(atoms, 2)
+        for chunk in keep:                       # splits = [dag - chunk0, dag - chunk1].reverse: left half, then right half
+            split = sorted([x for a in chunk for x in a])
+            union = sorted(set(split) | set(remainder))
+            self.total_replays += 1
+            self.tests.append(tuple(i for i, _ in union))
+            if self.test([e for _, e in union]):
+                return self.ddmin2(split, remainder)
+        s0 = sorted([x for a in keep[0] for x in a]); s1 = sorted([x for a in keep[1] for x in a])
+        left = self.ddmin2(s0, sorted(set(s1) | set(remainder)))
+        right = self.ddmin2(s1, sorted(set(s0) | set(remainder)))
+        return sorted(set(left) | set(right))

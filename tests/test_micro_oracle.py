@@ -1,0 +1,129 @@
+"""Cross-check of the C oracle (oracle/*.c) against the independently written Python restatement of the same Scala
+(tests/micro_oracle.py): 10^4 seeds, event by event.  Both are restatements; they share no code, no headers and no
+author-time assumptions beyond the Scala sources and DESIGN.md §3's model specification."""
+import os
+
+import numpy as np
+
+import demi_b200 as D
+from demi_b200 import _native as N
+import micro_oracle as M
+
+
+def to_prog(prog):
+    out = []
+    for e in prog:
+        k = type(e).__name__
+        if k in ("Start", "Kill"):
+            out.append((k, str(e.a)))
+        elif k == "Send":
+            out.append(("Send", str(e.a), (e.type, e.p0, e.p1)))
+        elif k in ("Partition", "UnPartition"):
+            out.append((k, str(e.a), str(e.b)))
+        else:
+            out.append(("WaitQuiescence",))
+    return out
+
+
+def name_idx(s):
+    return 0xFE if s == "Timer" else 0xFF if s == M.DEADLETTERS else int(s)
+
+
+def flat(events):
+    rows = []
+    for e in events:
+        if e[0] in ("MsgSend", "MsgEvent"):
+            _, snd, rcv, (t, p0, p1), uniq, node = e
+            rows.append((1 if e[0] == "MsgSend" else 2, name_idx(snd), int(rcv), t, p0, p1, uniq, node))
+        elif e[0] == "Spawn":
+            rows.append((3, 0xFF, int(e[1]), 0, 0, 0, 0, 0))
+        elif e[0] == "Kill":
+            rows.append((4, 0xFF, int(e[1]), 0, 0, 0, 0, 0))
+        elif e[0] == "Partition":
+            rows.append((5, int(e[1]), int(e[2]), 0, 0, 0, 0, 0))
+        elif e[0] == "UnPartition":
+            rows.append((6, int(e[1]), int(e[2]), 0, 0, 0, 0, 0))
+        elif e[0] == "BeginWaitQuiescence":
+            rows.append((7, 0xFF, 0xFF, 0, 0, 0, 0, 0))
+        else:
+            rows.append((8, 0xFF, 0xFF, 0, 0, 0, 0, 0))
+    return rows
+
+
+def run_micro(model, prog, seed, maxm, interval, flags):
+    if model == N.MODEL_RAFT5:
+        actors = {str(i): M.RaftActor(i, flags) for i in range(5)}
+        inv = M.raft_invariant
+    else:
+        actors = {str(i): M.PingPongActor(i) for i in range(3)}
+        inv = M.pingpong_invariant(flags)
+    ext_types = (1, 2) if model == N.MODEL_RAFT5 else (1,)
+    ex = M.Execution(actors, to_prog(prog), seed, maxm, interval, inv, lambda m: m[0] in ext_types)
+    v = ex.run()
+    return ex, (v or 0)
+
+
+def compare(oracle, model, prog, seeds, maxm, interval, flags, full_trace_every=1):
+    ext = D.pack_externals(prog)
+    res = oracle.fuzz_batch(model, ext, seeds[0], len(seeds), maxm, interval, model_flags=flags)
+    n_viol = 0
+    for k, seed in enumerate(seeds):
+        ex, v = run_micro(model, prog, seed, maxm, interval, flags)
+        r = res[k]
+        assert (int(r["violation"]), int(r["steps"]), int(r["n_nodes"]), int(r["n_events"]), int(r["max_pending"]), int(r["status"])) == \
+               (v, ex.messagesScheduledSoFar, ex.depTracker.next_id, len(ex.events), ex.max_pending, 0), seed
+        n_viol += bool(v)
+        if k % full_trace_every == 0:
+            ev, par, _ = oracle.fuzz_trace(model, ext, seed, maxm, interval, model_flags=flags)
+            rows = flat(ex.events)
+            assert len(rows) == len(ev), seed
+            got = [(int(e["kind"]), int(e["src"]), int(e["dst"]), int(e["type"]), int(e["p0"]), int(e["p1"]), int(e["uniq"]), int(e["node"]))
+                   for e in ev]
+            assert got == rows, (seed, next(i for i in range(len(rows)) if got[i] != rows[i]))
+            assert [int(x) for x in par] == [ex.depTracker.parent_of[i] for i in range(ex.depTracker.next_id)], seed
+    return n_viol
+
+
+def test_raft5_bench_workload_10k_seeds(oracle):
+    """The headline workload (raft5, depth 50, invariant every 5, double-vote bug): verdicts + counters on 10^4 seeds,
+    the whole EventTrace and DepTracker tree on every 10th."""
+    n = int(os.environ.get("DEMI_MICRO_SEEDS", "10000"))
+    n_viol = compare(oracle, N.MODEL_RAFT5, D.raft5_program(), list(range(1, n + 1)), 50, 5, 1, full_trace_every=10)
+    assert n_viol > n // 50                                          # the seeded bug is found (~5 % of the prefixes)
+
+
+def test_raft5_with_kills_partitions_and_client_commands(oracle):
+    prog = D.raft5_program(client_cmds=4)[:-1] + [D.WaitQuiescence(), D.Partition(0, 1), D.Kill(2), D.Send(3, 2, 9), D.WaitQuiescence(),
+                                                  D.UnPartition(0, 1), D.Start(2), D.Send(0, 2, 11), D.WaitQuiescence()]
+    compare(oracle, N.MODEL_RAFT5, prog, list(range(1, 401)), 120, 7, 3, full_trace_every=4)
+    compare(oracle, N.MODEL_RAFT5, prog, list(range(1000, 1200)), -1 if False else 300, 0, 2, full_trace_every=4)
+
+
+def test_pingpong3_config0(oracle):
+    """BASELINE.json configs[0]: 3-actor ping-pong, 100 external messages, seed = 1 (and its neighbours)."""
+    compare(oracle, N.MODEL_PINGPONG3, D.pingpong3_program(100), list(range(1, 301)), -1, 0, 0, full_trace_every=3)
+    compare(oracle, N.MODEL_PINGPONG3, D.pingpong3_program(20), list(range(1, 2001)), -1, 3, 1 | (4 << 8), full_trace_every=20)
+
+
+def test_ddmin2_test_sequence_matches_the_c_oracle(oracle):
+    """DDMin.ddmin2 over a monotone oracle ("violates iff the subsequence contains K"): same tests, in the same order."""
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(4, 28))
+        prog = [D.Start(a) for a in range(3)] + [D.Send(k % 3, 1, k) for k in range(n)]
+        if trial % 3 == 0:
+            prog += [D.Partition(0, 1), D.Send(2, 1, 99), D.UnPartition(0, 1), D.Kill(2)]
+        ext = D.pack_externals(prog)
+        K = set(int(x) for x in rng.choice(np.arange(3, 3 + n), size=int(rng.integers(1, 4)), replace=False))
+        Kmask = np.zeros(1, dtype=np.uint64)
+        for i in K:
+            Kmask[0] |= np.uint64(1 << i)
+        rc, mcs, total, iters, log = oracle.ddmin_superset(ext, Kmask)
+        assert rc == 0
+        events = to_prog(prog)
+        index = {id(e): i for i, e in enumerate(events)}
+        dd = M.DDMin(lambda sub: K <= set(index[id(e)] for e in sub))
+        got = dd.minimize(events)
+        assert sorted(i for i, _ in got) == [i for i in range(len(prog)) if (int(mcs[0]) >> i) & 1]
+        assert dd.total_replays == total
+        assert [sum(1 << i for i in t) for t in dd.tests] == [int(m[0]) for m in log]
