@@ -132,7 +132,7 @@ struct FrState {
   uint4* tr = nullptr; uint32_t* tr_meta = nullptr; unsigned long long* E = nullptr; ulonglong2* pool = nullptr;
   ulonglong2* sel = nullptr; unsigned long long* out_hash = nullptr; uint32_t* out_viol = nullptr;
   uint4* pendA = nullptr; uint32_t* pendP1 = nullptr; uint32_t* pendNX = nullptr;
-  uint32_t* races = nullptr; uint32_t* n_races = nullptr; uint32_t* counts = nullptr; uint32_t* tot = nullptr;
+  uint32_t* races = nullptr; uint32_t* n_races = nullptr; uint32_t* counts = nullptr; uint32_t* tot = nullptr; uint32_t* tile_tot = nullptr;
   unsigned long long* base = nullptr; unsigned long long* ctr = nullptr; FrInfo* info = nullptr;
   ulonglong2* win = nullptr; uint8_t* flag = nullptr; unsigned long long* skey = nullptr; uint32_t* sidx = nullptr;
   uint32_t* blockcnt = nullptr; FrSeg* segs_dev = nullptr; uint32_t segs_cap = 0;
@@ -191,7 +191,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   DA(sel, std::max<uint32_t>(st.W, F.steal_max)) DA(out_hash, st.cap_exec) DA(out_viol, st.cap_exec)
   const size_t warps = (st.W + 31) / 32;
   DA(pendA, warps * st.cap_pend * 32) DA(pendP1, warps * st.cap_pend * 32) DA(pendNX, warps * st.cap_pend * 32)
-  DA(races, (size_t)st.W * st.rcap) DA(n_races, st.W) DA(counts, (size_t)st.T1 * st.W) DA(tot, st.T1) DA(base, st.T1)
+  DA(races, (size_t)st.W * st.rcap) DA(n_races, st.W) DA(counts, (size_t)st.T1 * st.W) DA(tot, st.T1) DA(base, st.T1) DA(tile_tot, (size_t)st.T1 * ((st.W + FR_TILE - 1) / FR_TILE + 1))
   DA(ctr, FRC_N) DA(info, 1)
   DA(win, st.win_cap) DA(flag, st.win_cap) DA(skey, st.s_slots) DA(sidx, st.s_slots) DA(blockcnt, (st.win_cap + 255) / 256 + 1)
   st.segs_cap = 1 << 16; DA(segs_dev, st.segs_cap)
@@ -224,7 +224,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   A.sel = st.sel; A.out_hash = st.out_hash; A.out_viol = st.out_viol;
   A.pendA = st.pendA; A.pendP1 = st.pendP1; A.pendNX = st.pendNX; A.cap_pend = st.cap_pend;
   A.ctr = st.ctr; A.races = st.races; A.rcap = st.rcap; A.n_races = st.n_races;
-  A.counts = st.counts; A.tot = st.tot; A.base = st.base; A.pool = st.pool; A.info = st.info;
+  A.counts = st.counts; A.tot = st.tot; A.base = st.base; A.tile_tot = st.tile_tot; A.pool = st.pool; A.info = st.info;
   return DEMI_OK;
 }
 
@@ -361,8 +361,9 @@ int32_t fr_execute_and_scan(FrState& st, uint32_t n_sel, bool root) {
   const size_t scan_smem = (size_t)SCAN_WPB * fr_scan_words(st.T1) * 4, cnt_smem = (size_t)SCAN_WPB * fr_cnt_words(st.T1) * 4;
   fr_scan_kernel<SCAN_WPB><<<wb, SCAN_WPB * 32, scan_smem, st.s>>>(A);       // every race of the round is marked explored ...
   fr_count_kernel<SCAN_WPB><<<wb, SCAN_WPB * 32, cnt_smem, st.s>>>(A);        // ... before any of its points is enqueued
-  fr_rowscan_kernel<<<st.T1, 256, 0, st.s>>>(A);
-  fr_base_kernel<<<1, 32, 0, st.s>>>(A);
+  const uint32_t n_tiles = (n_sel + FR_TILE - 1) / FR_TILE;
+  fr_rowscan_kernel<<<dim3(st.T1, n_tiles), 256, 0, st.s>>>(A);
+  fr_base_kernel<<<1, 1024, 0, st.s>>>(A, n_tiles);
   fr_scatter_kernel<SCAN_WPB><<<wb, SCAN_WPB * 32, cnt_smem, st.s>>>(A, st.F.pool_cap);
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaEventRecord(st.ev[2], st.s));

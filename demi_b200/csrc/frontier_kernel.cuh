@@ -54,6 +54,7 @@ struct FrArgs {
   // race scan / enqueue
   uint32_t* races; uint32_t rcap; uint32_t* n_races;   // per trace of the round
   uint32_t* counts; uint32_t* tot; unsigned long long* base;   // [T1][n_sel] emitted points per (branch, trace); per-branch totals / bases
+  uint32_t* tile_tot;                                          // [T1][n_tiles] sums, then offsets, of FR_TILE-trace tiles of a row
   ulonglong2* pool; unsigned long long pool_top;
   FrInfo* info;
 };
@@ -444,38 +445,43 @@ fr_count_kernel(const __grid_constant__ FrArgs A) {
   for (uint32_t i = lane; i < T1; i += 32) A.counts[(size_t)i * A.n_sel + j] = cnt[i];
 }
 
-// enqueue, step 2: exclusive scan of every branch row (one block per branch), row totals
+// enqueue, step 2: exclusive scan of every branch row, tiled: block (branch, tile) scans FR_TILE counters in place
+// and leaves the tile's sum; step 3 turns the tile sums into tile offsets and the per-branch bases
+constexpr uint32_t FR_TILE = 1024;
 __global__ void __launch_bounds__(256)
 fr_rowscan_kernel(const __grid_constant__ FrArgs A) {
   __shared__ uint32_t wsum[8];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = A.counts + (size_t)blockIdx.x * A.n_sel;
+  const uint32_t b = blockIdx.x, tile = blockIdx.y, n_tiles = gridDim.y;
+  uint32_t* row = A.counts + (size_t)b * A.n_sel;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  const uint32_t i0 = tile * FR_TILE + threadIdx.x * 4;                       // four consecutive counters per thread
+  uint32_t v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (i0 + k < A.n_sel) ? row[i0 + k] : 0u; t += v[k]; }
+  uint32_t x = t;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL_MASK, x, o); if ((int)lane >= o) x += y; }
+  if (lane == 31) wsum[wid] = x;
   __syncthreads();
-  for (uint32_t base = 0; base < A.n_sel; base += 256) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < A.n_sel ? row[i] : 0u;
-    uint32_t x = v;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL_MASK, x, o); if ((int)lane >= o) x += y; }
-    if (lane == 31) wsum[wid] = x;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (uint32_t k = 0; k < wid; k++) woff += wsum[k];
-    const uint32_t carry = carry_s;
-    if (i < A.n_sel) row[i] = carry + woff + x - v;
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + woff + x;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) A.tot[blockIdx.x] = carry_s;
+  uint32_t off = x - t;
+  for (uint32_t k = 0; k < wid; k++) off += wsum[k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (i0 + k < A.n_sel) row[i0 + k] = off; off += v[k]; }
+  if (threadIdx.x == 255) A.tile_tot[(size_t)b * n_tiles + tile] = off;
 }
-// enqueue, step 3: where each branch's points start in the queue (deeper branch first)
-__global__ void fr_base_kernel(const __grid_constant__ FrArgs A) {
-  if (threadIdx.x || blockIdx.x) return;
-  unsigned long long off = A.pool_top;
-  for (uint32_t b = A.T1; b-- > 0;) { A.base[b] = off; off += A.tot[b]; }
-  A.info->new_top = off;
+// enqueue, step 3: tile offsets per branch, then where each branch's points start in the queue (deeper branch first)
+__global__ void __launch_bounds__(1024)
+fr_base_kernel(const __grid_constant__ FrArgs A, uint32_t n_tiles) {
+  for (uint32_t b = threadIdx.x; b < A.T1; b += blockDim.x) {
+    uint32_t acc = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) { const uint32_t c = A.tile_tot[(size_t)b * n_tiles + t]; A.tile_tot[(size_t)b * n_tiles + t] = acc; acc += c; }
+    A.tot[b] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long off = A.pool_top;
+    for (uint32_t b = A.T1; b-- > 0;) { A.base[b] = off; off += A.tot[b]; }
+    A.info->new_top = off;
+  }
 }
 // enqueue, step 4: write the points in queue order
 template <int WPB>
@@ -513,7 +519,8 @@ fr_scatter_kernel(const __grid_constant__ FrArgs A, unsigned long long pool_cap)
     if (alive && rank == 0) cnt[br] = old + __popc(grp);
     __syncwarp();
     if (alive) {
-      const unsigned long long dst = A.base[br] + A.counts[(size_t)br * A.n_sel + j] + old + rank;
+      const unsigned long long dst = A.base[br] + A.tile_tot[(size_t)br * ((A.n_sel + FR_TILE - 1) / FR_TILE) + j / FR_TILE] +
+                                     A.counts[(size_t)br * A.n_sel + j] + old + rank;
       A.pool[dst] = make_ulonglong2(demi_fr_ord(br, slot, li, ei), demi_fr_pair_key(ids[li], ids[ei]));
     }
   }

@@ -97,7 +97,7 @@ def c2_dpor(rank, world, local_rank, cores, with_cpu):
         eng.close()
     # ---- (b) trackHistory = false, budgeted, all ranks + steal round
     per_gpu = int(os.environ.get("DEMI_C2_BUDGET", str(1 << 20)))
-    width = 65536
+    width = int(os.environ.get("DEMI_C2_WIDTH", "131072"))
     eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=3, device=local_rank))
     if world > 1:
         uid = torch.zeros(N.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
