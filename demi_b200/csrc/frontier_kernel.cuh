@@ -377,7 +377,39 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
   uint32_t* rec = A.races + (size_t)j * A.rcap;
   uint32_t nr = 0;
   unsigned long long new_pairs = 0;
-  for (uint32_t li = b + 1; li < n; li++) {
+  // one candidate (earlier delivery to the same receiver) per lane.  A later position rarely has more than 16
+  // candidates, so two consecutive later positions share an iteration, one per half-warp; lane order is then still
+  // (later, earlier) order, which the ballot compaction below relies on.
+  auto test_pair = [&](uint32_t li, uint32_t lfp, uint32_t ei, uint32_t& br) -> bool {
+    const uint32_t efp = (meta[ei] >> 8) & 0xFFFu;
+    uint32_t a = lfp;
+    while (a > efp) a = meta[a] >> 20;                                        // laterN.pathTo(earlierN) :1104
+    if (a == efp) return false;
+    uint32_t e2 = efp; a = lfp;                                               // getCommonPrefix(...).last :994-1018
+    while (a != e2) { if (a > e2) a = meta[a] >> 20; else e2 = meta[e2] >> 20; }
+    br = a;
+    (void)li;
+    return true;
+  };
+  for (uint32_t li = b + 1; li < n;) {
+    const bool two = li + 1 < n && lidx[li] <= 16 && lidx[li + 1] <= 16;
+    if (two) {
+      const uint32_t my_li = li + (lane >> 4), k = lane & 15;
+      const uint32_t ml = meta[my_li];
+      bool race = false; uint32_t ei = 0, br = 0;
+      if (k < lidx[my_li]) {
+        ei = lst[roff[(ml & 0xFFu) + 1] + k];
+        race = test_pair(my_li, (ml >> 8) & 0xFFFu, ei, br);
+      }
+      const unsigned m = __ballot_sync(FULL_MASK, race);
+      if (race) {
+        rec[nr + __popc(m & ((1u << lane) - 1u))] = fr_rec(my_li, ei, br);
+        if (!A.no_history && fr_e_insert(A.E, A.e_slots, demi_fr_pair_key(ids[ei], ids[my_li]), A.ctr)) new_pairs++;   // :1071-1073
+      }
+      nr += __popc(m);
+      li += 2;
+      continue;
+    }
     const uint32_t ml = meta[li];
     const uint32_t lfp = (ml >> 8) & 0xFFFu;
     const uint32_t c = lidx[li];
@@ -385,18 +417,7 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
     for (uint32_t k0 = 0; k0 < c; k0 += 32) {
       const uint32_t k = k0 + lane;
       bool race = false; uint32_t ei = 0, br = 0;
-      if (k < c) {
-        ei = bucket[k];
-        const uint32_t efp = (meta[ei] >> 8) & 0xFFFu;
-        uint32_t a = lfp;
-        while (a > efp) a = meta[a] >> 20;                                    // laterN.pathTo(earlierN) :1104
-        if (a != efp) {
-          race = true;
-          uint32_t e2 = efp; a = lfp;                                         // getCommonPrefix(...).last :994-1018
-          while (a != e2) { if (a > e2) a = meta[a] >> 20; else e2 = meta[e2] >> 20; }
-          br = a;
-        }
-      }
+      if (k < c) { ei = bucket[k]; race = test_pair(li, lfp, ei, br); }
       const unsigned m = __ballot_sync(FULL_MASK, race);
       if (race) {
         rec[nr + __popc(m & ((1u << lane) - 1u))] = fr_rec(li, ei, br);
@@ -404,6 +425,7 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
       }
       nr += __popc(m);
     }
+    li++;
   }
   for (int o = 16; o > 0; o >>= 1) new_pairs += __shfl_xor_sync(FULL_MASK, new_pairs, o);
   if (lane == 0) {
