@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdemi_b200.so")
 OK, ERR_INVALID, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_REPLAY = 0, -1, -2, -3, -4, -5, -6
 DEADLETTERS, TIMER_SND = 0xFF, 0xFE
 MODEL_PINGPONG3, MODEL_RAFT5, MODEL_BCAST32 = 1, 2, 3
-EXT_START, EXT_KILL, EXT_SEND, EXT_WAIT_QUIESCENCE, EXT_PARTITION, EXT_UNPARTITION = 1, 2, 3, 4, 5, 6
+EXT_START, EXT_KILL, EXT_SEND, EXT_WAIT_QUIESCENCE, EXT_PARTITION, EXT_UNPARTITION, EXT_HARD_KILL = 1, 2, 3, 4, 5, 6, 7
 EV_MSG_SEND, EV_MSG_EVENT, EV_SPAWN, EV_KILL, EV_PARTITION, EV_UNPARTITION, EV_BEGIN_WAIT_QUIESCENCE, EV_QUIESCENCE = range(1, 9)
 
 
@@ -105,8 +105,10 @@ EXPORTS = [
     "demi_provenance", "demi_fuzz_provenance", "demi_dpor_batch_ex", "demi_incremental_ddmin",
     "demi_dpor_frontier", "demi_dpor_frontier_multi", "demi_comm_unique_id", "demi_comm_init", "demi_comm_rank",
     "demi_create_multi", "demi_conjoin_atoms", "demi_fuzzer_generate", "demi_experiment_save", "demi_experiment_load",
-    "demi_load_model", "demi_actor_index", "demi_actor_name",
+    "demi_load_model", "demi_actor_index", "demi_actor_name", "demi_set_user_filter",
 ]
+FILTER_RULE_DTYPE = np.dtype([("src_mask", "<u4"), ("dst_mask", "<u4"), ("type_mask", "<u4"), ("flags", "<u4")])
+FRULE_DEADLETTERS = 1
 MODEL_IR = 100
 
 
@@ -221,6 +223,8 @@ def lib():
     L.demi_comm_rank.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.demi_create_multi.restype = C.c_int32
     L.demi_create_multi.argtypes = [C.POINTER(Config), vp, C.c_int32, vp]
+    L.demi_set_user_filter.restype = C.c_int32
+    L.demi_set_user_filter.argtypes = [vp, vp, C.c_uint32]
     L.demi_load_model.restype = C.c_int32
     L.demi_load_model.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.demi_actor_index.restype = C.c_int32

@@ -203,7 +203,7 @@ extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, 
   uint32_t sends = 0;
   for (uint32_t i = 0; i < n; i++) {
     const demi_ext_event& e = ev[i];
-    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION)
+    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_HARD_KILL)
       return fail(h, DEMI_ERR_INVALID, "demi_set_externals: event %u has unknown kind %u", i, e.kind);
     bool needs_a = e.kind != DEMI_EXT_WAIT_QUIESCENCE;
     bool needs_b = e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION;
@@ -225,10 +225,11 @@ extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, 
   // lane-engine side tables: the Send events in order; whether two Sends are
   // identical (they would share a DepTracker Unique under the root)
   std::vector<uint4> sv;
-  h->has_partitions = false; h->ext_sends_distinct = true;
+  h->has_partitions = false; h->ext_sends_distinct = true; h->has_hard_kill = false;
   for (uint32_t i = 0; i < n; i++) {
     const demi_ext_event& e = ev[i];
     if (e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION) h->has_partitions = true;
+    if (e.kind == DEMI_EXT_HARD_KILL) h->has_hard_kill = true;
     if (e.kind != DEMI_EXT_SEND) continue;
     uint4 m = make_uint4(DEMI_DEADLETTERS | ((uint32_t)e.a << 8) | ((uint32_t)e.type << 16) |
                          ((uint32_t)DEMI_MF_EXTERNAL << 24), e.p0, e.p1, 0u);
@@ -243,13 +244,21 @@ extern "C" int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, 
   return DEMI_OK;
 }
 
+extern "C" int32_t demi_set_user_filter(demi_handle* h, const demi_filter_rule* rules, uint32_t n) {
+  if (!h) return DEMI_ERR_INVALID;
+  if (n > DEMI_MAX_FILTER_RULES || (!rules && n)) return fail(h, DEMI_ERR_INVALID, "demi_set_user_filter: at most %d rules", DEMI_MAX_FILTER_RULES);
+  h->filter.assign(rules, rules + n);
+  return DEMI_OK;
+}
+
 static const LaneVariant* pick_lane_variant(const demi_handle* h) {
   static const std::vector<LaneVariant> v = {
     make_lane_variant<Raft5, 256, 96>(),
     make_lane_variant<PingPong3, 256, 128>(),
     make_lane_variant<Bcast32, 128, 8192>(),
   };
-  if (!h->use_lane_engine || h->cfg.blocked_mask || !h->ext_sends_distinct || h->cfg.strategy != DEMI_RS_FULLY_RANDOM) return nullptr;
+  if (!h->use_lane_engine || h->cfg.blocked_mask || !h->ext_sends_distinct || h->cfg.strategy != DEMI_RS_FULLY_RANDOM ||
+      h->has_hard_kill || !h->filter.empty()) return nullptr;          // actor termination and user filters: the general engine
   for (const LaneVariant& lv : v) if (lv.model == h->cfg.model) return &lv;
   return nullptr;
 }
@@ -309,6 +318,10 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
                      total_warps * (uint64_t)(v->pcap / 2 + 3 * FIFO_PAIRS) * sizeof(uint16_t))) != DEMI_OK) return rc;
     a.fifo_scratch = h->fifo_scratch;
   }
+  if (fifo && (h->has_hard_kill || !h->filter.empty()))
+    return fail(h, DEMI_ERR_INVALID, "HardKill and userDefinedFilter are offered for FullyRandom only");
+  a.n_filter = (uint32_t)h->filter.size();
+  for (uint32_t i = 0; i < a.n_filter; i++) a.filter[i] = make_uint4(h->filter[i].src_mask, h->filter[i].dst_mask, h->filter[i].type_mask, h->filter[i].flags);
   a.ext = h->ext_dev;
   a.n_ext = (uint32_t)h->ext_host.size();
   a.node_cap = node_cap;

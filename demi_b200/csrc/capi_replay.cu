@@ -46,7 +46,7 @@ extern "C" int32_t demi_set_trace(demi_handle* h, const demi_event* events, uint
   if (n_externals > 4096) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: more than 4096 external events");
   if (n_events >= (1u << 31)) return fail(h, DEMI_ERR_INVALID, "demi_set_trace: trace too long");
   { int32_t vrc = demi_check_events(h, "demi_set_trace", events, n_events, 0); if (vrc != DEMI_OK) return vrc;
-    vrc = demi_check_externals(h, "demi_set_trace", externals, n_externals); if (vrc != DEMI_OK) return vrc; }
+    vrc = demi_check_externals(h, "demi_set_trace", externals, n_externals); if (vrc != DEMI_OK) return vrc; }   // (rejects HardKill)
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   { int32_t mrc = demi_need_model(h); if (mrc != DEMI_OK) return mrc; }
   const uint32_t ext_mask = demi_ext_type_mask(h);

@@ -71,6 +71,9 @@ struct demi_handle {
   demi_ir_device ir_dev{};
   uint32_t ir_ext_mask = 0, ir_fanout = 0, ir_n_actors = 0, ir_n_types = 0;
   std::vector<std::string> names;      // actor names, then message-type names
+  // ---- FullyRandom's userDefinedFilter as rules (demi_set_user_filter); HardKill in the external program
+  std::vector<demi_filter_rule> filter;
+  bool has_hard_kill = false;
 };
 void demi_replay_free(demi_handle* h);
 void demi_comm_free(demi_handle* h);
@@ -106,7 +109,8 @@ inline int32_t demi_check_externals(demi_handle* h, const char* who, const demi_
   const uint32_t na = (uint32_t)demi_model_actors(h);
   for (uint32_t i = 0; i < n; i++) {
     const demi_ext_event& e = ev[i];
-    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION) return fail(h, DEMI_ERR_INVALID, "%s: external %u has unknown kind %u", who, i, (unsigned)e.kind);
+    if (e.kind < DEMI_EXT_START || e.kind > DEMI_EXT_UNPARTITION)      // HardKill: RandomScheduler fuzzing only
+      return fail(h, DEMI_ERR_INVALID, "%s: external %u has kind %u, which this entry point does not accept", who, i, (unsigned)e.kind);
     const bool needs_a = e.kind != DEMI_EXT_WAIT_QUIESCENCE;
     const bool needs_b = e.kind == DEMI_EXT_PARTITION || e.kind == DEMI_EXT_UNPARTITION;
     if ((needs_a && e.a >= na) || (needs_b && e.b >= na)) return fail(h, DEMI_ERR_INVALID, "%s: external %u names an unknown actor", who, i);

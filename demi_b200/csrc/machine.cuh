@@ -158,6 +158,8 @@ struct KernelArgs {
   uint4*    lane_pend;        // [total_warps][LPCAP][32] pending entries
   const uint4* ext_sends;     // the program's Send events as {hdr|EXTERNAL, p0, p1, 0}, in order
   uint32_t  has_partitions;   // program contains Partition/UnPartition events
+  // FullyRandom's userDefinedFilter as rules (demi_set_user_filter): {src_mask, dst_mask, type_mask, flags}
+  uint4     filter[DEMI_MAX_FILTER_RULES]; uint32_t n_filter;
 };
 
 // -----------------------------------------------------------------------------
@@ -194,6 +196,7 @@ struct Machine {
   uint32_t ext_idx;
   uint32_t violation, status;
   uint32_t inaccessible, killed;
+  uint32_t dead, blocked;     // hard-killed actors (receiverIsAlive false); Instrumenter.blockedActors of this execution
   uint64_t thash;
   // ---- SrcDstFIFO (RandomScheduler.scala:702-909); only in PEND_GLOBAL variants.  The lower half of the
   // pending array is timersAndExternals (:712), the upper half the entry pool of the per-pair FIFO lists
@@ -386,6 +389,7 @@ struct Machine {
     __syncwarp();
     for (uint32_t i = 0; i < n_tosend && !status; i++) {
       uint4 q = sm->tosend[i];
+      if ((dead >> hdr_dst(q.x)) & 1u) continue;     // "Dropping message to non-existent receiver" (ExternalEventInjector.scala:343-346)
       event_produced(q.x, q.y, q.z);
     }
     n_tosend = 0;
@@ -454,6 +458,49 @@ struct Machine {
     return (v && v == A->looking_for) ? A->looking_for : 0u;
   }
 
+  // EventOrchestrator.trigger_hard_kill (EventOrchestrator.scala:243-310) in the model world (include/demi_b200.h)
+  __device__ void hard_kill(uint32_t a) {
+    record_event(DEMI_EV_HARD_KILL, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
+    if (fifo_mode()) { status = DEMI_PS_QUEUE_OVF; return; }
+    // scheduler.actorTerminated(name) -> FullyRandom.removeAll (RandomScheduler.scala:686-696): every element of the
+    // array as it was when the loop started is visited once, in position order, and a match is swap-removed at its
+    // CURRENT index.  Pass 1 lists the Uniq ids of the matches in position order (in the free top of the array).
+    __syncwarp();
+    const uint32_t n0 = n_pending, TOP = (uint32_t)PCAP;
+    uint32_t r = 0;
+    for (uint32_t base = 0; base < n0; base += 32) {
+      const uint32_t i = base + lane;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      const bool hit = i < n0 && hdr_dst((q = pend_load(i)).x) == a;
+      const unsigned m = __ballot_sync(FULL_MASK, hit);
+      if (n0 + r + __popc(m) > TOP) { status = DEMI_PS_PENDING_OVF; return; }
+      __syncwarp();
+      if (hit) pend_store(TOP - 1 - (r + __popc(m & ((1u << lane) - 1u))), make_uint4(q.w & 0xFFFFu, 0, 0, 0));
+      r += __popc(m);
+      __syncwarp();
+    }
+    for (uint32_t k = 0; k < r; k++) {
+      const uint32_t u = pend_load(TOP - 1 - k).x;
+      int at = -1;
+      for (uint32_t base = 0; base < n_pending && at < 0; base += 32) {
+        const uint32_t i = base + lane;
+        const bool hit = i < n_pending && (pend_load(i).w & 0xFFFFu) == u;
+        const unsigned m = __ballot_sync(FULL_MASK, hit);
+        if (m) at = (int)(base + __ffs(m) - 1);
+      }
+      if (at >= 0) pending_remove_at((uint32_t)at);
+    }
+    blocked &= ~(1u << a);                                      // blockedActors - name :280
+    for (uint32_t i = 0; i < registry.n;) {                     // removeCancellable for its timers :281-287
+      uint32_t k, p0, p1; registry.get(i, k, p0, p1);
+      if ((k & 0xFFu) == a) registry.remove_at(lane, i); else i++;
+    }
+    killed |= 1u << a; inaccessible |= 1u << a; dead |= 1u << a;
+    // the stopped instance is gone: a later Start(name) is a fresh actor
+    for (uint32_t w = lane; w < (uint32_t)SW; w += 32) sm->states[a * SW + w] = MODEL::init_word(a * SW + w, A->model_flags);
+    __syncwarp();
+  }
+
   // EventOrchestrator.inject_until_quiescence (EventOrchestrator.scala:132-189)
   __device__ __forceinline__ void inject_until_quiescence() {
     bool loop = true;
@@ -463,8 +510,9 @@ struct Machine {
       switch (kind) {
         case DEMI_EXT_START:                 // trigger_start :219-231
           record_event(DEMI_EV_SPAWN, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
-          inaccessible &= ~(1u << a); killed &= ~(1u << a);
+          inaccessible &= ~(1u << a); killed &= ~(1u << a); dead &= ~(1u << a);
           break;
+        case DEMI_EXT_HARD_KILL: hard_kill(a); break;
         case DEMI_EXT_KILL:                  // trigger_kill :233-241
           record_event(DEMI_EV_KILL, DEMI_DEADLETTERS, a, 0, 0, 0, 0, 0, 0);
           killed |= 1u << a; inaccessible |= 1u << a;
@@ -493,53 +541,81 @@ struct Machine {
   // Util.find_non_blocked_message (schedulers/Util.scala:470-489) over
   // RandomizedHashSet.removeRandomElement (:171-176).  Rejected draws are
   // stashed at the top of the array and re-appended in draw order.
+  // entries [top - nb, top), written downward in draw order, go back behind the live entries in draw order
+  __device__ __forceinline__ void reappend_stash(uint32_t top, uint32_t nb) {
+    const uint32_t lo = top - nb;
+    for (uint32_t base = 0; base < nb / 2; base += 32) {          // reverse in place ...
+      uint32_t i = base + lane;
+      uint4 x = make_uint4(0, 0, 0, 0), y = x;
+      if (i < nb / 2) { x = pend_load(lo + i); y = pend_load(top - 1 - i); }
+      __syncwarp();
+      if (i < nb / 2) { pend_store(lo + i, y); pend_store(top - 1 - i, x); }
+      __syncwarp();
+    }
+    if (lo != n_pending) {                                         // ... then slide down
+      for (uint32_t base = 0; base < nb; base += 32) {
+        uint32_t i = base + lane;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (i < nb) x = pend_load(lo + i);
+        __syncwarp();
+        if (i < nb) pend_store(n_pending + i, x);
+        __syncwarp();
+      }
+    }
+    n_pending += nb;
+  }
+  // !userDefinedFilter(snd, rcv, msg), the filter given as rules (demi_set_user_filter)
+  __device__ __forceinline__ bool filter_rejects(uint32_t hdr) const {
+    const uint32_t src = hdr_src(hdr), dst = hdr_dst(hdr), type = hdr_type(hdr);
+    for (uint32_t i = 0; i < A->n_filter; i++) {
+      const uint4 r = A->filter[i];
+      const bool src_ok = src < DEMI_MAX_ACTORS ? ((r.x >> src) & 1u) : (r.w & DEMI_FRULE_DEADLETTERS);
+      if (src_ok && ((r.y >> dst) & 1u) && ((r.z >> (type & 31)) & 1u)) return true;
+    }
+    return false;
+  }
+  // FullyRandom.removeRandomElement (RandomScheduler.scala:666-684), as written: redraw while the filter rejects and
+  // more than one element is left; the rejected draws go back after the loop.  [.., top) is free stash space.
+  __device__ __forceinline__ uint4 draw(uint32_t top) {
+    uint32_t idx = rng.next_int(n_pending);
+    uint4 e = pending_remove_at(idx);
+    if (!A->n_filter) return e;
+    uint32_t nr = 0;
+    while (n_pending > 1 && filter_rejects(e.x)) {
+      if (lane == 0) pend_store(top - 1 - nr, e);
+      nr++;
+      __syncwarp();
+      idx = rng.next_int(n_pending);
+      e = pending_remove_at(idx);
+    }
+    if (nr) reappend_stash(top, nr);
+    return e;
+  }
+  // Util.find_non_blocked_message (schedulers/Util.scala:470-489) over the strategy's removeRandomElement.
+  // Rejected draws are stashed at the top of the array and re-appended in draw order.
   __device__ __forceinline__ bool find_non_blocked(uint4& out) {
     if (n_pending == 0) return false;
     __syncwarp();
-    const uint32_t blocked_mask = A->blocked_mask;
+    const uint32_t blocked_mask = blocked;
     const uint32_t TOP = fifo_mode() ? HALF : (uint32_t)PCAP;      // the stash lives at the top of the array in use
     uint32_t nb = 0;
-    uint32_t idx = rng.next_int(n_pending);
-    uint4 e = pending_remove_at(idx);
+    uint4 e = draw(TOP);
     bool got = true;
     while ((blocked_mask >> (hdr_dst(e.x) & 31)) & 1u) {
       if (lane == 0) pend_store(TOP - 1 - nb, e);
       nb++;
       __syncwarp();
       if (n_pending == 0) { got = false; break; }
-      idx = rng.next_int(n_pending);
-      e = pending_remove_at(idx);
+      e = draw(TOP - nb);
     }
-    if (nb) {
-      // reverse the stash in place, then slide it down behind the live entries
-      uint32_t lo = TOP - nb;
-      for (uint32_t base = 0; base < nb / 2; base += 32) {
-        uint32_t i = base + lane;
-        uint4 x = make_uint4(0, 0, 0, 0), y = x;
-        if (i < nb / 2) { x = pend_load(lo + i); y = pend_load(TOP - 1 - i); }
-        __syncwarp();
-        if (i < nb / 2) { pend_store(lo + i, y); pend_store(TOP - 1 - i, x); }
-        __syncwarp();
-      }
-      if (lo != n_pending) {
-        for (uint32_t base = 0; base < nb; base += 32) {
-          uint32_t i = base + lane;
-          uint4 x = make_uint4(0, 0, 0, 0);
-          if (i < nb) x = pend_load(lo + i);
-          __syncwarp();
-          if (i < nb) pend_store(n_pending + i, x);
-          __syncwarp();
-        }
-      }
-      n_pending += nb;
-    }
+    if (nb) reappend_stash(TOP, nb);
     out = e;
     return got;
   }
 
   // SrcDstFIFO.getNonBlockedMessage (RandomScheduler.scala:716-756) + dequeue (:758-768)
   __device__ __forceinline__ bool fifo_get_non_blocked(uint4& out) {
-    const uint32_t blocked_mask = A->blocked_mask;
+    const uint32_t blocked_mask = blocked;
     bool any = false;
     __syncwarp();
     for (uint32_t base = 0; base < n_pairs && !any; base += 32) {
@@ -670,7 +746,7 @@ struct Machine {
     violation = status = 0;
     // populateActorSystem: every actor starts isolated (ExternalEventInjector.scala:371-378)
     inaccessible = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
-    killed = 0; thash = 0;
+    killed = 0; thash = 0; dead = 0; blocked = A->blocked_mask;
     just.clear(); resend.clear(); registry.clear(); cancelled.clear();
     part_row = 0; delivered_bits = 0;
     r_hdr = r_p0 = r_p1 = r_parent = 0;

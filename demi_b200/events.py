@@ -49,6 +49,14 @@ class Kill(ExternalEvent):
         ExternalEvent.__init__(self, a=name, **kw)
 
 
+class HardKill(ExternalEvent):
+    """HardKill(name) (ExternalEvents.scala:69-71): the actor is stopped, not just isolated."""
+    kind = N.EXT_HARD_KILL
+
+    def __init__(self, name, **kw):
+        ExternalEvent.__init__(self, a=name, **kw)
+
+
 class Send(ExternalEvent):
     kind = N.EXT_SEND
 
@@ -86,7 +94,7 @@ def pack_externals(events):
 
 
 def unpack_externals(arr):
-    cls = {N.EXT_START: Start, N.EXT_KILL: Kill, N.EXT_SEND: Send, N.EXT_WAIT_QUIESCENCE: WaitQuiescence,
+    cls = {N.EXT_HARD_KILL: HardKill, N.EXT_START: Start, N.EXT_KILL: Kill, N.EXT_SEND: Send, N.EXT_WAIT_QUIESCENCE: WaitQuiescence,
            N.EXT_PARTITION: Partition, N.EXT_UNPARTITION: UnPartition}
     out = []
     for r in arr:

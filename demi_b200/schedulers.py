@@ -72,6 +72,11 @@ class Engine(object):
         v = N.lib().demi_actor_name(self._h, index)
         return v.decode() if v is not None else None
 
+    def set_user_filter(self, rules):
+        """FullyRandom(userDefinedFilter): rules = [(src_mask, dst_mask, type_mask, flags)], a match REJECTS the draw."""
+        arr = np.array(list(rules), dtype=N.FILTER_RULE_DTYPE) if len(rules) else np.zeros(0, dtype=N.FILTER_RULE_DTYPE)
+        self._check(N.lib().demi_set_user_filter(self._h, arr.ctypes.data if len(arr) else None, len(arr)))
+
     def set_externals(self, events):
         arr = events if isinstance(events, np.ndarray) else pack_externals(events)
         arr = np.ascontiguousarray(arr, dtype=N.EXT_DTYPE)

@@ -75,7 +75,15 @@ enum {
   DEMI_EXT_SEND = 3,             /* Send(name, msg)        a = dst, type/p0/p1*/
   DEMI_EXT_WAIT_QUIESCENCE = 4,  /* WaitQuiescence()                          */
   DEMI_EXT_PARTITION = 5,        /* Partition(a,b)                            */
-  DEMI_EXT_UNPARTITION = 6       /* UnPartition(a,b)                          */
+  DEMI_EXT_UNPARTITION = 6,      /* UnPartition(a,b)                          */
+  DEMI_EXT_HARD_KILL = 7         /* HardKill(name): the actor is stopped for good (EventOrchestrator.scala:243-310).
+                                    Model semantics: the scheduler drops every pending message addressed to it
+                                    (Scheduler.actorTerminated -> FullyRandom.removeAll, RandomScheduler.scala:536-547,
+                                    :686-696), its timers are unregistered (:281-287), it stops being blocked, queued
+                                    timers / externals for it are dropped when flushed (ExternalEventInjector.scala:343-346),
+                                    it is isolated like a killed actor, and a later Start(name) brings up a fresh instance.
+                                    RandomScheduler fuzzing only (the warp engine); replay and DPOR reject it as the
+                                    reference's DPOR does ("unsuported external event", DPORwHeuristics.scala:710). */
 };
 typedef struct demi_ext_event {
   uint8_t  kind, a, b, type;
@@ -93,7 +101,8 @@ enum {
   DEMI_EV_PARTITION = 5,         /* PartitionEvent                             */
   DEMI_EV_UNPARTITION = 6,       /* UnPartitionEvent                           */
   DEMI_EV_BEGIN_WAIT_QUIESCENCE = 7,
-  DEMI_EV_QUIESCENCE = 8
+  DEMI_EV_QUIESCENCE = 8,
+  DEMI_EV_HARD_KILL = 9          /* `events += hardKill` (EventOrchestrator.scala:244)                          */
 };
 typedef struct demi_event {
   uint8_t  kind, src, dst, type;
@@ -192,6 +201,17 @@ const char* demi_actor_name(const demi_handle* h, uint32_t index);        /* NUL
 /* The external-event program == the `_trace: Seq[ExternalEvent]` argument of
  * RandomScheduler.explore (RandomScheduler.scala:234) / TestOracle.test. */
 int32_t demi_set_externals(demi_handle* h, const demi_ext_event* ev, uint32_t n);
+
+/* FullyRandom(userDefinedFilter = ...) (RandomScheduler.scala:633-684): "userDefinedFilter can throw out entries to
+ * be delivered, by returning false".  The closure (src, dst, msg) => Boolean becomes data: a message is REJECTED when
+ * it matches any rule (sender in src_mask — or any deadLetters/timer sender when DEMI_FR_DEADLETTERS is set —, receiver
+ * in dst_mask, type in type_mask).  As written, a rejected draw is put back after the loop and the loop stops when one
+ * element is left (`pendingEvents.size > 1`), so the last remaining message is delivered even if the filter rejects it.
+ * n == 0 restores the default filter.  FullyRandom only; at most DEMI_MAX_FILTER_RULES rules. */
+typedef struct demi_filter_rule { uint32_t src_mask, dst_mask, type_mask, flags; } demi_filter_rule;
+#define DEMI_FRULE_DEADLETTERS 0x1u
+#define DEMI_MAX_FILTER_RULES 8
+int32_t demi_set_user_filter(demi_handle* h, const demi_filter_rule* rules, uint32_t n);
 
 /* ------------------------------------------------------------- random fuzz */
 /* RunnerUtils.fuzz inner loop (RunnerUtils.scala:75-91): n_prefixes independent

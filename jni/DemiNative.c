@@ -120,3 +120,69 @@ JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dedupCompact(J
                             (demi_fuzz_result*)BUF(env, outRecords), outIndex ? (uint32_t*)BUF(env, outIndex) : 0,
                             (uint64_t*)BUF(env, outCount));
 }
+
+/* ---- round 2: loaded models, frontier DPOR on one or several GPUs, conjoined atoms, fuzzer, experiment directory */
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_loadModel(JNIEnv* env, jclass c, jlong h, jobject blob, jint size) {
+  return demi_load_model(H(h), BUF(env, blob), (size_t)size);
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_actorIndex(JNIEnv* env, jclass c, jlong h, jstring name) {
+  const char* s = (*env)->GetStringUTFChars(env, name, 0);
+  jint r = demi_actor_index(H(h), s);
+  (*env)->ReleaseStringUTFChars(env, name, s);
+  return r;
+}
+JNIEXPORT jstring JNICALL Java_akka_dispatch_verification_DemiNative_actorName(JNIEnv* env, jclass c, jlong h, jint index) {
+  const char* s = demi_actor_name(H(h), (uint32_t)index);
+  return s ? (*env)->NewStringUTF(env, s) : 0;
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_conjoinAtoms(JNIEnv* env, jclass c, jlong h, jint e1, jint e2) {
+  return demi_conjoin_atoms(H(h), (uint32_t)e1, (uint32_t)e2);
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dporFrontier(JNIEnv* env, jclass c, jlong h, jobject externals, jint n,
+    jobject params, jobject result, jobject viol, jint capViol, jobject hashes, jlong capHashes) {
+  return demi_dpor_frontier(H(h), (const demi_ext_event*)BUF(env, externals), (uint32_t)n, (const demi_frontier_params*)BUF(env, params),
+                            (demi_frontier_result*)BUF(env, result), viol ? (demi_dpor_violation*)BUF(env, viol) : 0, (uint32_t)capViol,
+                            hashes ? (uint64_t*)BUF(env, hashes) : 0, (uint64_t)capHashes);
+}
+/* one JVM process drives all the GPUs of the box: handles[] is a direct buffer of n jlongs */
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_createMulti(JNIEnv* env, jclass c, jobject cfg, jobject devices, jint n,
+    jobject handles) {
+  return demi_create_multi((const demi_config*)BUF(env, cfg), (const int32_t*)BUF(env, devices), n, (demi_handle**)BUF(env, handles));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_dporFrontierMulti(JNIEnv* env, jclass c, jobject handles, jint n,
+    jobject externals, jint nExt, jobject params, jobject results, jobject viol, jint capViol, jobject hashes, jlong capHashes) {
+  return demi_dpor_frontier_multi((demi_handle**)BUF(env, handles), n, (const demi_ext_event*)BUF(env, externals), (uint32_t)nExt,
+                                  (const demi_frontier_params*)BUF(env, params), (demi_frontier_result*)BUF(env, results),
+                                  viol ? (demi_dpor_violation*)BUF(env, viol) : 0, (uint32_t)capViol,
+                                  hashes ? (uint64_t*)BUF(env, hashes) : 0, (uint64_t)capHashes);
+}
+/* one process per GPU (e.g. one JVM per device): rank 0 makes the id, the host ships its 128 bytes, every rank joins */
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_commUniqueId(JNIEnv* env, jclass c, jobject id128) {
+  return demi_comm_unique_id((uint8_t*)BUF(env, id128));
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_commInit(JNIEnv* env, jclass c, jlong h, jobject id128, jint rank, jint world) {
+  return demi_comm_init(H(h), (const uint8_t*)BUF(env, id128), rank, world);
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_fuzzerGenerate(JNIEnv* env, jclass c, jobject cfg, jlong seed,
+    jobject prefix, jint nPrefix, jobject postfix, jint nPostfix, jobject out, jint cap, jobject nOut /* u32 */) {
+  return demi_fuzzer_generate((const demi_fuzzer_config*)BUF(env, cfg), (int64_t)seed, (const demi_ext_event*)BUF(env, prefix), (uint32_t)nPrefix,
+                              postfix ? (const demi_ext_event*)BUF(env, postfix) : 0, (uint32_t)nPostfix, (demi_ext_event*)BUF(env, out),
+                              (uint32_t)cap, (uint32_t*)BUF(env, nOut));
+}
+/* `exp` = a direct buffer laid out as demi_experiment whose pointer fields the Scala side fills with
+ * GetDirectBufferAddress-style addresses (DemiNative.addressOf) */
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_experimentSave(JNIEnv* env, jclass c, jstring dir, jobject exp) {
+  const char* s = (*env)->GetStringUTFChars(env, dir, 0);
+  jint r = demi_experiment_save(s, (const demi_experiment*)BUF(env, exp));
+  (*env)->ReleaseStringUTFChars(env, dir, s);
+  return r;
+}
+JNIEXPORT jint JNICALL Java_akka_dispatch_verification_DemiNative_experimentLoad(JNIEnv* env, jclass c, jstring dir, jobject exp) {
+  const char* s = (*env)->GetStringUTFChars(env, dir, 0);
+  jint r = demi_experiment_load(s, (demi_experiment*)BUF(env, exp));
+  (*env)->ReleaseStringUTFChars(env, dir, s);
+  return r;
+}
+JNIEXPORT jlong JNICALL Java_akka_dispatch_verification_DemiNative_addressOf(JNIEnv* env, jclass c, jobject buf) {
+  return (jlong)(intptr_t)BUF(env, buf);
+}

@@ -43,6 +43,30 @@ object DemiNative {
                            outCount: ByteBuffer): Int
 
   def direct(n: Int): ByteBuffer = ByteBuffer.allocateDirect(n).order(ByteOrder.LITTLE_ENDIAN)
+  // ---- round 2
+  /** demi_load_model: the data-only model of the application (include/demi_model_ir.h); `h` was created with model = 100. */
+  @native def loadModel(h: Long, blob: ByteBuffer, size: Int): Int
+  @native def actorIndex(h: Long, name: String): Int
+  @native def actorName(h: Long, index: Int): String
+  /** UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178) on the dag demi_ddmin minimizes. */
+  @native def conjoinAtoms(h: Long, e1: Int, e2: Int): Int
+  /** One DPORwHeuristics.test explored as a frontier of backtrack points (demi_frontier_params / demi_frontier_result). */
+  @native def dporFrontier(h: Long, externals: ByteBuffer, n: Int, params: ByteBuffer, result: ByteBuffer,
+                           viol: ByteBuffer, capViol: Int, hashes: ByteBuffer, capHashes: Long): Int
+  /** All GPUs of the box from this JVM: n handles (jlongs in `handles`), NCCL wired up inside the library. */
+  @native def createMulti(cfg: ByteBuffer, devices: ByteBuffer, n: Int, handles: ByteBuffer): Int
+  @native def dporFrontierMulti(handles: ByteBuffer, n: Int, externals: ByteBuffer, nExt: Int, params: ByteBuffer,
+                                results: ByteBuffer, viol: ByteBuffer, capViol: Int, hashes: ByteBuffer, capHashes: Long): Int
+  @native def commUniqueId(id128: ByteBuffer): Int
+  @native def commInit(h: Long, id128: ByteBuffer, rank: Int, world: Int): Int
+  /** Fuzzer.generateFuzzTest, seeded (fuzzing/Fuzzer.scala:123-174). */
+  @native def fuzzerGenerate(cfg: ByteBuffer, seed: Long, prefix: ByteBuffer, nPrefix: Int, postfix: ByteBuffer, nPostfix: Int,
+                             out: ByteBuffer, cap: Int, nOut: ByteBuffer): Int
+  /** The flat experiment directory that replaces ExperimentSerializer's *.bin object streams (Serialization.scala:57-74). */
+  @native def experimentSave(dir: String, exp: ByteBuffer): Int
+  @native def experimentLoad(dir: String, exp: ByteBuffer): Int
+  @native def addressOf(buf: ByteBuffer): Long
+
 }
 
 /** Flat encoding of the model-level vocabulary: an application registers, once,

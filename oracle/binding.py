@@ -111,6 +111,15 @@ def _pow2_at_least(x, lo, hi):
     return c
 
 
+FILTER_RULE_DTYPE = np.dtype([("src_mask", "<u4"), ("dst_mask", "<u4"), ("type_mask", "<u4"), ("flags", "<u4")])
+
+
+def set_user_filter(rules):
+    """FullyRandom(userDefinedFilter) as rules for the following calls on this thread; [] clears."""
+    arr = np.array(list(rules), dtype=FILTER_RULE_DTYPE) if len(rules) else np.zeros(0, dtype=FILTER_RULE_DTYPE)
+    lib().oracle_set_user_filter(C.c_void_p(arr.ctypes.data) if len(arr) else None, C.c_uint32(len(arr)))
+
+
 def load_model(blob):
     """oracle_load_model: the CPU interpreter's copy of a demi_load_model blob (model id 100)."""
     rc = lib().oracle_load_model(bytes(blob), C.c_size_t(len(blob)))

@@ -91,9 +91,35 @@ static om_pending pending_remove_at(om_machine* m, uint32_t i) {
 /* RandomizedHashSet.removeRandomElement (schedulers/Util.scala:171-176);
  * FullyRandom.removeRandomElement with the default (always-true) filter
  * (RandomScheduler.scala:666-684) reduces to exactly one draw. */
+static demi_filter_rule g_filter[DEMI_MAX_FILTER_RULES];      /* process-wide: the batch driver's worker threads read it */
+static uint32_t g_n_filter = 0;
+void oracle_set_user_filter(const demi_filter_rule* rules, uint32_t n) {
+  g_n_filter = n > DEMI_MAX_FILTER_RULES ? DEMI_MAX_FILTER_RULES : n;
+  for (uint32_t i = 0; i < g_n_filter; i++) g_filter[i] = rules[i];
+}
+/* !userDefinedFilter(snd, rcv, msg) */
+static int filter_rejects(const demi_msg* c) {
+  for (uint32_t i = 0; i < g_n_filter; i++) {
+    const demi_filter_rule* r = &g_filter[i];
+    int src_ok = c->src < DEMI_MAX_ACTORS ? (int)((r->src_mask >> c->src) & 1u) : (int)(r->flags & DEMI_FRULE_DEADLETTERS);
+    if (src_ok && ((r->dst_mask >> c->dst) & 1u) && ((r->type_mask >> (c->type & 31)) & 1u)) return 1;
+  }
+  return 0;
+}
+/* FullyRandom.removeRandomElement (RandomScheduler.scala:666-684), as written: redraw while the filter rejects and
+ * more than one element is left; the rejected draws go back (appended, in draw order) after the loop */
 om_pending om_pending_remove_random(om_machine* m) {
   int32_t idx = jr_next_int_bound(&m->rng, (int32_t)m->n_pending);
-  return pending_remove_at(m, (uint32_t)idx);
+  om_pending ret = pending_remove_at(m, (uint32_t)idx);
+  if (!g_n_filter) return ret;
+  om_pending rejected[OM_MAX_PENDING]; uint32_t nr = 0;
+  while (m->n_pending > 1 && filter_rejects(&ret.msg)) {
+    rejected[nr++] = ret;
+    idx = jr_next_int_bound(&m->rng, (int32_t)m->n_pending);
+    ret = pending_remove_at(m, (uint32_t)idx);
+  }
+  for (uint32_t i = 0; i < nr; i++) m->pending[m->n_pending++] = rejected[i];
+  return ret;
 }
 /* Util.find_non_blocked_message (schedulers/Util.scala:470-489): draw until
  * the receiver is not blocked; rejected draws are re-appended in draw order. */
@@ -230,7 +256,10 @@ static void enqueue_timer(om_machine* m, int rcv, uint8_t type, uint32_t p0, uin
 /* ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365):
  * drain messagesToSend in queue order; each one reaches event_produced. */
 static void send_external_messages(om_machine* m) {
-  for (uint32_t i = 0; i < m->n_tosend && !m->status; i++) event_produced(m, &m->tosend[i]);
+  for (uint32_t i = 0; i < m->n_tosend && !m->status; i++) {
+    if ((m->dead >> m->tosend[i].dst) & 1u) continue;         /* "Dropping message to non-existent receiver" :343-346 */
+    event_produced(m, &m->tosend[i]);
+  }
   m->n_tosend = 0;
 }
 
@@ -316,7 +345,34 @@ static void inject_until_quiescence(om_machine* m) {
         record_event(m, DEMI_EV_SPAWN, DEMI_DEADLETTERS, e->a, 0, 0, 0, 0, 0, 0);
         m->inaccessible &= ~(1u << e->a);
         m->killed &= ~(1u << e->a);
+        m->dead &= ~(1u << e->a);
         break;
+      case DEMI_EXT_HARD_KILL: { /* trigger_hard_kill :243-310 */
+        record_event(m, DEMI_EV_HARD_KILL, DEMI_DEADLETTERS, e->a, 0, 0, 0, 0, 0, 0);
+        /* scheduler.actorTerminated(name) -> FullyRandom.removeAll (:686-696): every element of the array as it was
+         * when the loop started is visited once, in position order; a match is swap-removed at its CURRENT index */
+        if (m->strategy != DEMI_RS_FULLY_RANDOM) { m->status = DEMI_PS_QUEUE_OVF; break; }
+        {
+          om_pending snap[OM_MAX_PENDING]; uint32_t ns = m->n_pending;
+          memcpy(snap, m->pending, sizeof(om_pending) * ns);
+          for (uint32_t k = 0; k < ns; k++) {
+            if (snap[k].msg.dst != e->a) continue;
+            for (uint32_t j = 0; j < m->n_pending; j++)
+              if (m->pending[j].uniq == snap[k].uniq) { pending_remove_at(m, j); break; }
+          }
+        }
+        m->blocked_mask &= ~(1u << e->a);                       /* blockedActors - name :280 */
+        for (uint32_t k = 0; k < m->n_registry;)                /* removeCancellable for its timers :281-287 */
+          if (m->registry[k].dst == e->a) set_remove_at(m->registry, &m->n_registry, (int)k); else k++;
+        m->killed |= 1u << e->a; m->inaccessible |= 1u << e->a; m->dead |= 1u << e->a;
+        {                                                       /* the stopped instance is gone: a later Start is a fresh actor */
+          uint32_t fresh[DEMI_MAX_ACTORS * OM_MAX_STATE_WORDS];
+          memset(fresh, 0, sizeof(fresh));
+          m->model->init(fresh, m->model_flags);
+          memcpy(&m->states[e->a * m->model->state_words], &fresh[e->a * m->model->state_words], 4u * (uint32_t)m->model->state_words);
+        }
+        break;
+      }
       case DEMI_EXT_KILL:        /* trigger_kill :233-241 */
         record_event(m, DEMI_EV_KILL, DEMI_DEADLETTERS, e->a, 0, 0, 0, 0, 0, 0);
         m->killed |= 1u << e->a;
@@ -440,7 +496,7 @@ void oracle_run_prefix(const demi_config* cfg, const demi_ext_event* ext, uint32
   /* populateActorSystem: every actor is created and isolated until its Start
    * (ExternalEventInjector.scala:371-378) */
   m->inaccessible = model->n_actors >= 32 ? 0xFFFFFFFFu : ((1u << model->n_actors) - 1u);
-  m->killed = 0;
+  m->killed = 0; m->dead = 0;
   memset(m->partitioned, 0, sizeof(m->partitioned));
   m->n_pending = 0; m->max_pending = 0; m->n_tosend = 0;
   m->n_just = m->n_resend = m->n_registry = m->n_cancelled = 0;

@@ -65,6 +65,7 @@ struct om_machine {
   uint32_t states[DEMI_MAX_ACTORS * OM_MAX_STATE_WORDS];
   /* EventOrchestrator network state (EventOrchestrator.scala:51-59) */
   uint32_t inaccessible, killed;
+  uint32_t dead;                            /* hard-killed and not started again: Instrumenter.receiverIsAlive is false */
   uint32_t partitioned[DEMI_MAX_ACTORS];   /* ordered pairs: bit b of row a */
   /* RandomizedHashSet.arr (Util.scala:112) */
   om_pending pending[OM_MAX_PENDING];
@@ -111,6 +112,9 @@ void om_send(om_machine* m, int src, int dst, uint8_t type, uint32_t p0, uint32_
 void om_schedule_once(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1);
 void om_schedule_repeating(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1);
 void om_cancel_timer(om_machine* m, int self, uint8_t type, uint32_t p0, uint32_t p1);
+
+/* FullyRandom's userDefinedFilter as rules (include/demi_b200.h); thread-local test state, n = 0 clears */
+void oracle_set_user_filter(const demi_filter_rule* rules, uint32_t n);
 
 /* building blocks exposed for the known-answer tests */
 void     om_pending_insert(om_machine* m, const om_pending* e);

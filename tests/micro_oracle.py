@@ -113,7 +113,10 @@ class Execution(object):
     """One RandomScheduler.explore(trace) with max_executions = 1, FullyRandom(seed), checkpointing off."""
 
     def __init__(self, actors, externals, seed, max_messages, invariant_check_interval, invariant, external_filter,
-                 blocked=(), looking_for=None):
+                 blocked=(), looking_for=None, user_filter=None, fresh_actor=None):
+        self.userDefinedFilter = user_filter or (lambda snd, rcv, msg: True)      # FullyRandom ctor arg (:636)
+        self.fresh_actor = fresh_actor                                             # name -> new instance (HardKill + Start)
+        self.dead = set()
         self.actors = actors                     # name -> actor object with receive(ctx, sender, msg)
         self.externals = externals               # [("Start", name) | ("Kill", name) | ("Send", name, msg) | ("Partition", a, b) | ...]
         self.pendingEvents = RandomizedHashSet(seed)
@@ -155,11 +158,21 @@ class Execution(object):
             e = self.externals[self.traceIdx]
             if e[0] == "Start":
                 self.events.append(("Spawn", e[1]))
-                self.inaccessible.discard(e[1]); self.killed.discard(e[1])
+                self.inaccessible.discard(e[1]); self.killed.discard(e[1]); self.dead.discard(e[1])
                 self.blockedActors.discard(e[1])
             elif e[0] == "Kill":
                 self.events.append(("Kill", e[1]))
                 self.killed.add(e[1]); self.inaccessible.add(e[1])
+            elif e[0] == "HardKill":                                 # trigger_hard_kill (EventOrchestrator.scala:243-310)
+                self.events.append(("HardKill", e[1]))
+                for t in list(self.pendingEvents.arr):               # actorTerminated -> FullyRandom.removeAll (:686-696)
+                    if t[0][3] == e[1]:
+                        self.pendingEvents.remove(t)
+                self.blockedActors.discard(e[1])
+                for key in [k for k in self.timerToCancellable if k[0] == e[1]]:
+                    del self.timerToCancellable[key]
+                self.killed.add(e[1]); self.inaccessible.add(e[1]); self.dead.add(e[1])
+                self.actors[e[1]] = self.fresh_actor(e[1])
             elif e[0] == "Send":
                 self.enqueuedExternalMessages.append(e[2])           # enqueue_message :258-268
                 self.messagesToSend.append((None, e[1], e[2]))
@@ -236,6 +249,8 @@ class Execution(object):
     def send_external_messages(self):            # ExternalEventInjector :306-365
         queue, self.messagesToSend = self.messagesToSend, []
         for sender, rcv, msg in queue:
+            if rcv in self.dead:                                     # "Dropping message to non-existent receiver" (:343-346)
+                continue
             self.tell(DEADLETTERS if sender is None else sender, rcv, msg)
 
     def violationMatches(self, v):               # :138-154
@@ -260,14 +275,14 @@ class Execution(object):
         if self.pendingEvents.isEmpty():                             # find_non_blocked_message (Util.scala:470-489)
             return None
         blocked = []
-        e = self.pendingEvents.removeRandomElement()
+        e = self.strategy_removeRandomElement()
         while e[3] in self.blockedActors:
             blocked.append(e)
             if self.pendingEvents.isEmpty():
                 for b in blocked:
                     self.pendingEvents.insert(b)
                 return None
-            e = self.pendingEvents.removeRandomElement()
+            e = self.strategy_removeRandomElement()
         for b in blocked:
             self.pendingEvents.insert(b)
         uniq, unique, snd, rcv, msg = e
@@ -282,6 +297,16 @@ class Execution(object):
             self.timersToResend = []
             self.justScheduledTimers.clear()
         return e
+
+    def strategy_removeRandomElement(self):      # FullyRandom.removeRandomElement (:666-684), as written
+        ret = self.pendingEvents.removeRandomElement()
+        rejected = []
+        while len(self.pendingEvents.arr) > 1 and not self.userDefinedFilter(ret[2], ret[3], ret[4]):
+            rejected.append(ret)
+            ret = self.pendingEvents.removeRandomElement()
+        for r in rejected:
+            self.pendingEvents.insert(r)
+        return ret
 
     def dispatch_new_message(self, e):           # Instrumenter :913-1017
         _, _, snd, rcv, msg = e

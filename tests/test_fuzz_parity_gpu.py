@@ -172,3 +172,36 @@ def test_src_dst_fifo_strategy_matches_oracle(case, oracle):
             while q and q[0] != int(e["uniq"]):
                 q.pop(0)
             assert q and q.pop(0) == int(e["uniq"])
+
+
+def test_user_filter_and_hard_kill(oracle):
+    """FullyRandom(userDefinedFilter) — the redraw loop as written (RandomScheduler.scala:666-684) — and
+    HardKill -> Scheduler.actorTerminated -> FullyRandom.removeAll (:686-696, :536-547), on the general (warp) engine."""
+    rules = [(0b00110, 0b11111, 1 << 5, 0), (0, 0b00001, 1 << 3, N.FRULE_DEADLETTERS)]
+    hk = D.raft5_program(client_cmds=3)[:-1] + [D.WaitQuiescence(), D.HardKill(1), D.Send(1, 2, 40), D.Send(2, 2, 41), D.WaitQuiescence(),
+                                                D.Start(1), D.Send(1, 1, 0x1F), D.Kill(3), D.WaitQuiescence(), D.HardKill(0), D.WaitQuiescence()]
+    for prog, flt, maxm, interval, blocked in [(D.raft5_program(), rules, 50, 5, 0), (hk, [], 90, 7, 0), (hk, rules[:1], 90, 0, 0b00010),
+                                               (D.raft5_program(client_cmds=6), rules, 200, 20, 0b01000)]:
+        ext = D.pack_externals(prog)
+        eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1, blocked_mask=blocked))
+        eng.set_user_filter(flt)
+        eng.set_externals(ext)
+        n = 6000
+        gpu = eng.fuzz_batch(1, n, maxm, interval)
+        oracle.set_user_filter(flt)
+        try:
+            cpu = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, n, maxm, interval, model_flags=1, blocked_mask=blocked)
+            assert_same(gpu, cpu)
+            assert (gpu["status"] == 0).all()
+            for seed in (3, 77, 1234):
+                ev, par, r = eng.fuzz_trace(seed, maxm, interval)
+                cev, cpar, _ = oracle.fuzz_trace(N.MODEL_RAFT5, ext, seed, maxm, interval, model_flags=1, blocked_mask=blocked)
+                assert (ev == cev).all() and (par == cpar).all()
+        finally:
+            oracle.set_user_filter([])
+    # replay and DPOR refuse HardKill, like the reference's DPOR ("unsuported external event")
+    eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    with pytest.raises(D.DemiError):
+        eng.dpor_batch([hk[:-1]], 50, 10)
+    with pytest.raises(D.DemiError):
+        eng.dpor_frontier([e for e in hk if not isinstance(e, D.WaitQuiescence)], eng.frontier_params(50, 10, 4))

@@ -14,7 +14,7 @@ def to_prog(prog):
     out = []
     for e in prog:
         k = type(e).__name__
-        if k in ("Start", "Kill"):
+        if k in ("Start", "Kill", "HardKill"):
             out.append((k, str(e.a)))
         elif k == "Send":
             out.append(("Send", str(e.a), (e.type, e.p0, e.p1)))
@@ -39,6 +39,8 @@ def flat(events):
             rows.append((3, 0xFF, int(e[1]), 0, 0, 0, 0, 0))
         elif e[0] == "Kill":
             rows.append((4, 0xFF, int(e[1]), 0, 0, 0, 0, 0))
+        elif e[0] == "HardKill":
+            rows.append((9, 0xFF, int(e[1]), 0, 0, 0, 0, 0))
         elif e[0] == "Partition":
             rows.append((5, int(e[1]), int(e[2]), 0, 0, 0, 0, 0))
         elif e[0] == "UnPartition":
@@ -50,25 +52,43 @@ def flat(events):
     return rows
 
 
-def run_micro(model, prog, seed, maxm, interval, flags):
+def run_micro(model, prog, seed, maxm, interval, flags, rules=()):
     if model == N.MODEL_RAFT5:
-        actors = {str(i): M.RaftActor(i, flags) for i in range(5)}
+        fresh = lambda name: M.RaftActor(int(name), flags)
+        actors = {str(i): fresh(str(i)) for i in range(5)}
         inv = M.raft_invariant
     else:
-        actors = {str(i): M.PingPongActor(i) for i in range(3)}
+        fresh = lambda name: M.PingPongActor(int(name))
+        actors = {str(i): fresh(str(i)) for i in range(3)}
         inv = M.pingpong_invariant(flags)
     ext_types = (1, 2) if model == N.MODEL_RAFT5 else (1,)
-    ex = M.Execution(actors, to_prog(prog), seed, maxm, interval, inv, lambda m: m[0] in ext_types)
+
+    def user_filter(snd, rcv, msg):                                  # the closure the rules stand for
+        for src_mask, dst_mask, type_mask, fl in rules:
+            src_ok = ((src_mask >> int(snd)) & 1) if snd.isdigit() else (fl & 1)
+            if src_ok and (dst_mask >> int(rcv)) & 1 and (type_mask >> msg[0]) & 1:
+                return False
+        return True
+    ex = M.Execution(actors, to_prog(prog), seed, maxm, interval, inv, lambda m: m[0] in ext_types,
+                     user_filter=user_filter if rules else None, fresh_actor=fresh)
     v = ex.run()
     return ex, (v or 0)
 
 
-def compare(oracle, model, prog, seeds, maxm, interval, flags, full_trace_every=1):
+def compare(oracle, model, prog, seeds, maxm, interval, flags, full_trace_every=1, rules=()):
     ext = D.pack_externals(prog)
+    oracle.set_user_filter(rules)
+    try:
+        return _compare(oracle, model, prog, ext, seeds, maxm, interval, flags, full_trace_every, rules)
+    finally:
+        oracle.set_user_filter([])
+
+
+def _compare(oracle, model, prog, ext, seeds, maxm, interval, flags, full_trace_every, rules):
     res = oracle.fuzz_batch(model, ext, seeds[0], len(seeds), maxm, interval, model_flags=flags)
     n_viol = 0
     for k, seed in enumerate(seeds):
-        ex, v = run_micro(model, prog, seed, maxm, interval, flags)
+        ex, v = run_micro(model, prog, seed, maxm, interval, flags, rules)
         r = res[k]
         assert (int(r["violation"]), int(r["steps"]), int(r["n_nodes"]), int(r["n_events"]), int(r["max_pending"]), int(r["status"])) == \
                (v, ex.messagesScheduledSoFar, ex.depTracker.next_id, len(ex.events), ex.max_pending, 0), seed
@@ -97,6 +117,18 @@ def test_raft5_with_kills_partitions_and_client_commands(oracle):
                                                   D.UnPartition(0, 1), D.Start(2), D.Send(0, 2, 11), D.WaitQuiescence()]
     compare(oracle, N.MODEL_RAFT5, prog, list(range(1, 401)), 120, 7, 3, full_trace_every=4)
     compare(oracle, N.MODEL_RAFT5, prog, list(range(1000, 1200)), -1 if False else 300, 0, 2, full_trace_every=4)
+
+
+def test_user_filter_and_hard_kill(oracle):
+    """FullyRandom(userDefinedFilter) as written (redraw while more than one element is left, rejected draws go back
+    after the loop) and HardKill -> actorTerminated -> removeAll + a fresh instance on the next Start."""
+    rules = [(0b00110, 0b11111, 1 << 5, 0),                          # VoteReplies from nodes 1, 2 are held back ...
+             (0, 0b00001, 1 << 3, 1)]                                # ... and node 0's election tick (a timer: deadLetters)
+    compare(oracle, N.MODEL_RAFT5, D.raft5_program(), list(range(1, 801)), 50, 5, 1, full_trace_every=4, rules=rules)
+    prog = D.raft5_program(client_cmds=3)[:-1] + [D.WaitQuiescence(), D.HardKill(1), D.Send(1, 2, 40), D.Send(2, 2, 41), D.WaitQuiescence(),
+                                                  D.Start(1), D.Send(1, 1, 0x1F), D.Kill(3), D.WaitQuiescence(), D.HardKill(0), D.WaitQuiescence()]
+    compare(oracle, N.MODEL_RAFT5, prog, list(range(1, 601)), 90, 7, 1, full_trace_every=3)
+    compare(oracle, N.MODEL_RAFT5, prog, list(range(1, 301)), 90, 0, 3, full_trace_every=3, rules=rules[:1])
 
 
 def test_pingpong3_config0(oracle):
