@@ -47,6 +47,7 @@ def test_binding_layouts_match_the_header(native, tmp_path):
         "demi_frontier_params": C.sizeof(native.FrontierParams), "demi_frontier_result": native.FRONTIER_RESULT_DTYPE.itemsize,
         "demi_frontier_entry": native.FRONTIER_ENTRY_DTYPE.itemsize,
         "demi_fuzzer_config": C.sizeof(native.FuzzerConfig), "demi_experiment": C.sizeof(native.Experiment),
+        "demi_filter_rule": native.FILTER_RULE_DTYPE.itemsize,
     }
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "demi_b200.h"\nint main(void) {\n' +
