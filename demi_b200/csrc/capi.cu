@@ -113,7 +113,7 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (getenv("DEMI_DISABLE_LANE_ENGINE")) h->use_lane_engine = 0;
   if (e != cudaSuccess) {
     fail(nullptr, DEMI_ERR_CUDA, "demi_create: %s", cudaGetErrorString(e));
-    delete h;
+    demi_destroy(h);                       // frees whatever was created before the failure
     return DEMI_ERR_CUDA;
   }
   *out = h;
@@ -130,7 +130,7 @@ extern "C" void demi_destroy(demi_handle* h) {
   demi_replay_free(h);
   demi_frontier_free(h);
   demi_comm_free(h);
-  cudaFree(h->ir_blob_dev);
+  cudaFree(h->ir_blob_dev); cudaFree(h->trace_rec);
   cudaFree(h->dedup.keys); cudaFree(h->dedup.vals); cudaFree(h->dedup.keep); cudaFree(h->dedup.counts);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -285,9 +285,16 @@ static int32_t plan_launch(demi_handle* h, const demi_fuzz_params* p, bool recor
   const Variant* v = pick_variant(h->cfg.model, pcap, tcap, record, fifo);
   if (!v) return fail(h, DEMI_ERR_CAPACITY, "no kernel variant for pending_cap=%u tosend_cap=%u", pcap, tcap);
   const size_t smem = v->smem_per_warp * WARPS;
-  CUDA_TRY(h, cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the attribute and the occupancy of a variant are fixed per device: asked once, not on every launch
   int blocks_per_sm = 0;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, v->fn, WARPS * 32, smem));
+  {
+    auto it = h->occupancy.find((const void*)v->fn);
+    if (it == h->occupancy.end()) {
+      CUDA_TRY(h, cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, v->fn, WARPS * 32, smem));
+      h->occupancy[(const void*)v->fn] = blocks_per_sm;
+    } else blocks_per_sm = it->second;
+  }
   if (blocks_per_sm < 1) return fail(h, DEMI_ERR_CAPACITY, "kernel variant does not fit on an SM (smem %zu)", smem);
   uint64_t want = (p->n_prefixes + WARPS - 1) / WARPS;
   uint64_t full = (uint64_t)h->sm_count * (uint64_t)blocks_per_sm;
@@ -360,9 +367,15 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
   if (lv) {
     // K1-lane handles every prefix it can prove exact; the rest are deferred to the warp engine
     const size_t lsmem = lv->smem_per_block;
-    CUDA_TRY(h, cudaFuncSetAttribute(lv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
     int bps = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lv->fn, lv->bd, lsmem));
+    {
+      auto it = h->occupancy.find((const void*)lv->fn);
+      if (it == h->occupancy.end()) {
+        CUDA_TRY(h, cudaFuncSetAttribute(lv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lv->fn, lv->bd, lsmem));
+        h->occupancy[(const void*)lv->fn] = bps;
+      } else bps = it->second;
+    }
     if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "lane kernel does not fit on an SM");
     uint64_t want = (p->n_prefixes + lv->bd - 1) / lv->bd;
     int lgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * bps));
@@ -414,12 +427,15 @@ extern "C" int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p, de
     rc = launch_fuzz(h, &q, h->results_dev + off, h->stream, c == 0);
     if (rc != DEMI_OK) break;
     cudaEvent_t ev;
-    CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    evs.push_back(ev);
-    CUDA_TRY(h, cudaEventRecord(ev, h->stream));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
-    CUDA_TRY(h, cudaMemcpyAsync(out_host + off, h->results_dev + off, q.n_prefixes * sizeof(demi_fuzz_result),
-                                cudaMemcpyDeviceToHost, h->copy_stream));
+    cudaError_t ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) {
+      evs.push_back(ev);
+      ce = cudaEventRecord(ev, h->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->copy_stream, ev, 0);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(out_host + off, h->results_dev + off, q.n_prefixes * sizeof(demi_fuzz_result),
+                                                  cudaMemcpyDeviceToHost, h->copy_stream);
+    }
+    if (ce != cudaSuccess) { rc = fail(h, DEMI_ERR_CUDA, "demi_fuzz_batch: %s", cudaGetErrorString(ce)); break; }   // events freed below
   }
   cudaError_t e = cudaEventRecord(h->ev1, h->stream);
   unsigned long long cnt[2] = {0, 0};
@@ -467,11 +483,13 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
   LaunchPlan plan;
   int32_t rc = plan_launch(h, &q, true, &plan);
   if (rc != DEMI_OK) return rc;
-  demi_event* ev_dev = nullptr; uint16_t* par_dev = nullptr; demi_fuzz_result* res_dev = nullptr;
   const uint32_t cap_ev = std::max<uint32_t>(cap_events, 1), cap_n = std::max<uint32_t>(cap_nodes, 1);
-  CUDA_TRY(h, cudaMalloc(&ev_dev, (size_t)cap_ev * sizeof(demi_event)));
-  CUDA_TRY(h, cudaMalloc(&par_dev, (size_t)cap_n * sizeof(uint16_t)));
-  CUDA_TRY(h, cudaMalloc(&res_dev, sizeof(demi_fuzz_result)));
+  // one recording buffer, kept in the handle: events | parents | result
+  const size_t o_par = (size_t)cap_ev * sizeof(demi_event), o_res = (o_par + (size_t)cap_n * 2 + 15) & ~(size_t)15;
+  if ((rc = ensure(h, &h->trace_rec, &h->trace_rec_bytes, o_res + sizeof(demi_fuzz_result))) != DEMI_OK) return rc;
+  demi_event* ev_dev = (demi_event*)h->trace_rec;
+  uint16_t* par_dev = (uint16_t*)((unsigned char*)h->trace_rec + o_par);
+  demi_fuzz_result* res_dev = (demi_fuzz_result*)((unsigned char*)h->trace_rec + o_res);
   plan.args.results = res_dev;
   plan.args.rec_events = ev_dev; plan.args.rec_cap = cap_events;
   plan.args.rec_counts = h->rec_counts_dev;
@@ -489,7 +507,6 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
     if (e == cudaSuccess && dep_parent)
       e = cudaMemcpy(dep_parent, par_dev, (size_t)std::min(counts[1], cap_nodes) * sizeof(uint16_t), cudaMemcpyDeviceToHost);
   }
-  cudaFree(ev_dev); cudaFree(par_dev); cudaFree(res_dev);
   if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_fuzz_trace: %s", cudaGetErrorString(e));
   if (n_events) *n_events = counts[0];
   if (n_nodes) *n_nodes = counts[1];

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "../../include/demi_b200.h"
@@ -74,6 +75,9 @@ struct demi_handle {
   // ---- FullyRandom's userDefinedFilter as rules (demi_set_user_filter); HardKill in the external program
   std::vector<demi_filter_rule> filter;
   bool has_hard_kill = false;
+  // ---- launch bookkeeping
+  std::map<const void*, int> occupancy;          // kernel -> resident blocks per SM (asked once per handle)
+  void* trace_rec = nullptr; size_t trace_rec_bytes = 0;   // demi_fuzz_trace's recording buffer
 };
 void demi_replay_free(demi_handle* h);
 void demi_comm_free(demi_handle* h);

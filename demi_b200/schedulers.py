@@ -87,6 +87,8 @@ class Engine(object):
         p = N.FuzzParams(seed_base, n, max_messages, interval, looking_for or 0, flags)
         if out is None:
             out = np.empty(n, dtype=N.RESULT_DTYPE)
+        elif out.dtype != N.RESULT_DTYPE or len(out) < n or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous array of >= %d demi_fuzz_result records" % n)   # the C call writes n * 32 bytes
         self._check(N.lib().demi_fuzz_batch(self._h, C.byref(p), out.ctypes.data))
         return out
 
@@ -365,7 +367,13 @@ class RandomScheduler(object):
 
     def explore(self, trace, lookingFor=None):
         """Returns (EventTrace records, violation code) of the first violating
-        execution, else None (RandomScheduler.scala:234-272)."""
+        execution, else None (RandomScheduler.scala:234-272).
+
+        Deviation, on purpose: execution i runs FullyRandom(seed + i) — the loop of RunnerUtils.fuzz
+        (RunnerUtils.scala:75-91: a fresh RandomScheduler + FullyRandom per execution, max_executions = 1), made
+        reproducible.  The reference's own `for (i <- 1 to max_executions)` keeps ONE FullyRandom whose java.util.Random
+        stream runs on across executions (reset_all_state, :575-595, does not re-seed it), so for max_executions > 1
+        the i-th interleaving here is not the one a JVM run with the same seed would produce."""
         if self.test_invariant is None:
             raise ValueError("Must invoke setInvariant before test()")   # :244-246
         self.engine.set_externals(trace)
