@@ -134,3 +134,12 @@ def test_record_validation_rejects_out_of_range_indices(native):
     with pytest.raises(D.DemiError) as ei:
         eng.provenance(ev, np.array([0, 1], dtype=np.uint16), 1)  # node 1 is its own parent
     assert "parent" in str(ei.value)
+
+
+def test_jni_shim_names_match():
+    """Every @native method of jni/DemiNative.scala has its JNIEXPORT wrapper in jni/DemiNative.c and vice versa."""
+    scala = open(os.path.join(ROOT, "jni", "DemiNative.scala")).read()
+    c = open(os.path.join(ROOT, "jni", "DemiNative.c")).read()
+    natives = set(re.findall(r"@native def (\w+)", scala))
+    exports = set(re.findall(r"DemiNative_(\w+)\(", c))
+    assert natives == exports and len(natives) >= 30
