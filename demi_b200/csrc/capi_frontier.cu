@@ -531,11 +531,9 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
     for (uint32_t r = 0; r < S && allow && st.pool_live && !st.R.status; r++) {
       const uint32_t quota = (uint32_t)std::min<unsigned long long>(allow, st.W);
       uint32_t n_sel = 0;
-      CUDA_TRY(h, cudaEventRecord(st.ev[0], st.s));
-      if ((rc = fr_select_front(st, quota, &n_sel)) != DEMI_OK) return rc;
-      CUDA_TRY(h, cudaEventRecord(st.ev[3], st.s));
-      CUDA_TRY(h, cudaEventSynchronize(st.ev[3]));
-      float ms = 0; cudaEventElapsedTime(&ms, st.ev[0], st.ev[3]); st.R.select_ms += ms;
+      const auto ts0 = std::chrono::steady_clock::now();
+      if ((rc = fr_select_front(st, quota, &n_sel)) != DEMI_OK) return rc;      // ends with a stream sync (the cut)
+      st.R.select_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
       if (n_sel) { if ((rc = fr_execute_and_scan(st, n_sel, false)) != DEMI_OK) return rc; }
       else st.R.rounds++;
       allow -= n_sel;
@@ -551,17 +549,27 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
   st.R.pool_left = st.pool_live; st.R.trace_slots = st.n_slots;
   st.R.exhausted = (uint32_t)exhausted; st.R.budget_exhausted = (uint32_t)budget;
   if (st.n_exec) {
-    std::vector<unsigned long long> hh(st.n_exec); std::vector<uint32_t> vv(st.n_exec);
-    CUDA_TRY(h, cudaMemcpy(hh.data(), st.out_hash, st.n_exec * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(h, cudaMemcpy(vv.data(), st.out_viol, st.n_exec * 4, cudaMemcpyDeviceToHost));
-    if (hashes) for (unsigned long long i = 0; i < st.n_exec && i < cap_hashes; i++) hashes[i] = hh[i];
-    // violations in execution order; `interleaving` indexes this rank's executions (= hashes)
-    if (viol) {
-      unsigned long long nv = 0;
-      for (unsigned long long i = 0; i < st.n_exec; i++) if (vv[i] & 0xFFFFu) {
-        if (nv < cap_viol) { viol[nv].schedule_hash = hh[i]; viol[nv].interleaving = (uint32_t)i; viol[nv].length = (uint16_t)(vv[i] >> 16); viol[nv].code = (uint16_t)(vv[i] & 0xFFFFu); }
-        nv++;
+    // only what the caller asked for crosses PCIe: the schedule hashes if wanted, and the violating records (compacted
+    // on the device, then put back in execution order)
+    if (hashes) CUDA_TRY(h, cudaMemcpy(hashes, st.out_hash, std::min<unsigned long long>(st.n_exec, cap_hashes) * 8, cudaMemcpyDeviceToHost));
+    if (viol && cap_viol) {
+      demi_dpor_violation* vd = nullptr; unsigned int* cnt = nullptr;
+      CUDA_TRY(h, cudaMalloc(&vd, (size_t)cap_viol * sizeof(demi_dpor_violation) + 16));
+      cnt = (unsigned int*)(vd + cap_viol);
+      cudaError_t e = cudaMemsetAsync(cnt, 0, 4, st.s);
+      if (e == cudaSuccess) {
+        fr_collect_viol_kernel<<<(unsigned)((st.n_exec + 255) / 256), 256, 0, st.s>>>(st.out_hash, st.out_viol, st.n_exec, vd, cap_viol, cnt);
+        e = cudaGetLastError();
       }
+      unsigned int nv = 0;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&nv, cnt, 4, cudaMemcpyDeviceToHost, st.s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st.s);
+      const unsigned int got = std::min<unsigned int>(nv, cap_viol);
+      if (e == cudaSuccess && got) e = cudaMemcpy(viol, vd, (size_t)got * sizeof(demi_dpor_violation), cudaMemcpyDeviceToHost);
+      cudaFree(vd);
+      if (e != cudaSuccess) return fail(h, DEMI_ERR_CUDA, "demi_dpor_frontier: %s", cudaGetErrorString(e));
+      std::sort(viol, viol + got, [](const demi_dpor_violation& a, const demi_dpor_violation& b) { return a.interleaving < b.interleaving; });
+      h->perf.kernel_launches++;
     }
   }
   return DEMI_OK;

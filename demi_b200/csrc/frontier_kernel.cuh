@@ -651,6 +651,18 @@ __global__ void __launch_bounds__(256) fr_sel_assign_kernel(const __grid_constan
   if (rank == q - 1 && total > S.quota) S.info->cut = i + 1;
 }
 
+// ------------------------------------------------------------------ results: the violating interleavings only
+__global__ void __launch_bounds__(256)
+fr_collect_viol_kernel(const unsigned long long* out_hash, const uint32_t* out_viol, unsigned long long n,
+                       demi_dpor_violation* viol, uint32_t cap, unsigned int* count) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = out_viol[i];
+  if (!(v & 0xFFFFu)) return;
+  const unsigned int k = atomicAdd(count, 1u);
+  if (k < cap) { viol[k].schedule_hash = out_hash[i]; viol[k].interleaving = (uint32_t)i; viol[k].length = (uint16_t)(v >> 16); viol[k].code = (uint16_t)(v & 0xFFFFu); }
+}
+
 // ------------------------------------------------------------------ steal round
 // record = 16-byte header {branch, later, earlier, pair key lo|hi} + (later + 1) trace entries; fixed stride
 struct FrXArgs {

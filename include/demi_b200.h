@@ -470,7 +470,8 @@ typedef struct demi_frontier_entry {    /* one delivered event of a trace, 16 by
 } demi_frontier_entry;
 /* Runs on this handle's device; with a communicator (demi_comm_init) every rank calls it collectively.
  * hashes (cap_hashes, may be NULL): schedule hash of every interleaving executed on this rank, in slot order;
- * viol (cap_viol): this rank's violating interleavings in slot order. */
+ * viol (cap_viol): this rank's violating interleavings in execution order (`interleaving` indexes `hashes`); when more
+ * than cap_viol violate, result->violations still counts them all and which cap_viol records are returned is unspecified. */
 int32_t demi_dpor_frontier(demi_handle* h, const demi_ext_event* ext, uint32_t n_ext,
                            const demi_frontier_params* params, demi_frontier_result* result,
                            demi_dpor_violation* viol, uint32_t cap_viol, uint64_t* hashes, uint64_t cap_hashes);
