@@ -137,6 +137,8 @@ struct FrState {
   ulonglong2* win = nullptr; uint8_t* flag = nullptr; unsigned long long* skey = nullptr; uint32_t* sidx = nullptr;
   uint32_t* blockcnt = nullptr; FrSeg* segs_dev = nullptr; uint32_t segs_cap = 0;
   uint4* sendbuf = nullptr; uint4* recvbuf = nullptr; uint32_t* hist = nullptr; unsigned long long* gather_dev = nullptr;
+  unsigned long long* log_keys = nullptr; unsigned int* log_n = nullptr; unsigned int log_cap = 0;     // explored pairs to share
+  unsigned long long* log_all = nullptr; unsigned long long* log_counts = nullptr;
   uint4* ext_dev = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // host: the queue directory
@@ -197,7 +199,11 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   st.segs_cap = 1 << 16; DA(segs_dev, st.segs_cap)
   if (world > 1) {
     DA(sendbuf, (size_t)F.steal_max * (world - 1) * st.rec_u4) DA(recvbuf, (size_t)F.steal_max * (world - 1) * st.rec_u4)
-    DA(gather_dev, (size_t)world * std::max(world, 4))
+    DA(gather_dev, (size_t)world * std::max(world, 8))
+    if (!(F.flags & DEMI_FR_NO_HISTORY)) {
+      st.log_cap = (unsigned int)std::min<unsigned long long>(F.explored_slots / 2, 1ull << 22);
+      DA(log_keys, st.log_cap) DA(log_n, 4) DA(log_all, (size_t)world * st.log_cap) DA(log_counts, world)
+    }
   }
   DA(hist, st.T1)
   DA(ext_dev, std::max<uint32_t>(n_ext, 64))
@@ -208,6 +214,7 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   memset(&st.R, 0, sizeof(st.R));
   if (!(F.flags & DEMI_FR_NO_HISTORY)) CUDA_TRY(h, cudaMemsetAsync(st.E, 0, F.explored_slots * 8, st.s));
   CUDA_TRY(h, cudaMemsetAsync(st.ctr, 0, FRC_N * 8, st.s));
+  if (st.log_n) CUDA_TRY(h, cudaMemsetAsync(st.log_n, 0, 16, st.s));
   CUDA_TRY(h, cudaMemsetAsync(st.info, 0, sizeof(FrInfo), st.s));
   if (n_ext) CUDA_TRY(h, cudaMemcpyAsync(st.ext_dev, ext, n_ext * sizeof(demi_ext_event), cudaMemcpyHostToDevice, st.s));
   CUDA_TRY(h, cudaFuncSetAttribute(st.v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.v->smem));
@@ -224,7 +231,8 @@ int32_t fr_setup(FrState& st, const demi_ext_event* ext, uint32_t n_ext, bool re
   A.sel = st.sel; A.out_hash = st.out_hash; A.out_viol = st.out_viol;
   A.pendA = st.pendA; A.pendP1 = st.pendP1; A.pendNX = st.pendNX; A.cap_pend = st.cap_pend;
   A.ctr = st.ctr; A.races = st.races; A.rcap = st.rcap; A.n_races = st.n_races;
-  A.counts = st.counts; A.tot = st.tot; A.base = st.base; A.tile_tot = st.tile_tot; A.pool = st.pool; A.info = st.info;
+  A.counts = st.counts; A.tot = st.tot; A.base = st.base; A.tile_tot = st.tile_tot;
+  A.log = FrLog{st.log_keys, st.log_n, st.log_cap}; A.pool = st.pool; A.info = st.info;
   return DEMI_OK;
 }
 
@@ -256,6 +264,7 @@ int32_t fr_select_window(FrState& st, const std::vector<FrSeg>& segs, uint32_t w
   S.blockcnt = st.blockcnt; S.n_blocks = (win_n + 255) / 256;
   S.sel = dst; S.sel_base = dst_base; S.quota = quota; S.info = st.info; S.ctr = st.ctr;
   S.no_history = (st.F.flags & DEMI_FR_NO_HISTORY) ? 1u : 0u;
+  S.log = FrLog{st.log_keys, st.log_n, st.log_cap};
   fr_sel_probe_kernel<<<S.n_blocks, 256, 0, st.s>>>(S);
   fr_sel_winner_kernel<<<S.n_blocks, 256, 0, st.s>>>(S);
   fr_sel_blockscan_kernel<<<1, 1024, 0, st.s>>>(S);
@@ -391,6 +400,27 @@ int32_t fr_execute_and_scan(FrState& st, uint32_t n_sel, bool root) {
   return DEMI_OK;
 }
 
+// the pair keys every rank marked explored since the last exchange become known to all ranks (a set union, so the
+// order in which they were logged does not matter): the rank-local explored sets stop diverging
+int32_t fr_share_explored(FrState& st, const std::vector<unsigned long long>& n_new) {
+  demi_handle* h = st.h; NcclApi* nc = nccl_api(); FrComm* cm = st.comm;
+  const int G = cm->world, me = cm->rank;
+  unsigned long long maxn = 0;
+  for (int q = 0; q < G; q++) maxn = std::max(maxn, n_new[q]);
+  if (!maxn) return DEMI_OK;
+  if (maxn > st.log_cap) { st.R.status = DEMI_DS_EXPLORED_OVF; return DEMI_OK; }
+  // equal-size all-gather: every rank contributes `maxn` slots of its log (the tail beyond its own count is ignored)
+  CUDA_TRY(h, cudaMemcpyAsync(st.log_counts, n_new.data(), (size_t)G * 8, cudaMemcpyHostToDevice, st.s));
+  NCCL_TRY(h, nc->AllGather(st.log_keys, st.log_all, (size_t)maxn, ncclUint64, cm->comm, st.s));
+  fr_merge_keys_kernel<<<dim3((unsigned)((maxn + 255) / 256), (unsigned)G), 256, 0, st.s>>>(st.log_all, (unsigned int)maxn, st.log_counts, (unsigned)G, (unsigned)me,
+                                                                                          st.E, st.F.explored_slots, st.ctr);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemsetAsync(st.log_n, 0, 4, st.s));
+  h->perf.kernel_launches++;
+  st.R.bytes_sent += n_new[me] * 8ull * (unsigned long long)(G - 1);
+  return DEMI_OK;
+}
+
 // one steal exchange; `have` = every rank's queue length (all-gathered).  The plan is a pure function of the all-gathered lengths, so every rank computes the same one.
 int32_t fr_exchange(FrState& st, const std::vector<unsigned long long>& have_in, unsigned long long total_pool,
                     std::vector<unsigned long long>& have_after) {
@@ -495,20 +525,26 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
   int exhausted = 0, budget = 0;
   for (;;) {
     // ---- what every rank learns at an exchange point
-    unsigned long long mine[4] = {st.pool_live, st.n_exec, st.R.violations, st.R.status};
-    std::vector<unsigned long long> all((size_t)G * 4);
+    unsigned long long mine[8] = {st.pool_live, st.n_exec, st.R.violations, st.R.status, 0, 0, 0, 0};
+    std::vector<unsigned long long> all((size_t)G * 8);
     if (G > 1) {
       const auto t0 = std::chrono::steady_clock::now();
       NcclApi* nc = nccl_api();
-      CUDA_TRY(h, cudaMemcpyAsync(st.gather_dev + (size_t)me * 4, mine, sizeof(mine), cudaMemcpyHostToDevice, st.s));
-      NCCL_TRY(h, nc->AllGather(st.gather_dev + (size_t)me * 4, st.gather_dev, 4, ncclUint64, st.comm->comm, st.s));
-      CUDA_TRY(h, cudaMemcpyAsync(all.data(), st.gather_dev, (size_t)G * 32, cudaMemcpyDeviceToHost, st.s));
+      if (st.log_n) {                                                         // how many pair keys this rank has to share
+        unsigned int nn = 0;
+        CUDA_TRY(h, cudaMemcpyAsync(&nn, st.log_n, 4, cudaMemcpyDeviceToHost, st.s));
+        CUDA_TRY(h, cudaStreamSynchronize(st.s));
+        mine[4] = nn;
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(st.gather_dev + (size_t)me * 8, mine, sizeof(mine), cudaMemcpyHostToDevice, st.s));
+      NCCL_TRY(h, nc->AllGather(st.gather_dev + (size_t)me * 8, st.gather_dev, 8, ncclUint64, st.comm->comm, st.s));
+      CUDA_TRY(h, cudaMemcpyAsync(all.data(), st.gather_dev, (size_t)G * 64, cudaMemcpyDeviceToHost, st.s));
       CUDA_TRY(h, cudaStreamSynchronize(st.s));
       st.R.exchange_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     } else memcpy(all.data(), mine, sizeof(mine));
     unsigned long long executed = 0, total_pool = 0; bool any_status = false, found = false;
-    std::vector<unsigned long long> have(G);
-    for (int q = 0; q < G; q++) { have[q] = all[q * 4]; total_pool += have[q]; executed += all[q * 4 + 1]; found |= all[q * 4 + 2] != 0; any_status |= all[q * 4 + 3] != 0; }
+    std::vector<unsigned long long> have(G), n_new(G);
+    for (int q = 0; q < G; q++) { have[q] = all[q * 8]; total_pool += have[q]; executed += all[q * 8 + 1]; found |= all[q * 8 + 2] != 0; any_status |= all[q * 8 + 3] != 0; n_new[q] = all[q * 8 + 4]; }
     if (any_status) break;
     if (F.stop_if_found && found) break;                                      // :1147
     if (executed >= F.max_interleavings) { budget = 1; break; }
@@ -516,6 +552,8 @@ int32_t fr_run(FrState& st, demi_dpor_violation* viol, uint32_t cap_viol, uint64
     std::vector<unsigned long long> have_after = have;
     if (G > 1) {
       const auto t0 = std::chrono::steady_clock::now();
+      if (st.log_n && (rc = fr_share_explored(st, n_new)) != DEMI_OK) return rc;
+      if (st.R.status) continue;
       if ((rc = fr_exchange(st, have, total_pool, have_after)) != DEMI_OK) return rc;
       st.R.exchange_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (st.R.status) continue;                                              // reported at the next exchange point

@@ -35,9 +35,12 @@ struct FrInfo {                 // device-written, host-read
   uint32_t total_winners, cut, taken, pad;
   unsigned long long new_top;
 };
+// pair keys this rank marked explored since the last exchange (multi-rank, history on): shared with the other ranks there
+struct FrLog { unsigned long long* keys; unsigned int* n; unsigned int cap; };
 enum { FRC_DELIVERIES = 0, FRC_VIOLATIONS = 1, FRC_RACES = 2, FRC_EXPLORED = 3, FRC_STATUS = 4, FRC_N = 8 };
 
 struct FrArgs {
+  FrLog log;
   uint32_t model_flags, blocked_mask; int32_t ignore_timers;
   int32_t max_messages; uint32_t looking_for;
   const uint4* ext; uint32_t n_ext;
@@ -84,6 +87,13 @@ __device__ __forceinline__ bool fr_e_insert(unsigned long long* E, unsigned long
   }
   atomicMax(&ctr[FRC_STATUS], (unsigned long long)DEMI_DS_EXPLORED_OVF);
   return false;
+}
+
+__device__ __forceinline__ void fr_log_key(const FrLog& log, unsigned long long key, unsigned long long* ctr) {
+  if (!log.keys) return;
+  const unsigned int k = atomicAdd(log.n, 1u);
+  if (k < log.cap) log.keys[k] = key;
+  else atomicMax(&ctr[FRC_STATUS], (unsigned long long)DEMI_DS_EXPLORED_OVF);
 }
 
 // ------------------------------------------------------------------ executor
@@ -404,7 +414,7 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
       const unsigned m = __ballot_sync(FULL_MASK, race);
       if (race) {
         rec[nr + __popc(m & ((1u << lane) - 1u))] = fr_rec(my_li, ei, br);
-        if (!A.no_history && fr_e_insert(A.E, A.e_slots, demi_fr_pair_key(ids[ei], ids[my_li]), A.ctr)) new_pairs++;   // :1071-1073
+        if (!A.no_history) { const unsigned long long pk = demi_fr_pair_key(ids[ei], ids[my_li]); if (fr_e_insert(A.E, A.e_slots, pk, A.ctr)) { new_pairs++; fr_log_key(A.log, pk, A.ctr); } }   // :1071-1073
       }
       nr += __popc(m);
       li += 2;
@@ -421,7 +431,7 @@ fr_scan_kernel(const __grid_constant__ FrArgs A) {
       const unsigned m = __ballot_sync(FULL_MASK, race);
       if (race) {
         rec[nr + __popc(m & ((1u << lane) - 1u))] = fr_rec(li, ei, br);
-        if (!A.no_history && fr_e_insert(A.E, A.e_slots, demi_fr_pair_key(ids[ei], ids[li]), A.ctr)) new_pairs++;   // :1071-1073
+        if (!A.no_history) { const unsigned long long pk = demi_fr_pair_key(ids[ei], ids[li]); if (fr_e_insert(A.E, A.e_slots, pk, A.ctr)) { new_pairs++; fr_log_key(A.log, pk, A.ctr); } }   // :1071-1073
       }
       nr += __popc(m);
     }
@@ -558,6 +568,7 @@ struct FrSelArgs {
   ulonglong2* sel; uint32_t sel_base; uint32_t quota;
   FrInfo* info; unsigned long long* ctr;
   uint32_t no_history;
+  FrLog log;
 };
 __device__ __forceinline__ uint32_t fr_s_slot(unsigned long long key, uint32_t slots) {
   return (uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 33) & (slots - 1);
@@ -646,9 +657,22 @@ __global__ void __launch_bounds__(256) fr_sel_assign_kernel(const __grid_constan
   const uint32_t q = total < S.quota ? total : S.quota;
   if (rank >= q) return;
   const ulonglong2 k = S.win[i];
-  if (!S.no_history && fr_e_insert(S.E, S.e_slots, k.y, S.ctr)) atomicAdd(&S.ctr[FRC_EXPLORED], 1ull);
+  if (!S.no_history && fr_e_insert(S.E, S.e_slots, k.y, S.ctr)) { atomicAdd(&S.ctr[FRC_EXPLORED], 1ull); fr_log_key(S.log, k.y, S.ctr); }
   S.sel[S.sel_base + rank] = k;
   if (rank == q - 1 && total > S.quota) S.info->cut = i + 1;
+}
+
+// ------------------------------------------------------------------ explored pairs learned from the other ranks
+// keys[r * stride + i], i < counts[r], for every rank r != me: set union into the local table (not logged again)
+__global__ void __launch_bounds__(256)
+fr_merge_keys_kernel(const unsigned long long* keys, unsigned int stride, const unsigned long long* counts, unsigned int n_ranks,
+                     unsigned int me, unsigned long long* E, unsigned long long e_slots, unsigned long long* ctr) {
+  const unsigned int r = blockIdx.y;
+  if (r == me || r >= n_ranks) return;
+  const unsigned int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= (unsigned int)counts[r]) return;
+  const unsigned long long k = keys[(size_t)r * stride + i];
+  if (k && fr_e_insert(E, e_slots, k, ctr)) atomicAdd(&ctr[FRC_EXPLORED], 1ull);
 }
 
 // ------------------------------------------------------------------ results: the violating interleavings only

@@ -30,6 +30,7 @@ typedef struct { uint64_t id; demi_msg msg; uint16_t ppos; } fpend;  /* a pendin
 typedef struct {
   /* explored ordered pairs */
   uint64_t* E; uint64_t e_slots, n_E; int no_history;     /* trackHistory = false (:86): the set stays empty */
+  uint64_t* log; uint64_t n_log, cap_log;                  /* pair keys marked since the last exchange (shared with the other ranks there) */
   /* trace store */
   demi_frontier_entry* tr; uint32_t* tr_len; uint32_t* tr_branch; uint32_t n_slots, cap_slots, T1;
   /* backtrack queue, ascending ord */
@@ -68,6 +69,7 @@ static void e_add(frank* r, uint64_t key) {
   while (r->E[s]) { if (r->E[s] == key) return; s = (s + 1) & (r->e_slots - 1); }
   if (r->n_E * 2 >= r->e_slots) { r->R.status = DEMI_DS_EXPLORED_OVF; return; }
   r->E[s] = key; r->n_E++;
+  if (r->log) { if (r->n_log >= r->cap_log) { r->R.status = DEMI_DS_EXPLORED_OVF; return; } r->log[r->n_log++] = key; }
 }
 
 /* --------------------------------------------- DPORwHeuristics.event_produced */
@@ -333,6 +335,7 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
   for (uint32_t q = 0; q < n_ranks; q++) {
     frank* r = &R[q];
     r->e_slots = F->explored_slots; r->E = (uint64_t*)calloc(r->e_slots, 8); r->no_history = (F->flags & DEMI_FR_NO_HISTORY) != 0;
+    if (n_ranks > 1 && !r->no_history) { r->cap_log = F->explored_slots / 2 < (1ull << 22) ? F->explored_slots / 2 : (1ull << 22); r->log = (uint64_t*)malloc(8 * r->cap_log); }
     r->T1 = T1; r->cap_slots = F->trace_cap;
     r->tr = (demi_frontier_entry*)malloc(sizeof(demi_frontier_entry) * (size_t)r->cap_slots * T1);
     r->tr_len = (uint32_t*)calloc(r->cap_slots, 4); r->tr_branch = (uint32_t*)calloc(r->cap_slots, 4);
@@ -371,6 +374,21 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
     if (F->stop_if_found && found) break;                                   /* :1147 */
     if (executed >= F->max_interleavings) { budget = 1; break; }
     if (!total_pool) { exhausted = 1; break; }
+    /* ---- the pair keys every rank marked since the last exchange become known to all ranks (a set union) */
+    if (n_ranks > 1 && R[0].log) {
+      for (uint32_t q = 0; q < n_ranks; q++) R[q].R.bytes_sent += R[q].n_log * 8ull * (n_ranks - 1);
+      for (uint32_t rcv = 0; rcv < n_ranks; rcv++)
+        for (uint32_t src = 0; src < n_ranks; src++) {
+          if (src == rcv) continue;
+          uint64_t* keep = R[rcv].log; R[rcv].log = 0;                 /* learned keys are not shared again */
+          for (uint64_t i = 0; i < R[src].n_log; i++) e_add(&R[rcv], R[src].log[i]);
+          R[rcv].log = keep;
+        }
+      for (uint32_t q = 0; q < n_ranks; q++) R[q].n_log = 0;
+      any_status = 0;
+      for (uint32_t q = 0; q < n_ranks; q++) any_status |= R[q].R.status != 0;
+      if (any_status) break;
+    }
     /* ---- steal plan: ranks that cannot fill their next S rounds take from ranks that can spare */
     if (n_ranks > 1) {
       const uint64_t need = (uint64_t)S * F->width;
@@ -448,7 +466,7 @@ int oracle_dpor_frontier(const demi_config* cfg, const demi_ext_event* ext, uint
     r->R.explored_pairs = r->n_E; r->R.pool_left = r->n_pool; r->R.trace_slots = r->n_slots;
     r->R.exhausted = (uint32_t)exhausted; r->R.budget_exhausted = (uint32_t)budget;
     results[q] = r->R;
-    free(r->E); free(r->tr); free(r->tr_len); free(r->tr_branch); free(r->pool);
+    free(r->log); free(r->E); free(r->tr); free(r->tr_len); free(r->tr_branch); free(r->pool);
   }
   free(scratch); free(sbuf); free(x->pend); free(x); free(R);
   return any_status ? DEMI_ERR_CAPACITY : DEMI_OK;

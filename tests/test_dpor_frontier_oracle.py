@@ -64,11 +64,11 @@ def test_exhaustive_set_parity_and_multi_rank_coverage(oracle):
             if ranks == 1:
                 assert f_all == seq_all and f_viol == seq_viol
             else:
-                # explored sets are rank-local: more interleavings run, and which redundant reversals are pruned
-                # depends on where a point ran, so the visited set is close to, not equal to, the sequential one
-                assert len(f_all & seq_all) >= 0.8 * len(seq_all)
+                # every rank keeps its own explored set and learns the other ranks' newly explored pairs at the exchange
+                # points: every racing pair is still reversed about once (the work stays close to the sequential search's),
+                # but WHICH context reverses it depends on where a point ran, so the visited schedules differ
                 assert len(f_viol & seq_viol) >= 0.8 * len(seq_viol)
-                assert res["interleavings"].sum() >= len(seq_all)
+                assert len(seq_all) * 0.8 <= res["interleavings"].sum() <= 3 * len(seq_all)
                 assert res["records_sent"].sum() == res["records_received"].sum() > 0
     assert with_viol >= 2
 
