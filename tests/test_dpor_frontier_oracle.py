@@ -76,7 +76,7 @@ def test_exhaustive_set_parity_and_multi_rank_coverage(oracle):
 def test_multi_rank_runs_are_deterministic_and_respect_the_budget(oracle):
     prog = D.raft5_program(client_cmds=2)[:-1]
     ext = D.pack_externals(prog)
-    for flags, budget in [(0, 300), (N.FR_NO_HISTORY, 3000)]:               # trackHistory = true / false
+    for flags, budget in [(0, 120), (N.FR_NO_HISTORY, 3000)]:               # trackHistory = true / false
         F = oracle.frontier_params(60, budget, 32, explored_slots=1 << 20, pool_cap=1 << 22, rounds_per_exchange=2, steal_max=64,
                                    flags=flags)
         a = oracle.dpor_frontier(N.MODEL_RAFT5, ext, F, 4, model_flags=3)
