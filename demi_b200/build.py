@@ -103,7 +103,8 @@ def build_oracle(force=False):
     same_cpu = os.path.exists(ORACLE_STAMP) and open(ORACLE_STAMP).read().strip() == stamp
     if not force and same_cpu and _newer(ORACLE_LIB, srcs):
         return ORACLE_LIB
-    subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle.so"])
+    # make's chatter goes to stderr: bench.py prints exactly one JSON line on stdout
+    subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle.so"], stdout=sys.stderr)
     with open(ORACLE_STAMP, "w") as f:
         f.write(stamp + "\n")
     return ORACLE_LIB
