@@ -96,7 +96,7 @@ def c2_dpor(rank, world, local_rank, cores, with_cpu):
         out["search"] = a
         eng.close()
     # ---- (b) trackHistory = false, budgeted, all ranks + steal round
-    per_gpu = int(os.environ.get("DEMI_C2_BUDGET", str(1 << 20)))
+    per_gpu = int(os.environ.get("DEMI_C2_BUDGET", str(1 << 22)))
     width = int(os.environ.get("DEMI_C2_WIDTH", "131072"))
     eng = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=3, device=local_rank))
     if world > 1:
@@ -105,7 +105,7 @@ def c2_dpor(rank, world, local_rank, cores, with_cpu):
             uid.copy_(torch.frombuffer(bytearray(D.Engine.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-    F = eng.frontier_params(100, per_gpu * world, width, explored_slots=1 << 10, pool_cap=1 << 28,
+    F = eng.frontier_params(100, per_gpu * world, width, explored_slots=1 << 10, pool_cap=1 << 30,
                             trace_cap=per_gpu + width + 8 * 4096 + 16, rounds_per_exchange=4, steal_max=4096,
                             flags=N.FR_NO_HISTORY)
     eng.dpor_frontier(prog, F, want_hashes=False)                    # warm-up: allocates, first NCCL exchange
