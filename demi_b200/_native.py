@@ -33,7 +33,7 @@ class Perf(C.Structure):
     _fields_ = [("prefixes", C.c_uint64), ("deliveries", C.c_uint64), ("violations", C.c_uint64),
                 ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("deferred", C.c_uint32)]
 
 
 EXT_DTYPE = np.dtype([("kind", "u1"), ("a", "u1"), ("b", "u1"), ("type", "u1"),

@@ -107,7 +107,7 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
-  if (e == cudaSuccess) e = cudaMalloc(&h->counters_dev, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters_dev, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 4 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ovf_count, sizeof(uint32_t));
   if (getenv("DEMI_DISABLE_LANE_ENGINE")) h->use_lane_engine = 0;
@@ -359,7 +359,7 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
   cudaStream_t s = (cudaStream_t)stream;
   plan.args.results = (demi_fuzz_result*)out_dev;
   if (reset_counters) {
-    CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 4 * sizeof(unsigned long long), s));
     h->perf.kernel_launches = 0;
     h->perf.prefixes = 0;
   }
@@ -367,13 +367,14 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
   if (lv) {
     // K1-lane handles every prefix it can prove exact; the rest are deferred to the warp engine
     const size_t lsmem = lv->smem_per_block;
+    const kernel_fn lfn = lv->fn;
     int bps = 0;
     {
-      auto it = h->occupancy.find((const void*)lv->fn);
+      auto it = h->occupancy.find((const void*)lfn);
       if (it == h->occupancy.end()) {
-        CUDA_TRY(h, cudaFuncSetAttribute(lv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lv->fn, lv->bd, lsmem));
-        h->occupancy[(const void*)lv->fn] = bps;
+        CUDA_TRY(h, cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lfn, lv->bd, lsmem));
+        h->occupancy[(const void*)lfn] = bps;
       } else bps = it->second;
     }
     if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "lane kernel does not fit on an SM");
@@ -389,7 +390,7 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
     la.ext_sends = h->ext_sends_dev;
     la.has_partitions = h->has_partitions ? 1u : 0u;
     la.ovf_list = h->ovf_list; la.ovf_count = h->ovf_count;
-    lv->fn<<<lgrid, lv->bd, lsmem, s>>>(la);
+    lfn<<<lgrid, lv->bd, lsmem, s>>>(la);
     CUDA_TRY(h, cudaGetLastError());
     h->perf.kernel_launches++;
     plan.args.index_list = h->ovf_list;
@@ -438,7 +439,7 @@ extern "C" int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p, de
     if (ce != cudaSuccess) { rc = fail(h, DEMI_ERR_CUDA, "demi_fuzz_batch: %s", cudaGetErrorString(ce)); break; }   // events freed below
   }
   cudaError_t e = cudaEventRecord(h->ev1, h->stream);
-  unsigned long long cnt[2] = {0, 0};
+  unsigned long long cnt[3] = {0, 0, 0};
   if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, h->counters_dev, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->copy_stream);
@@ -450,6 +451,7 @@ extern "C" int32_t demi_fuzz_batch(demi_handle* h, const demi_fuzz_params* p, de
   h->perf.kernel_ms = ms;
   h->perf.deliveries = cnt[0];
   h->perf.violations = cnt[1];
+  h->perf.deferred = (uint32_t)std::min<unsigned long long>(cnt[2], 0xFFFFFFFFull);      // deferred to the general engine
   h->perf.d2h_bytes = bytes + sizeof(cnt);
   h->perf.h2d_bytes = 0;
   return DEMI_OK;
@@ -460,13 +462,14 @@ extern "C" int32_t demi_fuzz_summary_dev(demi_handle* h, const void* /*results_d
                                          void* stream, uint64_t* n_violations, uint64_t* sum_steps) {
   if (!h) return DEMI_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  unsigned long long c[2] = {0, 0};
+  unsigned long long c[3] = {0, 0, 0};
   CUDA_TRY(h, cudaMemcpyAsync(c, h->counters_dev, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
   if (sum_steps) *sum_steps = c[0];
   if (n_violations) *n_violations = c[1];
   h->perf.deliveries = c[0];
   h->perf.violations = c[1];
+  h->perf.deferred = (uint32_t)std::min<unsigned long long>(c[2], 0xFFFFFFFFull);
   return DEMI_OK;
 }
 
@@ -494,7 +497,7 @@ extern "C" int32_t demi_fuzz_trace(demi_handle* h, const demi_fuzz_params* p, in
   plan.args.rec_events = ev_dev; plan.args.rec_cap = cap_events;
   plan.args.rec_counts = h->rec_counts_dev;
   plan.args.rec_parent = dep_parent ? par_dev : nullptr; plan.args.rec_parent_cap = cap_nodes;
-  CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 2 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->counters_dev, 0, 4 * sizeof(unsigned long long), h->stream));
   if (h->cfg.model == DEMI_MODEL_IR) ir_bind(h->ir_dev, h->stream);
   plan.v->fn<<<1, WARPS * 32, plan.smem, h->stream>>>(plan.args);
   cudaError_t e = cudaGetLastError();

@@ -449,13 +449,14 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   m.pend = args.lane_pend + gwarp * (uint64_t)LPCAP * 32 + (tid & 31);
   m.A = &args;
 
-  unsigned long long my_steps = 0, my_viol = 0;
+  unsigned long long my_steps = 0, my_viol = 0, my_defer = 0;
   for (uint64_t idx = gthread; idx < args.n_prefixes; idx += total) {
     demi_fuzz_result r;
     m.run(args.seed_base + (int64_t)idx, r);
     if (r.status == LANE_DEFER) {
       uint32_t pos = atomicAdd(args.ovf_count, 1u);
       args.ovf_list[pos] = (uint32_t)idx;
+      my_defer++;
     } else {
       uint4* dst = reinterpret_cast<uint4*>(args.results + idx);
       dst[0] = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
@@ -470,10 +471,12 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   for (int o = 16; o > 0; o >>= 1) {
     my_steps += __shfl_xor_sync(FULL_MASK, my_steps, o);
     my_viol += __shfl_xor_sync(FULL_MASK, my_viol, o);
+    my_defer += __shfl_xor_sync(FULL_MASK, my_defer, o);
   }
-  if ((tid & 31) == 0 && args.sum_steps && (my_steps | my_viol)) {
+  if ((tid & 31) == 0 && args.sum_steps && (my_steps | my_viol | my_defer)) {
     atomicAdd(args.sum_steps, my_steps);
     atomicAdd(args.n_violations, my_viol);
+    if (my_defer) atomicAdd(args.sum_steps + 2, my_defer);      // [2]: prefixes handed to the general engine
   }
 }
 

@@ -173,7 +173,7 @@ typedef struct demi_perf {
   double   h2d_ms, d2h_ms;
   uint64_t h2d_bytes, d2h_bytes;
   uint32_t kernel_launches;
-  uint32_t reserved;
+  uint32_t deferred;           /* random fuzz: prefixes the lane engine handed to the general engine */
 } demi_perf;
 
 typedef struct demi_handle demi_handle;
