@@ -253,7 +253,10 @@ extern "C" int32_t demi_set_user_filter(demi_handle* h, const demi_filter_rule* 
 
 static const LaneVariant* pick_lane_variant(const demi_handle* h) {
   static const std::vector<LaneVariant> v = {
-    make_lane_variant<Raft5, 256, 96>(),
+#ifndef DEMI_K1_BD_RAFT5
+#define DEMI_K1_BD_RAFT5 256
+#endif
+    make_lane_variant<Raft5, DEMI_K1_BD_RAFT5, DEMI_K1_LPCAP_RAFT5>(),
     make_lane_variant<PingPong3, 256, 128>(),
     make_lane_variant<Bcast32, 128, 8192>(),
   };

@@ -28,7 +28,46 @@
 
 namespace demi {
 
+#ifndef DEMI_K1_PEND_HINT
+#define DEMI_K1_PEND_HINT 1      // pending array accessed with an L2 evict_last policy
+#endif
+#ifndef DEMI_K1_RESULT_CS
+#define DEMI_K1_RESULT_CS 1      // result records written with streaming (evict-first) stores
+#endif
+#ifndef DEMI_K1_LPCAP_RAFT5
+#define DEMI_K1_LPCAP_RAFT5 96
+#endif
+
 constexpr uint32_t LANE_DEFER = 0xFFFFu;      // internal status: hand over to the warp engine
+
+// The pending arrays are the only data this kernel re-reads from global memory; the result records are written once.
+// An L2 evict_last policy on the former (and evict-first stores for the latter) keeps the arrays cache-resident:
+// measured 533 -> 121 B of DRAM traffic per prefix (profiles/r2_k1_l2_policy.md).  Every access to the arrays goes
+// through these two volatile asm statements (which keep their program order), and nothing else aliases the arrays,
+// so no "memory" clobber is needed.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_l2_hint(const uint4* p, uint64_t pol) {
+#if DEMI_K1_PEND_HINT
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol; return *p;
+#endif
+}
+__device__ __forceinline__ void st_l2_hint(uint4* p, uint4 v, uint64_t pol) {
+#if DEMI_K1_PEND_HINT
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol));
+#else
+  (void)pol; *p = v;
+#endif
+}
 constexpr int LANE_TOSEND_CAP = 16;
 constexpr int LANE_RESEND_CAP = 8;
 
@@ -96,6 +135,7 @@ struct LaneMachine {
 
   uint32_t* smw;             // &smem[tid]; word w at smw[w*BD]
   uint4* pend;               // entry i at pend[i*32]
+  uint64_t pol;              // L2 cache policy of the pending array
   const KernelArgs* A;
 
   JRandom rng;
@@ -127,21 +167,22 @@ struct LaneMachine {
   // RandomizedHashSet.insert (schedulers/Util.scala:126-136)
   __device__ __forceinline__ void pending_insert(uint4 e) {
     if (n_pending >= A->pending_cap || n_pending >= LPCAP) { defer(); return; }
-    pend[n_pending * 32] = e;
+    st_l2_hint(pend + n_pending * 32, e, pol);
     n_pending++;
     if (n_pending > max_pending) max_pending = n_pending;
   }
   // RandomizedHashSet.remove (schedulers/Util.scala:146-163)
   __device__ __forceinline__ uint4 pending_remove_at(uint32_t i) {
-    uint4 v = pend[i * 32];
-    uint4 last = pend[(n_pending - 1) * 32];
-    pend[i * 32] = last;
+    uint4 v = ld_l2_hint(pend + i * 32, pol);
+    uint4 last = ld_l2_hint(pend + (n_pending - 1) * 32, pol);
+    st_l2_hint(pend + i * 32, last, pol);
     n_pending--;
     return v;
   }
 
   // EventOrchestrator.crosses_partition (EventOrchestrator.scala:345-351)
   __device__ __forceinline__ bool crosses_partition(uint32_t snd, uint32_t rcv) {
+    if (!(inaccessible | killed) && !A->has_partitions) return false;      // everyone started, no one isolated
     bool snd_actor = snd < DEMI_MAX_ACTORS;
     if (snd == rcv && !((killed >> snd) & 1u)) return false;
     if (A->has_partitions && snd_actor) {
@@ -158,6 +199,20 @@ struct LaneMachine {
   // DepTracker.getMessage (DepTracker.scala:82-109): in the regime this engine
   // accepts no child is ever reused, so the Unique id is simply the next one.
   // `slot_hint`: the timer slot when the caller already knows it (flush), -2 = unknown
+  // The sends of receive() itself (sender an actor, no flags): the external / timer branches do not apply.
+  __device__ __forceinline__ void actor_send_produced(uint32_t self, uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (cancelled) {
+      const int slot = MODEL::timer_slot(dst, type, p0, p1);
+      if (slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
+    }
+    if (n_nodes >= A->node_cap) { defer(); return; }
+    const uint32_t uniq = ++n_uniq, node = n_nodes++;
+    if (!crosses_partition(self, dst)) {
+      pending_insert(make_uint4(make_hdr(self, dst, type, 0), p0, p1, uniq | (node << 16)));
+      if (status) return;
+    }
+    record_event(DEMI_EV_MSG_SEND, self, dst, type, p0, p1, uniq, node, parent_event);
+  }
   __device__ __forceinline__ void event_produced(uint32_t hdr, uint32_t p0, uint32_t p1, int slot_hint) {
     if (status) return;
     uint32_t src = hdr_src(hdr), dst = hdr_dst(hdr), type = hdr_type(hdr), flags = hdr_flags(hdr);
@@ -214,7 +269,7 @@ struct LaneMachine {
     for (uint32_t i = 0; i < n_ops && !status; i++) {
       const uint32_t w0 = ob[(i * 3) * BD], p0 = ob[(i * 3 + 1) * BD], p1 = ob[(i * 3 + 2) * BD];
       const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-      if (kind == OP_SEND) { event_produced(make_hdr(self, odst, otype, 0), p0, p1, -2); continue; }
+      if (kind == OP_SEND) { actor_send_produced(self, odst, otype, p0, p1); continue; }
       if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
       int s2 = MODEL::timer_slot(odst, otype, p0, p1);
       if (s2 < 0) { defer(); return; }
@@ -256,7 +311,7 @@ struct LaneMachine {
     for (uint32_t i = 0; i < tosend.n; i++)           // handle_timer_cancel (ExternalEventInjector.scala:601-610)
       if (tosend.get(i) == (uint32_t)slot) { tosend.remove_at(i); return; }
     for (uint32_t i = 0; i < n_pending; i++) {        // FullyRandom.remove (RandomScheduler.scala:653-664)
-      uint4 q = pend[i * 32];
+      uint4 q = ld_l2_hint(pend + i * 32, pol);
       if (hdr_src(q.x) == DEMI_DEADLETTERS && hdr_dst(q.x) == self && hdr_type(q.x) == type &&
           q.y == p0 && q.z == p1) { pending_remove_at(i); return; }
     }
@@ -358,6 +413,7 @@ struct LaneMachine {
     // equal sends out of one receive() would share a Unique (child reuse): defer.  A 64-bit filter over the
     // (op, dst, type) words settles the common case — all headers distinct — in one pass; only a filter hit
     // (a real duplicate, or a 1-in-64 collision) pays for the pairwise comparison.
+    if (MODEL::LANE_SENDS_DISTINCT) return ob.n;                    // one send per receiver: nothing can be equal
     uint64_t seen = 0; bool maybe = false;
     for (uint32_t i = 0; i < ob.n; i++) {
       const uint64_t bit = 1ull << ((ob.base[(i * 3) * BD] * 0x9E3779B1u) >> 26);
@@ -422,7 +478,7 @@ struct LaneMachine {
       if (A->fuzz_flags & DEMI_FF_HASH_PENDING)
 #pragma unroll 1
         for (uint32_t i = 0; i < n_pending; i++) {
-          uint4 q = pend[i * 32];
+          uint4 q = ld_l2_hint(pend + i * 32, pol);
           sh += demi_pending_term(q.x & 0x00FFFFFFu, q.y, q.z);
         }
       out.violation = violation; out.steps = (uint32_t)nsched;
@@ -435,7 +491,7 @@ struct LaneMachine {
 };
 
 template <class MODEL, int BD, int LPCAP>
-__global__ void __launch_bounds__(BD, 3)
+__global__ void __launch_bounds__(BD, MODEL::N_ACTORS <= 8 ? 768 / BD : 3)
 fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   using M = LaneMachine<MODEL, BD, LPCAP>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
@@ -448,6 +504,7 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   m.smw = lane_smem + tid;
   m.pend = args.lane_pend + gwarp * (uint64_t)LPCAP * 32 + (tid & 31);
   m.A = &args;
+  m.pol = l2_evict_last_policy();
 
   unsigned long long my_steps = 0, my_viol = 0, my_defer = 0;
   for (uint64_t idx = gthread; idx < args.n_prefixes; idx += total) {
@@ -458,11 +515,16 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
       args.ovf_list[pos] = (uint32_t)idx;
       my_defer++;
     } else {
+      // written once, never re-read here: streaming stores, so that the records do not push the pending arrays out of L2
       uint4* dst = reinterpret_cast<uint4*>(args.results + idx);
-      dst[0] = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
-      dst[1] = make_uint4((uint32_t)r.trace_hash, (uint32_t)(r.trace_hash >> 32),
-                          (uint32_t)r.n_nodes | ((uint32_t)r.n_events << 16),
-                          (uint32_t)r.max_pending | ((uint32_t)r.status << 16));
+      const uint4 r0 = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
+      const uint4 r1 = make_uint4((uint32_t)r.trace_hash, (uint32_t)(r.trace_hash >> 32), (uint32_t)r.n_nodes | ((uint32_t)r.n_events << 16),
+                                  (uint32_t)r.max_pending | ((uint32_t)r.status << 16));
+#if DEMI_K1_RESULT_CS
+      __stcs(dst, r0); __stcs(dst + 1, r1);
+#else
+      dst[0] = r0; dst[1] = r1;
+#endif
       my_steps += r.steps;
       my_viol += r.violation ? 1u : 0u;
     }

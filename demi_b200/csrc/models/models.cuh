@@ -36,6 +36,7 @@ struct PingPong3 {
   enum { PING = 1, PONG = 2 };
   __device__ static __forceinline__ uint32_t init_word(uint32_t, uint32_t) { return 0; }
   static constexpr int LANE_OUTBOX = 2;
+  static constexpr bool LANE_SENDS_DISTINCT = false;
   static constexpr int REPLAY_OUTBOX = 2;
   template <class S, class O>
   __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
@@ -87,6 +88,9 @@ struct Raft5 {
   }
 
   static constexpr int LANE_OUTBOX = 6;
+  // every receive() sends at most one message to each receiver (votes / AppendEntries per peer, one reply), so no two
+  // sends of one delivery are equal and the lane engine's duplicate-send screen is skipped
+  static constexpr bool LANE_SENDS_DISTINCT = true;
   static constexpr int REPLAY_OUTBOX = 6;
   // timer universe: (actor, ELECTION_TICK) -> 2*actor, (actor, HEARTBEAT_TICK) -> 2*actor+1
   __device__ static __forceinline__ int timer_slot(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
@@ -328,6 +332,7 @@ struct Bcast32 {
   }
   static constexpr int REPLAY_OUTBOX = 32;
   static constexpr int LANE_OUTBOX = 32;
+  static constexpr bool LANE_SENDS_DISTINCT = false;
   template <class A>
   __device__ static __forceinline__ uint32_t invariant(A all, uint32_t flags) {
     if (!flags) return 0;
