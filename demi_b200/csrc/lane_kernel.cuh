@@ -198,7 +198,6 @@ struct LaneMachine {
   // Instrumenter.aroundDispatch's cancelled-timer drop (Instrumenter.scala:1090-1096).
   // DepTracker.getMessage (DepTracker.scala:82-109): in the regime this engine
   // accepts no child is ever reused, so the Unique id is simply the next one.
-  // `slot_hint`: the timer slot when the caller already knows it (flush), -2 = unknown
   // The sends of receive() itself (sender an actor, no flags): the external / timer branches do not apply.
   __device__ __forceinline__ void actor_send_produced(uint32_t self, uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
     if (cancelled) {
@@ -213,35 +212,38 @@ struct LaneMachine {
     }
     record_event(DEMI_EV_MSG_SEND, self, dst, type, p0, p1, uniq, node, parent_event);
   }
-  __device__ __forceinline__ void event_produced(uint32_t hdr, uint32_t p0, uint32_t p1, int slot_hint) {
-    if (status) return;
-    uint32_t src = hdr_src(hdr), dst = hdr_dst(hdr), type = hdr_type(hdr), flags = hdr_flags(hdr);
-    int slot = slot_hint;
-    if (slot == -2 && (cancelled || (flags & DEMI_MF_EXTERNAL))) slot = MODEL::timer_slot(dst, type, p0, p1);
-    if (cancelled && slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
+  // A timer message flushed from messagesToSend (sender deadLetters, recorded as "Timer"); `slot` is its key.
+  __device__ __forceinline__ void timer_produced(uint32_t slot) {
+    const uint32_t bit = 1u << slot;
+    if (cancelled & bit) { cancelled &= ~bit; return; }
     if (n_nodes >= A->node_cap) { defer(); return; }
-    uint32_t uniq = ++n_uniq;
-    bool is_timer = false;
-    uint32_t node;
-    if (flags & DEMI_MF_EXTERNAL) {
-      if (slot >= 0) { defer(); return; }       // an external that equals a timer key could share its Unique
-      parent_event = 0;                         // reportNewlyEnabledExternal (DepTracker.scala:119-122)
-      node = n_nodes++;                         // (identical external Sends are screened on the host)
-      pending_insert(make_uint4(hdr, p0, p1, uniq | (node << 16)));
-    } else {
-      is_timer = (src == DEMI_DEADLETTERS);
-      if (is_timer) {
-        // two equal timer sends under one parent would share a Unique: defer those
-        if (slot < 0) { defer(); return; }
-        uint32_t bit = 1u << slot;
-        if (parent_event == 0) { if (root_timers & bit) { defer(); return; } root_timers |= bit; }
-        else { if (window_timers & bit) { defer(); return; } window_timers |= bit; }
-      }
-      node = n_nodes++;
-      if (!crosses_partition(src, dst)) pending_insert(make_uint4(hdr, p0, p1, uniq | (node << 16)));
+    // two equal timer sends under one parent would share a Unique: defer those
+    if (parent_event == 0) { if (root_timers & bit) { defer(); return; } root_timers |= bit; }
+    else { if (window_timers & bit) { defer(); return; } window_timers |= bit; }
+    const uint32_t uniq = ++n_uniq, node = n_nodes++;
+    uint32_t dst, type, p0, p1;
+    MODEL::slot_msg(slot, dst, type, p0, p1);
+    if (!crosses_partition(DEMI_DEADLETTERS, dst)) {
+      pending_insert(make_uint4(make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER), p0, p1, uniq | (node << 16)));
+      if (status) return;
     }
+    record_event(DEMI_EV_MSG_SEND, DEMI_TIMER_SND, dst, type, p0, p1, uniq, node, parent_event);
+  }
+  // An external Send flushed from messagesToSend (`hdr` carries DEMI_MF_EXTERNAL).
+  __device__ __forceinline__ void external_produced(uint32_t hdr, uint32_t p0, uint32_t p1) {
+    const uint32_t dst = hdr_dst(hdr), type = hdr_type(hdr);
+    const int slot = MODEL::timer_slot(dst, type, p0, p1);
+    if (slot >= 0) {
+      if ((cancelled >> slot) & 1u) { cancelled &= ~(1u << slot); return; }
+      defer(); return;                          // an external that equals a timer key could share its Unique
+    }
+    if (n_nodes >= A->node_cap) { defer(); return; }
+    const uint32_t uniq = ++n_uniq;
+    parent_event = 0;                           // reportNewlyEnabledExternal (DepTracker.scala:119-122)
+    const uint32_t node = n_nodes++;            // (identical external Sends are screened on the host)
+    pending_insert(make_uint4(hdr, p0, p1, uniq | (node << 16)));
     if (status) return;
-    record_event(DEMI_EV_MSG_SEND, is_timer ? DEMI_TIMER_SND : src, dst, type, p0, p1, uniq, node, parent_event);
+    record_event(DEMI_EV_MSG_SEND, hdr_src(hdr), dst, type, p0, p1, uniq, node, 0u);
   }
 
   // ExternalEventInjector.handle_timer (ExternalEventInjector.scala:282-297)
@@ -284,17 +286,12 @@ struct LaneMachine {
 #pragma unroll 1
     for (uint32_t i = 0; i < tosend.n && !status; i++) {
       const uint32_t b = tosend.get(i);
-      uint32_t hdr, p0, p1; int slot = -2;
       if (b & 0x80u) {
-        uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
-        hdr = raw.x; p0 = raw.y; p1 = raw.z;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A->ext_sends) + (b & 0x7Fu));
+        external_produced(raw.x, raw.y, raw.z);
       } else {
-        uint32_t dst, type;
-        MODEL::slot_msg(b, dst, type, p0, p1);
-        hdr = make_hdr(DEMI_DEADLETTERS, dst, type, DEMI_MF_TIMER);
-        slot = (int)b;
+        timer_produced(b);
       }
-      event_produced(hdr, p0, p1, slot);
     }
     if (!status) tosend.clear();
   }
