@@ -34,6 +34,9 @@ namespace demi {
 #ifndef DEMI_K1_RESULT_CS
 #define DEMI_K1_RESULT_CS 1      // result records written with streaming (evict-first) stores
 #endif
+#ifndef DEMI_K1_DIRECT_OUTBOX
+#define DEMI_K1_DIRECT_OUTBOX 1  // models with LANE_SENDS_DISTINCT: receive()'s operations are applied as they are issued
+#endif
 #ifndef DEMI_K1_LPCAP_RAFT5
 #define DEMI_K1_LPCAP_RAFT5 96
 #endif
@@ -126,6 +129,18 @@ struct ByteQueue16 {
   }
 };
 
+// receive()'s view when its operations are applied as they are issued (`dst ! msg` is synchronous in the reference,
+// Instrumenter.scala:1098-1108): no staging in shared memory.  Only for models whose receive() cannot produce two equal
+// sends (MODEL::LANE_SENDS_DISTINCT), because the duplicate-send screen needs the whole outbox.
+template <class M>
+struct LaneDirectOutbox {
+  M* m; uint32_t self;
+  __device__ __forceinline__ void send(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) { m->actor_send_produced(self, dst, type, p0, p1); }
+  __device__ __forceinline__ void schedule_once(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_ONCE, self, type, p0, p1); }
+  __device__ __forceinline__ void schedule_repeating(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_REPEAT, self, type, p0, p1); }
+  __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { m->cancel_timer(self, type, p0, p1); }
+};
+
 template <class MODEL, int BD, int LPCAP>
 struct LaneMachine {
   static constexpr int N = MODEL::N_ACTORS;
@@ -200,6 +215,7 @@ struct LaneMachine {
   // accepts no child is ever reused, so the Unique id is simply the next one.
   // The sends of receive() itself (sender an actor, no flags): the external / timer branches do not apply.
   __device__ __forceinline__ void actor_send_produced(uint32_t self, uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
     if (cancelled) {
       const int slot = MODEL::timer_slot(dst, type, p0, p1);
       if (slot >= 0 && ((cancelled >> slot) & 1u)) { cancelled &= ~(1u << slot); return; }
@@ -262,6 +278,18 @@ struct LaneMachine {
     }
     handle_timer(slot);
   }
+  // scheduler.scheduleOnce / schedule (Instrumenter.scala:1126-1190)
+  __device__ __forceinline__ void schedule_timer(uint32_t kind, uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
+    const int s2 = MODEL::timer_slot(self, type, p0, p1);
+    if (s2 < 0) { defer(); return; }
+    if ((registry >> s2) & 1u) return;                        // "Non-unique timer" (Instrumenter.scala:1154-1157)
+    if (kind == OP_SCHED_REPEAT) {
+      if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); return; }
+      registry |= 1u << s2;
+    }
+    enqueue_timer((uint32_t)s2);
+  }
   // First the ops receive() left in the outbox (`n_ops`, sender `self`), in program order; then, if `do_flush`,
   // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365).  Two loops, so that the
   // lanes of a warp reconverge between the phases and their flush items are processed together.
@@ -273,14 +301,7 @@ struct LaneMachine {
       const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
       if (kind == OP_SEND) { actor_send_produced(self, odst, otype, p0, p1); continue; }
       if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
-      int s2 = MODEL::timer_slot(odst, otype, p0, p1);
-      if (s2 < 0) { defer(); return; }
-      if ((registry >> s2) & 1u) continue;                    // "Non-unique timer" (Instrumenter.scala:1154-1157)
-      if (kind == OP_SCHED_REPEAT) {
-        if (__popc(registry) >= DEMI_TIMERSET_CAP) { defer(); return; }
-        registry |= 1u << s2;
-      }
-      enqueue_timer((uint32_t)s2);
+      schedule_timer(kind, odst, otype, p0, p1);
     }
     if (status || !do_flush) return;
 #pragma unroll 1
@@ -299,6 +320,7 @@ struct LaneMachine {
   // Cancellable.cancel(): Instrumenter.cancelTimer (Instrumenter.scala:159-168) ->
   // RandomScheduler.notify_timer_cancel (RandomScheduler.scala:525-534)
   __device__ __forceinline__ void cancel_timer(uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
     int slot = MODEL::timer_slot(self, type, p0, p1);
     if (slot < 0) { defer(); return; }
     uint32_t bit = 1u << slot;
@@ -403,6 +425,13 @@ struct LaneMachine {
     int slot = MODEL::timer_slot(dst, type, pick.y, pick.z);
     if (slot >= 0 && ((registry >> slot) & 1u)) enqueue_timer((uint32_t)slot);     // re-arm :1008-1016
     if (status) return 0;
+#if DEMI_K1_DIRECT_OUTBOX
+    if constexpr (MODEL::LANE_SENDS_DISTINCT) {
+      LaneDirectOutbox<LaneMachine> direct{this, dst};
+      MODEL::receive(direct, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
+      return 0;
+    }
+#endif
     LaneOutbox<OB> ob;
     ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
     MODEL::receive(ob, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);

@@ -102,23 +102,15 @@ struct Raft5 {
   }
 
   // S is an accessor: s[i] is byte i of this actor's state
-  template <class C, class O>
-  __device__ static __forceinline__ void step_down(O& out, C& c, uint32_t t) {
-    if (c[ROLE] == LEADER) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
+  // returns true when the actor was leader: its heartbeat timer is to be cancelled (the caller issues the operation)
+  template <class C>
+  __device__ static __forceinline__ bool step_down(C& c, uint32_t t) {
+    const bool was_leader = c[ROLE] == LEADER;
     if (t > c[TERM]) { c[TERM] = (uint8_t)t; c[VOTED] = (uint8_t)NONE; }
     c[ROLE] = FOLLOWER;
     c[VOTES] = 0;
+    return was_leader;
   }
-  template <class S, class C, class O>
-  __device__ static __forceinline__ void send_append(O& out, S& s, C& c, uint32_t j) {
-    uint32_t prev = s[NEXT + j];
-    uint32_t pt = prev ? s[LOGTERM + prev - 1] : 0u;
-    uint32_t has = prev < c[LOGLEN] ? 1u : 0u;
-    uint32_t et = has ? s[LOGTERM + prev] : 0u, ev = has ? s[LOGVAL + prev] : 0u;
-    out.send(j, APPEND_ENTRIES, (uint32_t)c[TERM] | (prev << 8) | (pt << 16) | ((uint32_t)c[COMMIT] << 24),
-             has | (et << 8) | (ev << 16));
-  }
-
   // The eight scalar bytes of the state (words 0 and 1) are held in two registers for the duration of a receive():
   // a field access is a bit-field extract / insert instead of a byte load or store in (interleaved) shared memory.
   template <class S>
@@ -149,6 +141,12 @@ struct Raft5 {
     receive_body(out, self, s, c, src, type, p0, p1, flags);
     c.flush(s);
   }
+  // Every handler emits its operations in the order: cancel (step_down), then its sends, then schedule.  The sends
+  // are either one reply to the sender or one message per peer, so the handlers only DESCRIBE their operations and
+  // these leave through ONE cancel, ONE send and ONE schedule site after the switch: engines that apply an operation
+  // as it is issued (the lane engine) then carry one copy of that code instead of one per handler, and the threads of
+  // a warp that handle different message types meet again at those sites.
+  enum { PLAN_NONE = 0, PLAN_REPLY = 1, PLAN_REQUEST_VOTES = 2, PLAN_APPEND_ALL = 3 };
   template <class S, class C, class O>
   __device__ static __forceinline__ void receive_body(O& out, uint32_t self, S& s, C& c, uint32_t src,
                                                       uint32_t type, uint32_t p0, uint32_t p1, uint32_t flags) {
@@ -156,9 +154,11 @@ struct Raft5 {
     const uint32_t last_term = last_idx ? s[LOGTERM + last_idx - 1] : 0u;
     const uint32_t t = p0 & 0xFF;
     if (type != BOOT && type != CLIENT_CMD && c[ROLE] == INIT) return;
+    uint32_t plan = PLAN_NONE, plan_type = 0, plan_p0 = 0, sched = 0;
+    bool cancel_heartbeat = false;
     switch (type) {
       case BOOT:
-        if (c[ROLE] == INIT) { c[ROLE] = FOLLOWER; out.schedule_repeating(ELECTION_TICK, 0, 0); }
+        if (c[ROLE] == INIT) { c[ROLE] = FOLLOWER; sched = ELECTION_TICK; }
         break;
       case CLIENT_CMD:
         if (c[ROLE] == LEADER && c[LOGLEN] < LOG_CAP) {
@@ -175,23 +175,21 @@ struct Raft5 {
         c[ROLE] = CANDIDATE;
         c[VOTED] = (uint8_t)self;
         c[VOTES] = (uint8_t)(1u << self);
-#pragma unroll 1
-        for (uint32_t j = 0; j < 5; j++)
-          if (j != self) out.send(j, REQUEST_VOTE, (uint32_t)c[TERM] | (last_idx << 8) | (last_term << 16), 0);
+        plan = PLAN_REQUEST_VOTES; plan_p0 = (uint32_t)c[TERM] | (last_idx << 8) | (last_term << 16);
         break;
       case REQUEST_VOTE: {
         uint32_t li = (p0 >> 8) & 0xFF, lt = (p0 >> 16) & 0xFF;
-        if (t > c[TERM]) step_down(out, c, t);
+        if (t > c[TERM]) cancel_heartbeat = step_down(c, t);
         bool up_to_date = lt > last_term || (lt == last_term && li >= last_idx);
         bool can_vote = (c[VOTED] == NONE || c[VOTED] == src) || (flags & BUG_DOUBLE_VOTE);
         uint32_t grant = (t == c[TERM] && can_vote && up_to_date) ? 1u : 0u;
         if (grant) { c[VOTED] = (uint8_t)src; c[HEARD] = 1; }
-        out.send(src, VOTE_REPLY, (uint32_t)c[TERM] | (grant << 8), 0);
+        plan = PLAN_REPLY; plan_type = VOTE_REPLY; plan_p0 = (uint32_t)c[TERM] | (grant << 8);
         break;
       }
       case VOTE_REPLY: {
         uint32_t g = (p0 >> 8) & 1u;
-        if (t > c[TERM]) { step_down(out, c, t); break; }
+        if (t > c[TERM]) { cancel_heartbeat = step_down(c, t); break; }
         if (c[ROLE] == CANDIDATE && t == c[TERM] && g) {
           c[VOTES] |= (uint8_t)(1u << src);
           if (__popc((uint32_t)c[VOTES]) >= 3) {
@@ -202,27 +200,23 @@ struct Raft5 {
               s[LOGVAL + c[LOGLEN]] = (uint8_t)(0x80u | self);
               c[LOGLEN]++;
             }
-#pragma unroll 1
-            for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, c, j);
-            out.schedule_repeating(HEARTBEAT_TICK, 0, 0);
+            plan = PLAN_APPEND_ALL; sched = HEARTBEAT_TICK;   // AppendEntries to every peer, then the heartbeat timer
           }
         }
         break;
       }
       case HEARTBEAT_TICK:
-        if (c[ROLE] == LEADER) {
-#pragma unroll 1
-          for (uint32_t j = 0; j < 5; j++) if (j != self) send_append(out, s, c, j);
-        }
+        if (c[ROLE] == LEADER) plan = PLAN_APPEND_ALL;
         break;
       case APPEND_ENTRIES: {
         uint32_t prev = (p0 >> 8) & 0xFF, pt = (p0 >> 16) & 0xFF, lc = (p0 >> 24) & 0xFF;
         uint32_t has = p1 & 1u, et = (p1 >> 8) & 0xFF, ev = (p1 >> 16) & 0xFF;
-        if (t < c[TERM]) { out.send(src, APPEND_REPLY, (uint32_t)c[TERM], 0); break; }
-        if (t > c[TERM] || c[ROLE] != FOLLOWER) step_down(out, c, t);
+        plan = PLAN_REPLY; plan_type = APPEND_REPLY;
+        if (t < c[TERM]) { plan_p0 = (uint32_t)c[TERM]; break; }
+        if (t > c[TERM] || c[ROLE] != FOLLOWER) cancel_heartbeat = step_down(c, t);
         c[HEARD] = 1;
         bool ok = prev <= c[LOGLEN] && (prev == 0 || s[LOGTERM + prev - 1] == pt);
-        if (!ok) { out.send(src, APPEND_REPLY, (uint32_t)c[TERM], 0); break; }
+        if (!ok) { plan_p0 = (uint32_t)c[TERM]; break; }
         uint32_t mi = prev;
         if (has) {
           if (c[LOGLEN] > prev && s[LOGTERM + prev] != et) {          // conflict: truncate
@@ -237,12 +231,12 @@ struct Raft5 {
         }
         uint32_t nc = lc < mi ? lc : mi;
         if (nc > c[COMMIT]) c[COMMIT] = (uint8_t)nc;
-        out.send(src, APPEND_REPLY, (uint32_t)c[TERM] | (1u << 8) | (mi << 16), 0);
+        plan_p0 = (uint32_t)c[TERM] | (1u << 8) | (mi << 16);
         break;
       }
       case APPEND_REPLY: {
         uint32_t ok = (p0 >> 8) & 1u, mi = (p0 >> 16) & 0xFF;
-        if (t > c[TERM]) { step_down(out, c, t); break; }
+        if (t > c[TERM]) { cancel_heartbeat = step_down(c, t); break; }
         if (c[ROLE] != LEADER || t != c[TERM]) break;
         if (ok) {
           if (mi > s[MATCH + src]) s[MATCH + src] = (uint8_t)mi;
@@ -260,6 +254,25 @@ struct Raft5 {
       }
       default: break;
     }
+    if (cancel_heartbeat) out.cancel_timer(HEARTBEAT_TICK, 0, 0);
+    if (plan != PLAN_NONE) {
+#pragma unroll 1
+      for (uint32_t j = (plan == PLAN_REPLY ? src : 0u), end = (plan == PLAN_REPLY ? src + 1u : 5u); j < end; j++) {
+        if (plan != PLAN_REPLY && j == self) continue;
+        uint32_t q0 = plan_p0, q1 = 0, qt = plan == PLAN_REPLY ? plan_type : (uint32_t)REQUEST_VOTE;
+        if (plan == PLAN_APPEND_ALL) {
+          const uint32_t prev = s[NEXT + j];
+          const uint32_t pt = prev ? s[LOGTERM + prev - 1] : 0u;
+          const uint32_t has = prev < c[LOGLEN] ? 1u : 0u;
+          const uint32_t et = has ? s[LOGTERM + prev] : 0u, ev = has ? s[LOGVAL + prev] : 0u;
+          qt = APPEND_ENTRIES;
+          q0 = (uint32_t)c[TERM] | (prev << 8) | (pt << 16) | ((uint32_t)c[COMMIT] << 24);
+          q1 = has | (et << 8) | (ev << 16);
+        }
+        out.send(j, qt, q0, q1);
+      }
+    }
+    if (sched) out.schedule_repeating(sched, 0, 0);
   }
 
   // lanes 0..9 each own one unordered pair (i<j).  code 1: two leaders in one
