@@ -146,7 +146,10 @@ struct LaneMachine {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
   static constexpr int OB = MODEL::LANE_OUTBOX;
-  static constexpr int WORDS = N * SW + OB * 3 + N;    // states + outbox + partition rows
+  // the outbox is staged in shared memory only when receive()'s operations are not applied as they are issued
+  static constexpr bool DIRECT = DEMI_K1_DIRECT_OUTBOX && MODEL::LANE_SENDS_DISTINCT;
+  static constexpr int OBW = DIRECT ? 0 : OB * 3;
+  static constexpr int WORDS = N * SW + OBW + N;       // states + outbox + partition rows
 
   uint32_t* smw;             // &smem[tid]; word w at smw[w*BD]
   uint4* pend;               // entry i at pend[i*32]
@@ -166,7 +169,7 @@ struct LaneMachine {
   uint32_t inaccessible, killed;
   uint64_t thash;
 
-  __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OB * 3 + a) * BD]; }
+  __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OBW + a) * BD]; }
   __device__ __forceinline__ LaneState actor(uint32_t a) { return LaneState{smw + a * SW * BD, BD}; }
 
   __device__ __forceinline__ void defer() { status = LANE_DEFER; }
@@ -294,14 +297,16 @@ struct LaneMachine {
   // ExternalEventInjector.send_external_messages (ExternalEventInjector.scala:306-365).  Two loops, so that the
   // lanes of a warp reconverge between the phases and their flush items are processed together.
   __device__ __forceinline__ void drain(uint32_t n_ops, uint32_t self, bool do_flush) {
-    uint32_t* ob = smw + N * SW * BD;
+    if constexpr (!DIRECT) {
+      uint32_t* ob = smw + N * SW * BD;
 #pragma unroll 1
-    for (uint32_t i = 0; i < n_ops && !status; i++) {
-      const uint32_t w0 = ob[(i * 3) * BD], p0 = ob[(i * 3 + 1) * BD], p1 = ob[(i * 3 + 2) * BD];
-      const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-      if (kind == OP_SEND) { actor_send_produced(self, odst, otype, p0, p1); continue; }
-      if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
-      schedule_timer(kind, odst, otype, p0, p1);
+      for (uint32_t i = 0; i < n_ops && !status; i++) {
+        const uint32_t w0 = ob[(i * 3) * BD], p0 = ob[(i * 3 + 1) * BD], p1 = ob[(i * 3 + 2) * BD];
+        const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+        if (kind == OP_SEND) { actor_send_produced(self, odst, otype, p0, p1); continue; }
+        if (kind == OP_CANCEL) { cancel_timer(odst, otype, p0, p1); continue; }
+        schedule_timer(kind, odst, otype, p0, p1);
+      }
     }
     if (status || !do_flush) return;
 #pragma unroll 1
@@ -329,10 +334,17 @@ struct LaneMachine {
     registry &= ~bit;
     for (uint32_t i = 0; i < tosend.n; i++)           // handle_timer_cancel (ExternalEventInjector.scala:601-610)
       if (tosend.get(i) == (uint32_t)slot) { tosend.remove_at(i); return; }
-    for (uint32_t i = 0; i < n_pending; i++) {        // FullyRandom.remove (RandomScheduler.scala:653-664)
-      uint4 q = ld_l2_hint(pend + i * 32, pol);
-      if (hdr_src(q.x) == DEMI_DEADLETTERS && hdr_dst(q.x) == self && hdr_type(q.x) == type &&
-          q.y == p0 && q.z == p1) { pending_remove_at(i); return; }
+    // FullyRandom.remove (RandomScheduler.scala:653-664): first match in array order.  Four entries are fetched per
+    // step so that their latencies overlap (this scan was 6 % of the kernel's stall samples when it fetched one).
+    const uint32_t want = make_hdr(DEMI_DEADLETTERS, self, type, 0);
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_pending; i += 4) {
+      uint4 q[4];
+#pragma unroll
+      for (uint32_t k = 0; k < 4; k++) q[k] = (i + k < n_pending) ? ld_l2_hint(pend + (i + k) * 32, pol) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (uint32_t k = 0; k < 4; k++)
+        if ((q[k].x & 0x00FFFFFFu) == want && q[k].y == p0 && q[k].z == p1) { pending_remove_at(i + k); return; }
     }
   }
 
@@ -425,13 +437,11 @@ struct LaneMachine {
     int slot = MODEL::timer_slot(dst, type, pick.y, pick.z);
     if (slot >= 0 && ((registry >> slot) & 1u)) enqueue_timer((uint32_t)slot);     // re-arm :1008-1016
     if (status) return 0;
-#if DEMI_K1_DIRECT_OUTBOX
-    if constexpr (MODEL::LANE_SENDS_DISTINCT) {
+    if constexpr (DIRECT) {
       LaneDirectOutbox<LaneMachine> direct{this, dst};
       MODEL::receive(direct, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
       return 0;
     }
-#endif
     LaneOutbox<OB> ob;
     ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
     MODEL::receive(ob, dst, actor(dst), src, type, pick.y, pick.z, A->model_flags);
@@ -516,8 +526,11 @@ struct LaneMachine {
   }
 };
 
+#ifndef DEMI_K1_MIN_BLOCKS
+#define DEMI_K1_MIN_BLOCKS 3
+#endif
 template <class MODEL, int BD, int LPCAP>
-__global__ void __launch_bounds__(BD, MODEL::N_ACTORS <= 8 ? 768 / BD : 3)
+__global__ void __launch_bounds__(BD, DEMI_K1_MIN_BLOCKS)
 fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   using M = LaneMachine<MODEL, BD, LPCAP>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
