@@ -59,11 +59,11 @@ static const Variant* pick_variant(int model, uint32_t pcap, uint32_t tcap, bool
 }
 
 // lane-engine table
-struct LaneVariant { int model; int bd; uint32_t lpcap; kernel_fn fn; size_t smem_per_block; };
+struct LaneVariant { int model; int bd; uint32_t lpcap; kernel_fn fn; kernel_fn fn_rec; size_t smem_per_block; };
 template <class MODEL, int BD, int LPCAP>
 static LaneVariant make_lane_variant() {
   using M = LaneMachine<MODEL, BD, LPCAP>;
-  return LaneVariant{MODEL::ID, BD, (uint32_t)LPCAP, fuzz_lane_kernel<MODEL, BD, LPCAP>,
+  return LaneVariant{MODEL::ID, BD, (uint32_t)LPCAP, fuzz_lane_kernel<MODEL, BD, LPCAP>, fuzz_lane_kernel<MODEL, BD, LPCAP, true>,
                      (size_t)M::WORDS * BD * sizeof(uint32_t)};
 }
 static const LaneVariant* pick_lane_variant(const demi_handle* h);
@@ -111,6 +111,7 @@ extern "C" int32_t demi_create(const demi_config* cfg, demi_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->rec_counts_dev, 4 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->ovf_count, sizeof(uint32_t));
   if (getenv("DEMI_DISABLE_LANE_ENGINE")) h->use_lane_engine = 0;
+  if (const char* e = getenv("DEMI_LANE_PENDING_CAP")) h->lane_pending_cap = (uint32_t)atoi(e);   // tests: make the lane engine defer early
   if (e != cudaSuccess) {
     fail(nullptr, DEMI_ERR_CUDA, "demi_create: %s", cudaGetErrorString(e));
     demi_destroy(h);                       // frees whatever was created before the failure
@@ -351,6 +352,38 @@ extern "C" int32_t demi_fuzz_batch_dev(demi_handle* h, const demi_fuzz_params* p
   return launch_fuzz(h, p, out_dev, stream, true);
 }
 
+// One launch of the lane engine over `n_items` work items; what it defers is appended to h->ovf_list / h->ovf_count.
+static int32_t launch_lane(demi_handle* h, const LaneVariant* lv, kernel_fn lfn, const KernelArgs& base, uint64_t n_items, cudaStream_t s) {
+  const size_t lsmem = lv->smem_per_block;
+  int bps = 0;
+  {
+    auto it = h->occupancy.find((const void*)lfn);
+    if (it == h->occupancy.end()) {
+      CUDA_TRY(h, cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+      CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lfn, lv->bd, lsmem));
+      h->occupancy[(const void*)lfn] = bps;
+    } else bps = it->second;
+  }
+  if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "lane kernel does not fit on an SM");
+  uint64_t want = (n_items + lv->bd - 1) / lv->bd;
+  int lgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * bps));
+  const uint64_t lwarps = (uint64_t)lgrid * (lv->bd / 32);
+  int32_t rc2;
+  if ((rc2 = ensure(h, (void**)&h->lane_pend, &h->lane_pend_bytes, lwarps * lv->lpcap * 32 * sizeof(uint4))) != DEMI_OK) return rc2;
+  if ((rc2 = ensure(h, (void**)&h->ovf_list, &h->ovf_list_bytes, std::max<size_t>(n_items * sizeof(uint32_t), 64))) != DEMI_OK) return rc2;
+  CUDA_TRY(h, cudaMemsetAsync(h->ovf_count, 0, sizeof(uint32_t), s));
+  KernelArgs la = base;
+  la.lane_pend = h->lane_pend;
+  la.ext_sends = h->ext_sends_dev;
+  la.has_partitions = h->has_partitions ? 1u : 0u;
+  la.ovf_list = h->ovf_list; la.ovf_count = h->ovf_count;
+  if (h->lane_pending_cap) la.pending_cap = std::min(la.pending_cap, h->lane_pending_cap);     // deferring is always exact
+  lfn<<<lgrid, lv->bd, lsmem, s>>>(la);
+  CUDA_TRY(h, cudaGetLastError());
+  h->perf.kernel_launches++;
+  return DEMI_OK;
+}
+
 static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_dev, void* stream, bool reset_counters) {
   if (!h) return DEMI_ERR_INVALID;
   if (!out_dev) return fail(h, DEMI_ERR_INVALID, "demi_fuzz_batch_dev: null output");
@@ -369,33 +402,8 @@ static int32_t launch_fuzz(demi_handle* h, const demi_fuzz_params* p, void* out_
   const LaneVariant* lv = pick_lane_variant(h);
   if (lv) {
     // K1-lane handles every prefix it can prove exact; the rest are deferred to the warp engine
-    const size_t lsmem = lv->smem_per_block;
-    const kernel_fn lfn = lv->fn;
-    int bps = 0;
-    {
-      auto it = h->occupancy.find((const void*)lfn);
-      if (it == h->occupancy.end()) {
-        CUDA_TRY(h, cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lfn, lv->bd, lsmem));
-        h->occupancy[(const void*)lfn] = bps;
-      } else bps = it->second;
-    }
-    if (bps < 1) return fail(h, DEMI_ERR_CAPACITY, "lane kernel does not fit on an SM");
-    uint64_t want = (p->n_prefixes + lv->bd - 1) / lv->bd;
-    int lgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * bps));
-    const uint64_t lwarps = (uint64_t)lgrid * (lv->bd / 32);
-    int32_t rc2;
-    if ((rc2 = ensure(h, (void**)&h->lane_pend, &h->lane_pend_bytes, lwarps * lv->lpcap * 32 * sizeof(uint4))) != DEMI_OK) return rc2;
-    if ((rc2 = ensure(h, (void**)&h->ovf_list, &h->ovf_list_bytes, std::max<size_t>(p->n_prefixes * sizeof(uint32_t), 64))) != DEMI_OK) return rc2;
-    CUDA_TRY(h, cudaMemsetAsync(h->ovf_count, 0, sizeof(uint32_t), s));
-    KernelArgs la = plan.args;
-    la.lane_pend = h->lane_pend;
-    la.ext_sends = h->ext_sends_dev;
-    la.has_partitions = h->has_partitions ? 1u : 0u;
-    la.ovf_list = h->ovf_list; la.ovf_count = h->ovf_count;
-    lfn<<<lgrid, lv->bd, lsmem, s>>>(la);
-    CUDA_TRY(h, cudaGetLastError());
-    h->perf.kernel_launches++;
+    int32_t rc2 = launch_lane(h, lv, lv->fn, plan.args, p->n_prefixes, s);
+    if (rc2 != DEMI_OK) return rc2;
     plan.args.index_list = h->ovf_list;
     plan.args.index_count = h->ovf_count;
   }
@@ -634,10 +642,18 @@ extern "C" int32_t demi_fuzz_provenance(demi_handle* h, const demi_fuzz_params* 
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, s);
     if (h->cfg.model == DEMI_MODEL_IR) ir_bind(h->ir_dev, s);
-    plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
-    e = cudaGetLastError();
-    h->perf.kernel_launches++;
-    if (e == cudaSuccess) {
+    // the lane engine records every execution it can prove exact; the slots it defers go to the general engine
+    const LaneVariant* lv = pick_lane_variant(h);
+    if (lv) {
+      rc = launch_lane(h, lv, lv->fn_rec, plan.args, n, s);
+      plan.args.pos_list = h->ovf_list; plan.args.pos_count = h->ovf_count;
+    }
+    if (rc == DEMI_OK) {
+      plan.v->fn<<<plan.grid, WARPS * 32, plan.smem, s>>>(plan.args);
+      e = cudaGetLastError();
+      h->perf.kernel_launches++;
+    }
+    if (rc == DEMI_OK && e == cudaSuccess) {
       ProvArgs a{};
       a.events = (const demi_event*)buf; a.ev_stride = ev_cap;
       a.parent = (const uint16_t*)d_par; a.par_stride = node_cap;

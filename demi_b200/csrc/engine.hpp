@@ -41,6 +41,7 @@ struct demi_handle {
   uint32_t* ovf_count = nullptr;
   uint16_t* fifo_scratch = nullptr; size_t fifo_scratch_bytes = 0;
   int use_lane_engine = 1;
+  uint32_t lane_pending_cap = 0;      // DEMI_LANE_PENDING_CAP (tests): the lane engine defers beyond this many pending messages
   uint32_t* rec_counts_dev = nullptr;
   void* prov_scratch = nullptr; size_t prov_scratch_bytes = 0;
   void* dpor_buf[24] = {}; size_t dpor_buf_bytes[24] = {};     // K3 per-search structures (capi_dpor.cu)

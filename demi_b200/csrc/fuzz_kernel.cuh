@@ -30,10 +30,12 @@ fuzz_kernel(const __grid_constant__ KernelArgs args) {
     m.f_next = m.f_head = m.f_tail = m.f_pairs = nullptr;
   }
 
-  const uint64_t count = args.index_list ? (uint64_t)(*args.index_count) : args.n_prefixes;
+  const bool by_pos = RECORD && args.pos_list;      // the slots the lane engine's recording launch deferred
+  const uint64_t count = by_pos ? (uint64_t)(*args.pos_count) : args.index_list ? (uint64_t)(*args.index_count) : args.n_prefixes;
   unsigned long long my_steps = 0, my_viol = 0;
 
-  for (uint64_t it = gw; it < count; it += total_warps) {
+  for (uint64_t k = gw; k < count; k += total_warps) {
+    const uint64_t it = by_pos ? (uint64_t)args.pos_list[k] : k;
     const uint64_t idx = args.index_list ? (uint64_t)args.index_list[it] : it;
     demi_fuzz_result r;
     if (RECORD) m.rec_ev = args.rec_events + it * (uint64_t)args.rec_cap;

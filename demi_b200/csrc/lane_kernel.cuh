@@ -141,7 +141,8 @@ struct LaneDirectOutbox {
   __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { m->cancel_timer(self, type, p0, p1); }
 };
 
-template <class MODEL, int BD, int LPCAP>
+// REC: the execution's EventTrace and DepTracker parents are written out (provenance batches, demi_fuzz_provenance)
+template <class MODEL, int BD, int LPCAP, bool REC = false>
 struct LaneMachine {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
@@ -153,6 +154,7 @@ struct LaneMachine {
 
   uint32_t* smw;             // &smem[tid]; word w at smw[w*BD]
   uint4* pend;               // entry i at pend[i*32]
+  uint4* rec_ev; uint16_t* rec_par;   // REC: this execution's EventTrace slot and parent array
   uint64_t pol;              // L2 cache policy of the pending array
   const KernelArgs* A;
 
@@ -179,6 +181,11 @@ struct LaneMachine {
                                                uint32_t p0, uint32_t p1, uint32_t uniq, uint32_t node, uint32_t parent) {
     uint32_t w0 = kind | (src << 8) | (dst << 16) | (type << 24);
     thash += demi_event_term(w0, p0, p1, uniq | (node << 16), n_events, parent);
+    if (REC) {
+      if (n_events >= A->rec_cap) { defer(); return; }
+      rec_ev[n_events] = make_uint4(w0, p0, p1, uniq | (node << 16));
+      if (kind == DEMI_EV_MSG_SEND && node < A->rec_parent_cap) rec_par[node] = (uint16_t)parent;   // DepTracker edge
+    }
     n_events++;
   }
 
@@ -529,10 +536,12 @@ struct LaneMachine {
 #ifndef DEMI_K1_MIN_BLOCKS
 #define DEMI_K1_MIN_BLOCKS 3
 #endif
-template <class MODEL, int BD, int LPCAP>
+// REC launches walk a work list (`index_list`): slot `it` of the list owns rec_events[it*rec_cap ..), rec_parent[it*cap ..),
+// rec_counts[it*4 ..) and results[it]; a deferred slot is handed to the general engine by POSITION (ovf_list holds `it`).
+template <class MODEL, int BD, int LPCAP, bool REC = false>
 __global__ void __launch_bounds__(BD, DEMI_K1_MIN_BLOCKS)
 fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
-  using M = LaneMachine<MODEL, BD, LPCAP>;
+  using M = LaneMachine<MODEL, BD, LPCAP, REC>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
   const uint32_t tid = threadIdx.x;
   const uint64_t gthread = (uint64_t)blockIdx.x * BD + tid;
@@ -544,18 +553,26 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
   m.pend = args.lane_pend + gwarp * (uint64_t)LPCAP * 32 + (tid & 31);
   m.A = &args;
   m.pol = l2_evict_last_policy();
+  m.rec_ev = nullptr; m.rec_par = nullptr;
 
+  const uint64_t count = (REC && args.index_list) ? (uint64_t)(*args.index_count) : args.n_prefixes;
   unsigned long long my_steps = 0, my_viol = 0, my_defer = 0;
-  for (uint64_t idx = gthread; idx < args.n_prefixes; idx += total) {
+  for (uint64_t it = gthread; it < count; it += total) {
+    const uint64_t idx = (REC && args.index_list) ? (uint64_t)args.index_list[it] : it;
+    if (REC) {
+      m.rec_ev = reinterpret_cast<uint4*>(args.rec_events + it * (uint64_t)args.rec_cap);
+      m.rec_par = args.rec_parent + it * (uint64_t)args.rec_parent_cap;
+      m.rec_par[0] = 0;
+    }
     demi_fuzz_result r;
     m.run(args.seed_base + (int64_t)idx, r);
     if (r.status == LANE_DEFER) {
       uint32_t pos = atomicAdd(args.ovf_count, 1u);
-      args.ovf_list[pos] = (uint32_t)idx;
+      args.ovf_list[pos] = (uint32_t)(REC ? it : idx);
       my_defer++;
     } else {
       // written once, never re-read here: streaming stores, so that the records do not push the pending arrays out of L2
-      uint4* dst = reinterpret_cast<uint4*>(args.results + idx);
+      uint4* dst = reinterpret_cast<uint4*>(args.results + (REC ? it : idx));
       const uint4 r0 = make_uint4(r.violation, r.steps, (uint32_t)r.state_hash, (uint32_t)(r.state_hash >> 32));
       const uint4 r1 = make_uint4((uint32_t)r.trace_hash, (uint32_t)(r.trace_hash >> 32), (uint32_t)r.n_nodes | ((uint32_t)r.n_events << 16),
                                   (uint32_t)r.max_pending | ((uint32_t)r.status << 16));
@@ -564,6 +581,15 @@ fuzz_lane_kernel(const __grid_constant__ KernelArgs args) {
 #else
       dst[0] = r0; dst[1] = r1;
 #endif
+      if (REC) {
+        uint32_t aff = 0;
+        if (r.status == 0 && r.violation) {      // ViolationFingerprint.affectedNodes of the violation the execution stopped on
+          uint32_t st[M::N * M::SW];
+          for (uint32_t i = 0; i < (uint32_t)(M::N * M::SW); i++) st[i] = m.smw[i * BD];
+          aff = MODEL::affected(st, args.model_flags, r.violation);
+        }
+        reinterpret_cast<uint4*>(args.rec_counts)[it] = make_uint4(m.n_events, m.n_nodes, aff, r.violation);
+      }
       my_steps += r.steps;
       my_viol += r.violation ? 1u : 0u;
     }

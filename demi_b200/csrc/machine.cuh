@@ -143,6 +143,9 @@ struct KernelArgs {
   // tiering: if `index_list` != null the launch handles prefixes index_list[0..*index_count)
   const uint32_t* index_list;
   const uint32_t* index_count;
+  // recording launches only: if `pos_list` != null, handle just the work-list POSITIONS pos_list[0..*pos_count)
+  const uint32_t* pos_list;
+  const uint32_t* pos_count;
   // prefixes that overflowed THIS tier are appended here (may be null => final tier)
   uint32_t* ovf_list;
   uint32_t* ovf_count;

@@ -93,3 +93,34 @@ def test_fuzz_provenance_batch_matches_oracle(eng):
     assert (out["n_kept"][:len(viol[:300])] > 0).all() and (out["n_kept"][-5:] == 0).all()
     # pruning helps: it removes a real share of the deliveries
     assert out["n_kept"][:300].sum() < 0.9 * out["n_trace"][:300].sum()
+
+
+def test_fuzz_provenance_slots_deferred_by_the_lane_engine(monkeypatch):
+    """The lane engine records what it can prove exact; slots it defers (here: more than 24 pending messages, a bound
+    lowered for the test) are recorded by the general engine, addressed by work-list position.  Both kinds in one
+    batch, against the oracle."""
+    monkeypatch.setenv("DEMI_LANE_PENDING_CAP", "24")
+    ext = D.pack_externals(D.raft5_program())
+    eng2 = D.Engine(D.SchedulerConfig(N.MODEL_RAFT5, model_flags=1))
+    eng2.set_externals(ext)
+    n, maxm, interval = 20000, 50, 5
+    res = eng2.fuzz_batch(1, n, maxm, interval)
+    assert 0 < eng2.stats().deferred < n
+    cpu = O.fuzz_batch(N.MODEL_RAFT5, ext, 1, n, maxm, interval, model_flags=1)
+    assert (res == cpu).all()
+    big = np.nonzero((res["violation"] != 0) & (res["max_pending"] > 24))[0].astype(np.uint32)      # deferred
+    small = np.nonzero((res["violation"] != 0) & (res["max_pending"] <= 24))[0].astype(np.uint32)   # recorded by the lane engine
+    assert len(big) > 20 and len(small) > 20
+    idx = np.empty(0, dtype=np.uint32)
+    for a, b in zip(big[:60], small[:60]):          # interleaved, so positions and prefix indexes differ
+        idx = np.append(idx, [b, a]).astype(np.uint32)
+    keep, out, rec = eng2.fuzz_provenance(1, idx, maxm, interval)
+    assert np.array_equal(rec["trace_hash"], res["trace_hash"][idx])
+    assert np.array_equal(rec["violation"], res["violation"][idx])
+    for j, i in enumerate(idx):
+        k, o = O.fuzz_provenance(N.MODEL_RAFT5, ext, 1 + int(i), maxm, interval, keep.shape[1], model_flags=1)
+        assert o["status"] == out[j]["status"] == 0
+        assert np.array_equal(k, keep[j]), int(i)
+        for f in ("violation", "affected_mask", "n_trace", "n_kept"):
+            assert o[f] == out[j][f], (f, int(i))
+    eng2.close()
