@@ -149,6 +149,15 @@ class Engine {
     throw Error(rc, msg);
   }
   demi_handle* handle() const { return h; }
+  // an application model as data (demi_model_ir.h) for SchedulerConfig.model == 100; actor / message names as in the blob
+  void load_model(const std::vector<uint32_t>& blob) { check(demi_load_model(h, blob.data(), blob.size() * sizeof(uint32_t))); }
+  int32_t actor_index(const std::string& name) const { return demi_actor_index(h, name.c_str()); }
+  std::string actor_name(int32_t idx) const { const char* n = demi_actor_name(h, idx); return n ? n : ""; }
+  // FullyRandom's userDefinedFilter (RandomScheduler.scala:666-684) as rules; an empty list removes it
+  void set_user_filter(const std::vector<demi_filter_rule>& rules) { check(demi_set_user_filter(h, rules.data(), (uint32_t)rules.size())); }
+  // UnmodifiedEventDag.conjoinAtoms (minification/Util.scala:167-178): DDMin treats the two externals as one atom
+  void conjoin_atoms(uint32_t i1, uint32_t i2) { check(demi_conjoin_atoms(h, i1, i2)); }      // indices into the trace's externals
+  demi_perf stats() const { demi_perf p{}; demi_stats(h, &p); return p; }
   const SchedulerConfig cfg;
  private:
   demi_handle* h = nullptr;
@@ -444,6 +453,98 @@ class IncrementalDDMin {
   demi_incddmin_out last{};
  private:
   ResumableDPOR& oracle; int32_t maxMaxDistance; uint32_t stopAtSize; MinimizationStats* stats;
+};
+
+// Fuzzer (Fuzzer.scala:24-194): seeded generation of external-event programs.
+struct FuzzerWeights { double kill = 0.01, send = 0.3, wait_quiescence = 0.1, partition = 0.1, unpartition = 0.1; };
+class Fuzzer {
+ public:
+  Fuzzer(uint32_t num_events, FuzzerWeights w, uint32_t send_type, ExternalEvents prefix = {}, ExternalEvents postfix = {})
+      : num_events(num_events), weights(w), send_type(send_type), prefix(std::move(prefix)), postfix(std::move(postfix)) {}
+  ExternalEvents generateFuzzTest(int64_t seed) const {
+    demi_fuzzer_config c{weights.kill, weights.send, weights.wait_quiescence, weights.partition, weights.unpartition, num_events, send_type};
+    ExternalEvents out(prefix.size() + postfix.size() + 2 * (size_t)num_events + 8);
+    uint32_t n = 0;
+    int32_t rc = demi_fuzzer_generate(&c, seed, prefix.data(), (uint32_t)prefix.size(), postfix.data(), (uint32_t)postfix.size(),
+                                      out.data(), (uint32_t)out.size(), &n);
+    if (rc != DEMI_OK) throw Error(rc, demi_last_error(nullptr));
+    out.resize(n);
+    return out;
+  }
+ private:
+  uint32_t num_events; FuzzerWeights weights; uint32_t send_type; ExternalEvents prefix, postfix;
+};
+
+// The flat experiment directory that replaces ExperimentSerializer / ExperimentDeserializer (Serialization.scala:57-254).
+struct Experiment {
+  int32_t model = 0; uint32_t model_flags = 0; ViolationFingerprint violation = 0;
+  ExternalEvents externals; EventTrace trace; std::vector<uint16_t> dep_parent; std::vector<uint64_t> mcs_mask;
+  void save(const std::string& dir) const {
+    demi_experiment e{};
+    e.model = model; e.model_flags = model_flags; e.violation = violation;
+    e.externals = const_cast<demi_ext_event*>(externals.data()); e.n_externals = (uint32_t)externals.size();
+    e.events = const_cast<demi_event*>(trace.data()); e.n_events = (uint32_t)trace.size();
+    e.dep_parent = const_cast<uint16_t*>(dep_parent.data()); e.n_nodes = (uint32_t)dep_parent.size();
+    e.mcs_mask = const_cast<uint64_t*>(mcs_mask.data()); e.mask_words = (uint32_t)mcs_mask.size();
+    int32_t rc = demi_experiment_save(dir.c_str(), &e);
+    if (rc != DEMI_OK) throw Error(rc, demi_last_error(nullptr));
+  }
+  static Experiment load(const std::string& dir) {
+    Experiment x;
+    demi_experiment e{};
+    int32_t rc = demi_experiment_load(dir.c_str(), &e);                 // counts first
+    if (rc != DEMI_OK && rc != DEMI_ERR_CAPACITY) throw Error(rc, demi_last_error(nullptr));
+    x.externals.resize(e.n_externals); x.trace.resize(e.n_events); x.dep_parent.resize(e.n_nodes); x.mcs_mask.resize(e.mask_words);
+    e.externals = x.externals.data(); e.cap_externals = e.n_externals; e.events = x.trace.data(); e.cap_events = e.n_events;
+    e.dep_parent = x.dep_parent.data(); e.cap_nodes = e.n_nodes; e.mcs_mask = x.mcs_mask.data(); e.cap_mask_words = e.mask_words;
+    rc = demi_experiment_load(dir.c_str(), &e);
+    if (rc != DEMI_OK) throw Error(rc, demi_last_error(nullptr));
+    x.model = e.model; x.model_flags = e.model_flags; x.violation = e.violation;
+    return x;
+  }
+};
+
+// ONE DPORwHeuristics.test as a frontier of backtrack points (demi_dpor_frontier); with several devices the frontier is
+// sharded and rebalanced by the library's NCCL steal rounds (demi_create_multi + demi_dpor_frontier_multi).
+class FrontierDPOR {
+ public:
+  explicit FrontierDPOR(const SchedulerConfig& cfg, std::vector<int32_t> devices = {}) {
+    if (devices.empty()) devices.push_back(cfg.device);
+    demi_config dc{};
+    dc.device = devices[0]; dc.model = cfg.model; dc.model_flags = cfg.model_flags; dc.blocked_mask = cfg.blocked_mask;
+    dc.ignore_timers = cfg.ignoreTimers ? 1 : 0; dc.strategy = cfg.strategy;
+    hs.resize(devices.size(), nullptr);
+    int32_t rc = devices.size() == 1 ? demi_create(&dc, &hs[0]) : demi_create_multi(&dc, devices.data(), (int32_t)devices.size(), hs.data());
+    if (rc != DEMI_OK) throw Error(rc, demi_last_error(nullptr));
+  }
+  ~FrontierDPOR() { for (demi_handle* h : hs) demi_destroy(h); }
+  FrontierDPOR(const FrontierDPOR&) = delete;
+  FrontierDPOR& operator=(const FrontierDPOR&) = delete;
+  demi_frontier_params params{/*max_messages*/100, 0, 0, /*width*/16384, /*max_interleavings*/1u << 20, /*explored_slots*/1u << 22,
+                              /*pool_cap*/1u << 24, /*trace_cap*/0, /*rounds_per_exchange*/4, /*steal_max*/4096, 0};
+  void setMaxMessagesToSchedule(int32_t n) { params.max_messages = n; }
+  void trackHistory(bool on) { params.flags = on ? (params.flags & ~DEMI_FR_NO_HISTORY) : (params.flags | DEMI_FR_NO_HISTORY); }
+  // returns the violating interleavings found (all ranks); `results[r]` holds rank r's counters
+  std::vector<demi_dpor_violation> test(const ExternalEvents& events, ViolationFingerprint fp, uint32_t cap_viol = 4096) {
+    params.looking_for = fp;
+    const size_t n = hs.size();
+    results.assign(n, demi_frontier_result{});
+    std::vector<demi_dpor_violation> viol(n * cap_viol);
+    int32_t rc = n == 1 ? demi_dpor_frontier(hs[0], events.data(), (uint32_t)events.size(), &params, &results[0], viol.data(), cap_viol, nullptr, 0)
+                        : demi_dpor_frontier_multi(hs.data(), (int32_t)n, events.data(), (uint32_t)events.size(), &params, results.data(),
+                                                   viol.data(), cap_viol, nullptr, 0);
+    if (rc != DEMI_OK) { std::string msg = demi_last_error(hs[0]); if (rc == DEMI_ERR_INVALID) throw std::invalid_argument(msg); throw Error(rc, msg); }
+    std::vector<demi_dpor_violation> out;
+    for (size_t r = 0; r < n; r++) {
+      const uint64_t k = std::min<uint64_t>(results[r].violations, cap_viol);
+      out.insert(out.end(), viol.begin() + r * cap_viol, viol.begin() + r * cap_viol + k);
+    }
+    return out;
+  }
+  uint64_t interleavings() const { uint64_t t = 0; for (auto& r : results) t += r.interleavings; return t; }
+  std::vector<demi_frontier_result> results;
+ private:
+  std::vector<demi_handle*> hs;
 };
 
 }  // namespace demi

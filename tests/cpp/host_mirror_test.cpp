@@ -92,6 +92,45 @@ int main() {
   ExternalEvents pprog = {Start(0), Start(1), Start(2), Send(2, 1, 0), Send(2, 1, 1), Send(2, 1, 2)};
   auto hit = dpor.test(pprog, 7);
   CHECK(hit.has_value() && hit->code == 7);
-  std::printf("DPOR: violation after %u interleavings\nOK\n", dpor.last.interleavings);
+  std::printf("DPOR: violation after %u interleavings\n", dpor.last.interleavings);
+
+  // one search as a frontier of backtrack points: exhaustive, history on; the same search at width 1 is the reference's order
+  {
+    FrontierDPOR wide(cfg), narrow(cfg);
+    ExternalEvents fprog;
+    for (int a = 0; a < 5; a++) fprog.push_back(Start((uint8_t)a));
+    for (int a = 0; a < 5; a++) fprog.push_back(Send((uint8_t)a, 1, 0x1F));
+    wide.setMaxMessagesToSchedule(36); narrow.setMaxMessagesToSchedule(36);
+    wide.params.width = 4096; narrow.params.width = 1;
+    wide.params.max_interleavings = narrow.params.max_interleavings = 100000;
+    auto vw = wide.test(fprog, 0), vn = narrow.test(fprog, 0);
+    std::printf("frontier DPOR: %llu interleavings in %u rounds (width 4096), %llu in %u rounds (width 1); %zu / %zu violations\n",
+                (unsigned long long)wide.interleavings(), wide.results[0].rounds, (unsigned long long)narrow.interleavings(),
+                narrow.results[0].rounds, vw.size(), vn.size());
+    CHECK(wide.results[0].exhausted && narrow.results[0].exhausted);
+    CHECK(wide.interleavings() == narrow.interleavings() && vw.size() == vn.size());
+  }
+
+  // seeded Fuzzer + the flat experiment directory
+  {
+    ExternalEvents pre;
+    for (int a = 0; a < 5; a++) pre.push_back(Start((uint8_t)a));
+    Fuzzer fz(20, FuzzerWeights(), /*send_type=*/2, pre, {WaitQuiescence()});
+    ExternalEvents a = fz.generateFuzzTest(7), b = fz.generateFuzzTest(7), c = fz.generateFuzzTest(8);
+    CHECK(a.size() == b.size() && a.size() >= pre.size() + 1);
+    bool same = true, differs = a.size() != c.size();
+    for (size_t i = 0; i < a.size(); i++) same = same && a[i].kind == b[i].kind && a[i].a == b[i].a && a[i].p0 == b[i].p0;
+    for (size_t i = 0; i < a.size() && i < c.size(); i++) differs = differs || a[i].kind != c[i].kind || a[i].a != c[i].a || a[i].p0 != c[i].p0;
+    CHECK(same && differs);
+    Experiment x; x.model = cfg.model; x.model_flags = cfg.model_flags; x.violation = fp; x.externals = prog; x.trace = trace;
+    x.dep_parent = sched.depGraph; x.mcs_mask = mask_of(prog, mcs);
+    const std::string dir = "/tmp/demi_b200_cpp_experiment";
+    x.save(dir);
+    Experiment y = Experiment::load(dir);
+    CHECK(y.model == x.model && y.violation == fp && y.externals.size() == prog.size() && y.trace.size() == trace.size());
+    CHECK(y.dep_parent == x.dep_parent && y.mcs_mask == x.mcs_mask && y.trace.back().uniq == trace.back().uniq);
+    std::printf("Fuzzer: %zu externals (seeded, reproducible); experiment directory round trip ok\n", a.size());
+  }
+  std::printf("OK\n");
   return 0;
 }
