@@ -521,12 +521,13 @@ class FrontierDPOR {
   FrontierDPOR(const FrontierDPOR&) = delete;
   FrontierDPOR& operator=(const FrontierDPOR&) = delete;
   demi_frontier_params params{/*max_messages*/100, 0, 0, /*width*/16384, /*max_interleavings*/1u << 20, /*explored_slots*/1u << 22,
-                              /*pool_cap*/1u << 24, /*trace_cap*/0, /*rounds_per_exchange*/4, /*steal_max*/4096, 0};
+                              /*pool_cap*/1u << 22, /*trace_cap (0: max_interleavings + slack)*/0, /*rounds_per_exchange*/4, /*steal_max*/4096, 0};
   void setMaxMessagesToSchedule(int32_t n) { params.max_messages = n; }
   void trackHistory(bool on) { params.flags = on ? (params.flags & ~DEMI_FR_NO_HISTORY) : (params.flags | DEMI_FR_NO_HISTORY); }
   // returns the violating interleavings found (all ranks); `results[r]` holds rank r's counters
   std::vector<demi_dpor_violation> test(const ExternalEvents& events, ViolationFingerprint fp, uint32_t cap_viol = 4096) {
     params.looking_for = fp;
+    if (!params.trace_cap) params.trace_cap = (uint32_t)std::min<uint64_t>(params.max_interleavings + 8ull * params.steal_max + 16, (1u << 28) - 1);
     const size_t n = hs.size();
     results.assign(n, demi_frontier_result{});
     std::vector<demi_dpor_violation> viol(n * cap_viol);
