@@ -24,6 +24,7 @@ struct IrModel {
   static constexpr int ID = DEMI_MODEL_IR;
   static constexpr int LANE_OUTBOX = DEMI_IR_OUTBOX;
   static constexpr int REPLAY_OUTBOX = DEMI_IR_OUTBOX;
+  static constexpr bool REPLAY_DIRECT = false;    // a loaded program can overflow the outbox: DEMI_PS_QUEUE_OVF is observable
 
   __device__ static __forceinline__ uint32_t init_word(uint32_t i, uint32_t) {
     const uint32_t a = i / STATE_WORDS, w = i % STATE_WORDS;

@@ -50,12 +50,25 @@ struct ReplayArgs {
   unsigned long long* counters;   // [0] reproduced, [1] delivered
 };
 
+// receive()'s view when its operations are applied as they are issued (program order is the reference's order:
+// `!`, scheduleOnce and cancel() act synchronously inside receive()); no staging in shared memory.
+template <class M>
+struct ReplayDirectOutbox {
+  M* m; uint32_t self;
+  __device__ __forceinline__ void send(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) { m->event_produced(self, dst, type, p0, p1, false); }
+  __device__ __forceinline__ void schedule_once(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_ONCE, self, type, p0, p1); }
+  __device__ __forceinline__ void schedule_repeating(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_REPEAT, self, type, p0, p1); }
+  __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { m->cancel_timer(self, type, p0, p1); }
+};
+
 template <class MODEL, int BD, bool REC = false>
 struct ReplayMachine {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
   static constexpr int OB = MODEL::REPLAY_OUTBOX;
-  static constexpr int WORDS = N * SW + OB * 3 + N;
+  static constexpr bool DIRECT = MODEL::REPLAY_DIRECT;
+  static constexpr int OBW = DIRECT ? 0 : OB * 3;      // the outbox is staged in shared memory only when it can overflow
+  static constexpr int WORDS = N * SW + OBW + N;
 
   uint32_t* smw;
   const ReplayArgs* A;
@@ -73,7 +86,7 @@ struct ReplayMachine {
   uint32_t rem_cursor;               // next candidate index into ext for `remaining.head`
   uint32_t alive;                    // filterKnownAbsentInternals: actorToAlive
 
-  __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OB * 3 + a) * BD]; }
+  __device__ __forceinline__ uint32_t& part_row(uint32_t a) { return smw[(N * SW + OBW + a) * BD]; }
   __device__ __forceinline__ LaneState actor(uint32_t a) { return LaneState{smw + a * SW * BD, BD}; }
   // externals are consulted in (nearly) increasing index order: keep the current 64-bit word of the mask in registers
   uint32_t mword_idx; uint64_t mword;
@@ -202,6 +215,7 @@ struct ReplayMachine {
   }
   // STSScheduler.notify_timer_cancel (STSScheduler.scala:846-868)
   __device__ __forceinline__ void cancel_timer(uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
     int slot = MODEL::timer_slot(self, type, p0, p1);
     if (slot < 0) { status = DEMI_RS_UNSUPPORTED; return; }
     uint32_t bit = 1u << slot;
@@ -224,29 +238,35 @@ struct ReplayMachine {
     int slot = MODEL::timer_slot(dst, type, p0, p1);
     if (slot >= 0 && ((registry >> slot) & 1u)) handle_timer((uint32_t)slot);
     if (status) return;
-    LaneOutbox<OB> ob;
-    ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
-    MODEL::receive(ob, dst, actor(dst), src, type, p0, p1, A->model_flags);
-    if (ob.overflow) { status = DEMI_PS_QUEUE_OVF; return; }
-    for (uint32_t i = 0; i < ob.n && !status; i++) {
-      uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
-      uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-      if (kind == OP_SEND) {
-        event_produced(dst, odst, otype, q0, q1, false);
-      } else if (kind == OP_CANCEL) {
-        cancel_timer(odst, otype, q0, q1);
-      } else {
-        int s2 = MODEL::timer_slot(odst, otype, q0, q1);
-        if (s2 < 0) { status = DEMI_RS_UNSUPPORTED; break; }
-        if ((registry >> s2) & 1u) continue;
-        if (kind == OP_SCHED_REPEAT) {
-          if (__popc(registry) >= DEMI_TIMERSET_CAP) { status = DEMI_PS_QUEUE_OVF; break; }
-          registry |= 1u << s2;
-        }
-        handle_timer((uint32_t)s2);
+    if constexpr (DIRECT) {
+      ReplayDirectOutbox<ReplayMachine> direct{this, dst};
+      MODEL::receive(direct, dst, actor(dst), src, type, p0, p1, A->model_flags);
+    } else {
+      LaneOutbox<OB> ob;
+      ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
+      MODEL::receive(ob, dst, actor(dst), src, type, p0, p1, A->model_flags);
+      if (ob.overflow) { status = DEMI_PS_QUEUE_OVF; return; }
+      for (uint32_t i = 0; i < ob.n && !status; i++) {
+        uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
+        uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+        if (kind == OP_SEND) event_produced(dst, odst, otype, q0, q1, false);
+        else if (kind == OP_CANCEL) cancel_timer(odst, otype, q0, q1);
+        else schedule_timer(kind, odst, otype, q0, q1);
       }
     }
     flush();     // schedule_new_message begins with send_external_messages (:655)
+  }
+  // scheduler.scheduleOnce / schedule (Instrumenter.scala:1126-1190)
+  __device__ __forceinline__ void schedule_timer(uint32_t kind, uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
+    const int s2 = MODEL::timer_slot(self, type, p0, p1);
+    if (s2 < 0) { status = DEMI_RS_UNSUPPORTED; return; }
+    if ((registry >> s2) & 1u) return;
+    if (kind == OP_SCHED_REPEAT) {
+      if (__popc(registry) >= DEMI_TIMERSET_CAP) { status = DEMI_PS_QUEUE_OVF; return; }
+      registry |= 1u << s2;
+    }
+    handle_timer((uint32_t)s2);
   }
 
   __device__ __forceinline__ void run(uint32_t test_idx, uint32_t generation, demi_replay_result& out) {
@@ -364,7 +384,7 @@ struct ReplayMachine {
 };
 
 template <class MODEL, int BD, bool REC = false>
-__global__ void __launch_bounds__(BD)
+__global__ void __launch_bounds__(BD, (MODEL::REPLAY_DIRECT && MODEL::N_ACTORS <= 8) ? 1024 / BD : 1)
 replay_lane_kernel(const __grid_constant__ ReplayArgs args) {
   using M = ReplayMachine<MODEL, BD, REC>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
