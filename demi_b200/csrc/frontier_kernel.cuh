@@ -97,12 +97,24 @@ __device__ __forceinline__ void fr_log_key(const FrLog& log, unsigned long long 
 }
 
 // ------------------------------------------------------------------ executor
+// receive()'s view when its operations are applied as they are issued (built-in models: a receive() never exceeds the
+// outbox, so nothing observable depends on staging it)
+template <class M>
+struct FrDirectOutbox {
+  M* m; uint32_t self;
+  __device__ __forceinline__ void send(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) { m->event_produced(self, dst, type, p0, p1); }
+  __device__ __forceinline__ void schedule_once(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_ONCE, self, type, p0, p1); }
+  __device__ __forceinline__ void schedule_repeating(uint32_t type, uint32_t p0, uint32_t p1) { m->schedule_timer(OP_SCHED_REPEAT, self, type, p0, p1); }
+  __device__ __forceinline__ void cancel_timer(uint32_t type, uint32_t p0, uint32_t p1) { m->cancel_timer(self, type, p0, p1); }
+};
+
 template <class MODEL, int BD>
 struct FrExec {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
   static constexpr int OB = MODEL::REPLAY_OUTBOX;
-  static constexpr int WORDS = N * SW + OB * 3;
+  static constexpr bool DIRECT = MODEL::REPLAY_DIRECT;
+  static constexpr int WORDS = N * SW + (DIRECT ? 0 : OB * 3);
   static constexpr int NQ = (N + 1) * N;
   static constexpr int QW = (NQ + 31) / 32;
   static constexpr uint32_t NIL = 0xFFFFu;
@@ -154,7 +166,20 @@ struct FrExec {
     event_produced(DEMI_DEADLETTERS, dst, type, p0, p1);
   }
   // DPORwHeuristics.notify_timer_cancel (:961-985)
+  // scheduler.scheduleOnce / schedule (Instrumenter.scala:1126-1190)
+  __device__ __forceinline__ void schedule_timer(uint32_t kind, uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
+    const int s2 = MODEL::timer_slot(self, type, p0, p1);
+    if (s2 < 0) { status = DEMI_DS_UNSUPPORTED; return; }
+    if ((registry >> s2) & 1u) return;                                  // "Non-unique timer"
+    if (kind == OP_SCHED_REPEAT) {
+      if (__popc(registry) >= DEMI_TIMERSET_CAP) { status = DEMI_DS_QUEUE_OVF; return; }
+      registry |= 1u << s2;
+    }
+    timer_send((uint32_t)s2);
+  }
   __device__ __forceinline__ void cancel_timer(uint32_t self, uint32_t type, uint32_t p0, uint32_t p1) {
+    if (status) return;
     const int slot = MODEL::timer_slot(self, type, p0, p1);
     if (slot < 0) { status = DEMI_DS_UNSUPPORTED; return; }
     cancelled |= 1u << slot;
@@ -244,25 +269,21 @@ struct FrExec {
       const int slot = MODEL::timer_slot(dst, type, c.w, p1);
       if (slot >= 0 && ((registry >> slot) & 1u)) timer_send((uint32_t)slot);      // re-arm (Instrumenter.scala:1008-1016)
       if (status) break;
-      LaneOutbox<OB> ob;
-      ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
-      MODEL::receive(ob, dst, actor(dst), src, type, c.w, p1, A->model_flags);
-      if (ob.overflow) { status = DEMI_DS_QUEUE_OVF; break; }
+      if constexpr (DIRECT) {
+        FrDirectOutbox<FrExec> direct{this, dst};
+        MODEL::receive(direct, dst, actor(dst), src, type, c.w, p1, A->model_flags);
+      } else {
+        LaneOutbox<OB> ob;
+        ob.base = smw + N * SW * BD; ob.bd = BD; ob.n = 0; ob.self = dst; ob.overflow = false;
+        MODEL::receive(ob, dst, actor(dst), src, type, c.w, p1, A->model_flags);
+        if (ob.overflow) { status = DEMI_DS_QUEUE_OVF; break; }
 #pragma unroll 1
-      for (uint32_t i = 0; i < ob.n && !status; i++) {
-        const uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
-        const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
-        if (kind == OP_SEND) event_produced(dst, odst, otype, q0, q1);
-        else if (kind == OP_CANCEL) cancel_timer(odst, otype, q0, q1);
-        else {
-          const int s2 = MODEL::timer_slot(odst, otype, q0, q1);
-          if (s2 < 0) { status = DEMI_DS_UNSUPPORTED; break; }
-          if ((registry >> s2) & 1u) continue;                          // "Non-unique timer"
-          if (kind == OP_SCHED_REPEAT) {
-            if (__popc(registry) >= DEMI_TIMERSET_CAP) { status = DEMI_DS_QUEUE_OVF; break; }
-            registry |= 1u << s2;
-          }
-          timer_send((uint32_t)s2);
+        for (uint32_t i = 0; i < ob.n && !status; i++) {
+          const uint32_t w0 = ob.base[(i * 3) * BD], q0 = ob.base[(i * 3 + 1) * BD], q1 = ob.base[(i * 3 + 2) * BD];
+          const uint32_t kind = w0 & 0xFF, odst = (w0 >> 8) & 0xFF, otype = (w0 >> 16) & 0xFF;
+          if (kind == OP_SEND) event_produced(dst, odst, otype, q0, q1);
+          else if (kind == OP_CANCEL) cancel_timer(odst, otype, q0, q1);
+          else schedule_timer(kind, odst, otype, q0, q1);
         }
       }
     }
