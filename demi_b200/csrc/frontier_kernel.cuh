@@ -26,6 +26,7 @@
 //   fr_pack / fr_unpack     a stolen record = point + trace prefix; what moves over NVLink in the steal round.
 #pragma once
 #include "lane_kernel.cuh"
+#include "models/model_traits.cuh"
 #include "models/models.cuh"
 
 namespace demi {
@@ -113,7 +114,7 @@ struct FrExec {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
   static constexpr int OB = MODEL::REPLAY_OUTBOX;
-  static constexpr bool DIRECT = MODEL::REPLAY_DIRECT;
+  static constexpr bool DIRECT = model_replay_direct<MODEL>::value;
   static constexpr int WORDS = N * SW + (DIRECT ? 0 : OB * 3);
   static constexpr int NQ = (N + 1) * N;
   static constexpr int QW = (NQ + 31) / 32;

@@ -38,7 +38,6 @@ struct PingPong3 {
   static constexpr int LANE_OUTBOX = 2;
   static constexpr bool LANE_SENDS_DISTINCT = false;
   static constexpr int REPLAY_OUTBOX = 2;
-  static constexpr bool REPLAY_DIRECT = true;     // a receive() never exceeds the outbox: operations may be applied as issued
   template <class S, class O>
   __device__ static __forceinline__ void receive(O& out, uint32_t self, S st, uint32_t /*src*/,
                                                  uint32_t type, uint32_t p0, uint32_t /*p1*/, uint32_t /*flags*/) {
@@ -93,7 +92,6 @@ struct Raft5 {
   // sends of one delivery are equal and the lane engine's duplicate-send screen is skipped
   static constexpr bool LANE_SENDS_DISTINCT = true;
   static constexpr int REPLAY_OUTBOX = 6;
-  static constexpr bool REPLAY_DIRECT = true;
   // timer universe: (actor, ELECTION_TICK) -> 2*actor, (actor, HEARTBEAT_TICK) -> 2*actor+1
   __device__ static __forceinline__ int timer_slot(uint32_t dst, uint32_t type, uint32_t p0, uint32_t p1) {
     if ((type != ELECTION_TICK && type != HEARTBEAT_TICK) || p0 || p1 || dst >= 5) return -1;
@@ -346,7 +344,6 @@ struct Bcast32 {
       for (uint32_t j = 0; j < 32; j++) if (j != self) out.send(j, FLOOD, p0 - 1, 0);
   }
   static constexpr int REPLAY_OUTBOX = 32;
-  static constexpr bool REPLAY_DIRECT = true;
   static constexpr int LANE_OUTBOX = 32;
   static constexpr bool LANE_SENDS_DISTINCT = false;
   template <class A>

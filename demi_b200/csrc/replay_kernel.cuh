@@ -20,6 +20,7 @@
 // {hdr,p0,p1,generation|count} in HBM, interleaved per warp.
 #pragma once
 #include "lane_kernel.cuh"
+#include "models/model_traits.cuh"
 
 namespace demi {
 
@@ -66,7 +67,7 @@ struct ReplayMachine {
   static constexpr int N = MODEL::N_ACTORS;
   static constexpr int SW = MODEL::STATE_WORDS;
   static constexpr int OB = MODEL::REPLAY_OUTBOX;
-  static constexpr bool DIRECT = MODEL::REPLAY_DIRECT;
+  static constexpr bool DIRECT = model_replay_direct<MODEL>::value;
   static constexpr int OBW = DIRECT ? 0 : OB * 3;      // the outbox is staged in shared memory only when it can overflow
   static constexpr int WORDS = N * SW + OBW + N;
 
@@ -384,7 +385,7 @@ struct ReplayMachine {
 };
 
 template <class MODEL, int BD, bool REC = false>
-__global__ void __launch_bounds__(BD, (MODEL::REPLAY_DIRECT && MODEL::N_ACTORS <= 8) ? 1024 / BD : 1)
+__global__ void __launch_bounds__(BD, (model_replay_direct<MODEL>::value && MODEL::N_ACTORS <= 8) ? 1024 / BD : 1)
 replay_lane_kernel(const __grid_constant__ ReplayArgs args) {
   using M = ReplayMachine<MODEL, BD, REC>;
   extern __shared__ __align__(16) uint32_t lane_smem[];
