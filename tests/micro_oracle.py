@@ -513,6 +513,205 @@ def pingpong_invariant(flags):
     return lambda actors: 7 if (flags & 1) and actors["0"].pongs >= (flags >> 8) else None
 
 
+# ---------------------------------------------------------------- STSScheduler (schedulers/STSScheduler.scala, EventTrace.scala)
+def subsequence_intersection(events, original_externals, subseq, is_external, filter_known_absents):
+    """EventTrace.subsequenceIntersection (EventTrace.scala:290-380) -> filterSends (:382-452) -> filterKnownAbsentInternals
+    (:458-534), as written.  `subseq`: increasing indices into original_externals.  Events are the tuples Execution records."""
+    remaining = [original_externals[i] for i in subseq if original_externals[i][0] != "Send"]
+    result = []
+    for event in events:
+        k = event[0]
+        if not remaining:
+            if k in ("MsgSend", "MsgEvent"):                         # isMessageType
+                result.append(event)
+            elif k not in ("Spawn", "Kill", "Partition", "UnPartition", "HardKill"):   # !isExternal (EventTypes :184-201)
+                result.append(event)
+        else:
+            head = remaining[0]
+            if k == "Kill":
+                if head[0] == "Kill" and head[1] == event[1]:
+                    result.append(event); remaining = remaining[1:]
+            elif k == "Partition":
+                if head[0] == "Partition" and (head[1], head[2]) == (event[1], event[2]):
+                    result.append(event); remaining = remaining[1:]
+            elif k == "UnPartition":
+                if head[0] == "UnPartition" and (head[1], head[2]) == (event[1], event[2]):
+                    result.append(event); remaining = remaining[1:]
+            elif k == "Spawn":
+                if head[0] == "Start" and head[1] == event[1]:
+                    result.append(event); remaining = remaining[1:]
+            elif k == "HardKill":
+                if head[0] == "HardKill" and head[1] == event[1]:
+                    result.append(event); remaining = remaining[1:]
+            else:
+                result.append(event)                                 # "Always include all other internal events"
+    # filterSends: the i-th external MsgSend belongs to the i-th Send of original_externals (FIFO assumption)
+    original_sends = [i for i, e in enumerate(original_externals) if e[0] == "Send"]
+    in_subseq = set(subseq)
+    missing_indices = set(k for k, i in enumerate(original_sends) if i not in in_subseq)
+    msg_send_idx = -1
+    pruned_msg_ids = set()
+    remaining_events = []
+    for e in result:
+        if e[0] == "MsgSend":
+            if is_external(e[3]):
+                msg_send_idx += 1
+                if msg_send_idx not in missing_indices:
+                    remaining_events.append(e)
+                else:
+                    pruned_msg_ids.add(e[4])
+            else:
+                remaining_events.append(e)
+        elif e[0] == "MsgEvent":
+            if e[4] not in pruned_msg_ids:
+                remaining_events.append(e)
+        else:
+            remaining_events.append(e)
+    if not filter_known_absents:
+        return remaining_events
+    # filterKnownAbsentInternals, as written — including that a PartitionEvent marks the pair as NOT partitioned and an
+    # UnPartitionEvent marks it partitioned (:523-528)
+    alive = {DEADLETTERS: True, "Timer": True}
+    partitioned = {}
+    pruned_sends = set()
+    out = []
+    for e in remaining_events:
+        k = e[0]
+        if k == "MsgSend":
+            snd, rcv = e[1], e[2]
+            if alive.get(snd, False) and not partitioned.get((snd, rcv), False):
+                out.append(e)
+            else:
+                pruned_sends.add(e[4])
+        elif k == "MsgEvent":
+            snd, rcv = e[1], e[2]
+            if alive.get(rcv, False) and not partitioned.get((snd, rcv), False) and e[4] not in pruned_sends:
+                out.append(e)
+        elif k == "Spawn":
+            alive[e[1]] = True; out.append(e)
+        elif k == "Kill":
+            alive[e[1]] = False; out.append(e)
+        elif k == "Partition":
+            partitioned[(e[1], e[2])] = False; out.append(e)
+        elif k == "UnPartition":
+            partitioned[(e[1], e[2])] = True; out.append(e)
+        else:
+            out.append(e)
+    return out
+
+
+class STSReplay(Execution):
+    """STSScheduler.test (STSScheduler.scala:199-310) with allowPeek = false, no failure detector, no checkpointing,
+    abortUponDivergence off: advanceReplay (:405-559), event_produced (:561-623), schedule_new_message (:643-776),
+    notify_timer_cancel (:846-868).  The Instrumenter side (`!`, timers, dispatch) is Execution's."""
+
+    def __init__(self, actors, original_events, original_externals, invariant, is_external, filter_known_absents=False,
+                 looking_for=None):
+        Execution.__init__(self, actors, [], 0, -1, 0, invariant, is_external, looking_for=looking_for)
+        self.original_events, self.original_externals = original_events, original_externals
+        self.filterKnownAbsents = filter_known_absents
+        self.pending = {}                        # (snd, rcv) -> {fingerprint -> [(uniq, msg)]}   (:112-114)
+        self.delivered = self.ignored = 0
+
+    # ---- scheduler callbacks
+    def event_produced(self, snd, rcv, msg):     # :561-623
+        self.uniq_counter += 1
+        uniq = self.uniq_counter
+        is_timer = False
+        if msg in self.enqueuedExternalMessages:                     # handle_event_produced: ExternalMessage
+            self.pending.setdefault((snd, rcv), {}).setdefault(msg, []).append((uniq, msg))
+        else:
+            if snd == DEADLETTERS:
+                is_timer = True
+            if not self.crosses_partition(snd, rcv):
+                self.pending.setdefault((snd, rcv), {}).setdefault(msg, []).append((uniq, msg))
+        self.events.append(("MsgSend", "Timer" if is_timer else snd, rcv, msg, uniq, 0))
+
+    def enqueue_timer(self, rcv, msg):           # :870
+        self.handle_timer(rcv, msg)
+
+    def notify_timer_cancel(self, rcv, msg):     # :846-868
+        for i, (s, r, m) in enumerate(self.messagesToSend):          # handle_timer_cancel
+            if r == rcv and m == msg:
+                del self.messagesToSend[i]
+                return
+        h = self.pending.get((DEADLETTERS, rcv))
+        if h is not None and msg in h:
+            q = h[msg]
+            for i, (_, m) in enumerate(q):
+                if m == msg:
+                    del q[i]
+                    break
+            if not q:
+                del h[msg]
+                if not h:
+                    del self.pending[(DEADLETTERS, rcv)]
+
+    def message_pending(self, snd, rcv, msg):    # :381-403
+        self.send_external_messages()
+        h = self.pending.get((snd, rcv))
+        if h is None or msg not in h:
+            return False
+        return rcv not in self.blockedActors
+
+    def advance_replay(self):                    # :405-559
+        while self.traceIdx < len(self.trace):
+            e = self.trace[self.traceIdx]
+            k = e[0]
+            if k == "Spawn":                                         # trigger_start
+                self.events.append(e)
+                self.inaccessible.discard(e[1]); self.killed.discard(e[1]); self.blockedActors.discard(e[1])
+            elif k == "Kill":
+                self.events.append(e)
+                self.killed.add(e[1]); self.inaccessible.add(e[1])
+            elif k == "Partition":
+                self.events.append(e); self.partitioned.add((e[1], e[2]))
+            elif k == "UnPartition":
+                self.events.append(e); self.partitioned.discard((e[1], e[2]))
+            elif k == "MsgSend":
+                if self.is_external(e[3]):                           # enqueue_message(None, receiver, message)
+                    self.enqueuedExternalMessages.append(e[3])
+                    self.messagesToSend.append((None, e[2], e[3]))
+            elif k == "MsgEvent":
+                if self.message_pending(e[1], e[2], e[3]):
+                    return                                           # "Yay, it's already enabled."
+                self.ignored += 1                                    # "Ignoring message"
+            elif k in ("Quiescence", "BeginWaitQuiescence"):
+                self.events.append(e)
+            self.traceIdx += 1
+
+    def schedule_new_message(self):              # :643-776
+        self.send_external_messages()
+        self.advance_replay()
+        self.send_external_messages()
+        if self.traceIdx >= len(self.trace):
+            return None
+        _, snd, rcv, msg, _, _ = self.trace[self.traceIdx]           # a MsgEvent advanceReplay found enabled
+        h = self.pending[(snd, rcv)]
+        q = h[msg]
+        uniq, m = q.pop(0)                                           # Queue.dequeue: oldest first
+        if not q:
+            del h[msg]
+            if not h:
+                del self.pending[(snd, rcv)]
+        self.events.append(("MsgEvent", snd, rcv, m, uniq, 0))
+        self.traceIdx += 1
+        self.delivered += 1
+        return (uniq, None, snd, rcv, m)
+
+    def test(self, subseq):
+        self.trace = subsequence_intersection(self.original_events, self.original_externals, subseq, self.is_external,
+                                              self.filterKnownAbsents)
+        self.traceIdx = 0
+        self.advance_replay()                                        # "Start playing back trace"
+        while True:
+            e = self.schedule_new_message()
+            if e is None:
+                break
+            self.dispatch_new_message(e)
+        return self.violationMatches(self.invariant(self.actors))
+
+
 # ---------------------------------------------------------------- DDMin (minification/DeltaDebugging.scala, Util.scala)
 def split_list(l, split_ways):                   # minification/Util.scala:9-37
     if split_ways < 1:

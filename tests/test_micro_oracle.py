@@ -159,3 +159,69 @@ def test_ddmin2_test_sequence_matches_the_c_oracle(oracle):
         assert sorted(i for i, _ in got) == [i for i in range(len(prog)) if (int(mcs[0]) >> i) & 1]
         assert dd.total_replays == total
         assert [sum(1 << i for i in t) for t in dd.tests] == [int(m[0]) for m in log]
+
+
+def _replay_case(oracle, model, prog, seed, maxm, interval, flags, n_masks, rng, fka_modes=(0, 1), with_wait_quiescence=False):
+    """One recorded execution, many external subsequences: STSScheduler.test restated in Python (straight from
+    STSScheduler.scala / EventTrace.scala) against the C oracle — verdict, delivered / ignored counts and the whole
+    recorded EventTrace of every replay."""
+    ext = D.pack_externals(prog)
+    events = to_prog(prog)
+    ex, v = run_micro(model, prog, seed, maxm, interval, flags)
+    ev, par, r = oracle.fuzz_trace(model, ext, seed, maxm, interval, model_flags=flags)
+    assert [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in ev] == [row[:7] for row in flat(ex.events)]
+    code = int(r["violation"])
+    n_ext = len(ext)
+    full = np.asarray(oracle.full_mask(ext, drop_wait_quiescence=not with_wait_quiescence), dtype=np.uint64).reshape(-1)
+    mw = oracle.mask_words(n_ext)
+    ext_types = (1, 2) if model == N.MODEL_RAFT5 else (1,)
+    checked = 0
+    for t in range(n_masks):
+        keep = rng.random(n_ext) < rng.choice([0.95, 0.8, 0.5, 0.25])
+        if t == 0:
+            keep[:] = True
+        mask = np.zeros(mw, dtype=np.uint64)
+        for i in range(n_ext):
+            if keep[i]:
+                mask[i >> 6] |= np.uint64(1) << np.uint64(i & 63)
+        mask &= full
+        subseq = [i for i in range(n_ext) if (int(mask[i >> 6]) >> (i & 63)) & 1]
+        for fka in fka_modes:
+            if model == N.MODEL_RAFT5:
+                actors = {str(i): M.RaftActor(i, flags) for i in range(5)}
+                inv = M.raft_invariant
+            else:
+                actors = {str(i): M.PingPongActor(i) for i in range(3)}
+                inv = M.pingpong_invariant(flags)
+            sts = M.STSReplay(actors, ex.events, events, inv, lambda m: m[0] in ext_types, filter_known_absents=bool(fka),
+                              looking_for=code or None)
+            got = sts.test(subseq) or 0
+            res, rec = oracle.replay_trace(model, ev, ext, mask, looking_for=code, flags=fka, model_flags=flags)
+            assert int(res["status"]) == 0
+            assert (got, sts.delivered, sts.ignored) == (int(res["violation"]), int(res["delivered"]), int(res["ignored"])), (seed, t, fka)
+            rows = [row[:7] for row in flat(sts.events)]
+            crow = [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in rec]
+            assert rows == crow, (seed, t, fka, next((i for i in range(min(len(rows), len(crow))) if rows[i] != crow[i]), -1))
+            checked += 1
+    return code, checked
+
+
+def test_sts_replay_of_external_subsequences_matches_the_c_oracle(oracle):
+    rng = np.random.default_rng(5)
+    n_checked = n_viol = 0
+    res = oracle.fuzz_batch(N.MODEL_RAFT5, D.pack_externals(D.raft5_program(client_cmds=3)), 1, 600, 60, 5, model_flags=1)
+    seeds = [1 + int(i) for i in np.nonzero(res["violation"])[0][:6]] + [2, 3]
+    for seed in seeds:
+        code, c = _replay_case(oracle, N.MODEL_RAFT5, D.raft5_program(client_cmds=3), seed, 60, 5, 1, 40, rng)
+        n_checked += c; n_viol += bool(code)
+    prog = D.raft5_program(client_cmds=4)[:-1] + [D.WaitQuiescence(), D.Partition(0, 1), D.Kill(2), D.Send(3, 2, 9), D.WaitQuiescence(),
+                                                  D.UnPartition(0, 1), D.Start(2), D.Send(0, 2, 11), D.WaitQuiescence()]
+    for seed in (1, 2, 3, 4):
+        _, c = _replay_case(oracle, N.MODEL_RAFT5, prog, seed, 120, 7, 3, 40, rng)
+        n_checked += c
+    _, c = _replay_case(oracle, N.MODEL_RAFT5, prog, 5, 120, 7, 3, 30, rng, with_wait_quiescence=True)   # WaitQuiescence left in the subsequence
+    n_checked += c
+    for seed in (1, 2, 3):
+        _, c = _replay_case(oracle, N.MODEL_PINGPONG3, D.pingpong3_program(20), seed, -1, 3, 1 | (4 << 8), 30, rng)
+        n_checked += c
+    assert n_viol >= 4 and n_checked >= 1200
