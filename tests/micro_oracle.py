@@ -712,6 +712,248 @@ class STSReplay(Execution):
         return self.violationMatches(self.invariant(self.actors))
 
 
+# ---------------------------------------------------------------- DPORwHeuristics (schedulers/DPORwHeuristics.scala)
+class DPORSearch(object):
+    """DPORwHeuristics.test for external programs of Start / Send events: DefaultBacktrackOrdering, trackHistory on,
+    checkpointing off (invariant at the end of every interleaving), prioritizePendingUponDivergence off, no depth
+    bound.  Two choices the Scala leaves to scala-library internals are fixed as DESIGN.md §6 fixes them: the divergent
+    choice (`pendingEvents.find` over a HashMap, :454-456) takes the first non-empty queue in (sender, receiver) order
+    with deadLetters last, and backtrack points of equal branch depth leave the PriorityQueue oldest first."""
+
+    def __init__(self, make_actors, externals, invariant, max_messages, stop_if_found=True, looking_for=None):
+        self.make_actors, self.externals, self.invariant = make_actors, externals, invariant
+        self.max_messages, self.stopIfViolationFound, self.lookingFor = max_messages, stop_if_found, looking_for
+        # the dependency graph (child -> parent edges), ids from one counter, root = Unique(MsgEvent("null","null",null), 0)
+        self.event = {0: ("null", "null", None)}
+        self.parent_of = {0: None}
+        self.kids = {0: []}
+        self.next_id = 1
+        self.backTrack = []                      # (branchI, seq, (e1, e2), replayThis)
+        self.seq = 0
+        self.explored = set()                    # ExploredTacker: ordered pairs, whatever the index
+        self.interleavingCounter = 0
+        self.shortestTraceSoFar = None
+        self.nextTrace = []
+        self.races = 0
+        self.traces = []                         # every finished currentTrace (with the root at index 0)
+        self.violations = []                     # (interleaving index, code)
+
+    # ---- graph helpers
+    def path_from_root(self, n):
+        out = []
+        while n is not None:
+            out.append(n); n = self.parent_of[n]
+        return out[::-1]
+
+    def has_path_to(self, frm, to):              # laterN.pathTo(earlierN): edges point from a message to its parent
+        while frm is not None:
+            if frm == to:
+                return True
+            frm = self.parent_of[frm]
+        return False
+
+    # ---- Instrumenter: `!`, timers (enqueue_timer = enqueue_message = an immediate `!` from deadLetters, Scheduler.scala:73)
+    def tell(self, snd, rcv, msg):
+        if (rcv, msg) in self.timersCancelledThisStep:               # aroundDispatch :1090-1096
+            self.timersCancelledThisStep.discard((rcv, msg))
+            return
+        self.event_produced(snd, rcv, msg)
+
+    def registerCancellable(self, ongoing, rcv, msg):
+        if (rcv, msg) in self.timerToCancellable:
+            return
+        self.timerToCancellable[(rcv, msg)] = ongoing
+        self.handleTick(rcv, msg)
+
+    def handleTick(self, rcv, msg):
+        ongoing = self.timerToCancellable[(rcv, msg)]
+        self.tell(DEADLETTERS, rcv, msg)
+        if not ongoing:
+            del self.timerToCancellable[(rcv, msg)]
+
+    def cancelTimer(self, rcv, msg):
+        self.timersCancelledThisStep.add((rcv, msg))
+        self.timerToCancellable.pop((rcv, msg), None)
+        q = self.pending.get((DEADLETTERS, rcv))                     # notify_timer_cancel :961-985
+        if q is not None:
+            for i, (_, m) in enumerate(q):
+                if m == msg:
+                    del q[i]
+                    break
+
+    # ---- scheduler
+    def get_message(self, snd, rcv, msg):        # :773-801
+        for c in self.kids[self.parentEvent]:
+            if self.event[c] == (snd, rcv, msg):
+                return c
+        c = self.next_id
+        self.next_id += 1
+        self.event[c] = (snd, rcv, msg)
+        return c
+
+    def event_produced(self, snd, rcv, msg):     # :803-847
+        u = self.get_message(snd, rcv, msg)
+        self.pending.setdefault((snd, rcv), []).append((u, msg))
+        if u not in self.parent_of:                                  # addGraphNode + addEdge(unique, parentEvent)
+            self.parent_of[u] = self.parentEvent
+            self.kids[self.parentEvent].append(u)
+            self.kids[u] = []
+
+    def get_matching_message(self):              # :474-537 through getNextTraceMessage :363-372
+        while self.nextTrace:
+            u = self.nextTrace.pop(0)
+            if u == 0:
+                continue                                             # "All system messages need to ignored" (the root)
+            snd, rcv, _ = self.event[u]
+            q = self.pending.get((snd, rcv))
+            if q is not None:
+                for i, (v, m) in enumerate(q):
+                    if v == u:                                       # equivalentTo: same receiver and id
+                        del q[i]
+                        return (u, snd, rcv, m)
+            return None
+        return None
+
+    def get_pending_event(self):                 # :452-472
+        def order(key):
+            snd, rcv = key
+            return (10 ** 6 if snd == DEADLETTERS else int(snd), int(rcv))
+        for key in sorted(self.pending, key=order):
+            q = self.pending[key]
+            if q:
+                u, m = q.pop(0)
+                return (u, key[0], key[1], m)
+        return None
+
+    def schedule_new_message(self):              # :421-648
+        while True:
+            if self.foundLookingFor:
+                return None
+            self.messagesScheduledSoFar += 1
+            if self.messagesScheduledSoFar > self.max_messages:
+                return None
+            res = self.get_matching_message()
+            if res is None:
+                res = self.get_pending_event()
+            if res is None:
+                return None
+            u, snd, rcv, m = res
+            if snd in self.isolatedActors or rcv in self.isolatedActors:
+                continue                                             # "Discarding event ... due to not yet started node"
+            self.currentTrace.append(u)
+            self.parentEvent = u
+            return res
+
+    def run_interleaving(self):
+        self.actors = self.make_actors()
+        self.isolatedActors = set(self.actors)
+        self.pending = {}
+        self.timerToCancellable, self.timersCancelledThisStep = {}, set()
+        self.currentTrace = [0]
+        self.parentEvent = 0
+        self.messagesScheduledSoFar = 0
+        self.foundLookingFor = False
+        for e in self.externals:                                     # runExternal :684-721
+            if e[0] == "Start":
+                self.isolatedActors.discard(e[1])
+            elif e[0] == "Send":
+                self.tell(DEADLETTERS, e[1], e[2])
+            else:
+                raise ValueError("unsuported external event")
+        while True:
+            res = self.schedule_new_message()
+            if res is None:
+                break
+            u, snd, rcv, m = res
+            if self.timerToCancellable.get((rcv, m)):                # a repeating timer is re-armed after the hand-off
+                self.handleTick(rcv, m)
+            self.actors[rcv].receive(_DporContext(self, rcv), snd, m)
+        v = self.invariant(self.actors)                              # notify_quiescence -> checkInvariant :394-418
+        if v is not None and (self.lookingFor is None or v == self.lookingFor):
+            self.foundLookingFor = True
+            if self.shortestTraceSoFar is None or len(self.currentTrace) < len(self.shortestTraceSoFar):
+                self.shortestTraceSoFar = list(self.currentTrace)
+            return v
+        return None
+
+    def dpor(self, trace):                       # :1020-1185
+        self.interleavingCounter += 1
+        n = len(trace)
+        for laterI in range(n):
+            later = trace[laterI]
+            for earlierI in range(laterI):
+                earlier = trace[earlierI]
+                if self.event[earlier][1] != self.event[later][1]:   # isCoEnabeled: same receiver ...
+                    continue
+                if self.has_path_to(later, earlier):                 # ... and no dependency path from later to earlier
+                    continue
+                lp, ep = self.path_from_root(later), self.path_from_root(earlier)
+                common = [x for x in lp if x in ep]                  # laterPath.intersect(earlierPath)
+                branchI = trace.index(common[-1])
+                needToReplay = [x for x in trace[branchI + 1:laterI + 1] if x != earlier]
+                assert branchI < laterI
+                self.explored.add((earlier, later))
+                self.races += 1
+                self.backTrack.append((branchI, self.seq, (later, earlier), needToReplay))
+                self.seq += 1
+        while True:                                                  # getNext :1142-1162
+            if not self.backTrack or (self.stopIfViolationFound and self.shortestTraceSoFar is not None):
+                return None
+            best = max(range(len(self.backTrack)), key=lambda i: (self.backTrack[i][0], -self.backTrack[i][1]))
+            maxIndex, _, (e1, e2), replayThis = self.backTrack.pop(best)
+            if (e1, e2) in self.explored:
+                continue
+            self.explored.add((e1, e2))
+            return trace[:maxIndex + 1] + replayThis
+
+    def search(self, max_interleavings):
+        """test(): interleavings until the backtrack set is empty, a violation stops the search, or the budget is used."""
+        exhausted = False
+        while True:
+            v = self.run_interleaving()
+            k = len(self.traces)
+            self.traces.append(list(self.currentTrace))
+            if v is not None:
+                self.violations.append((k, v))
+                if self.stopIfViolationFound:
+                    break
+            if len(self.traces) >= max_interleavings:
+                break
+            nxt = self.dpor(self.currentTrace)
+            if nxt is None:
+                exhausted = not self.backTrack
+                break
+            self.nextTrace = nxt
+        return exhausted
+
+
+class _DporContext(object):
+    def __init__(self, s, name):
+        self.s, self.name = s, name
+
+    def send(self, dst, msg):
+        self.s.tell(self.name, dst, msg)
+
+    def schedule_repeating(self, msg):
+        self.s.registerCancellable(True, self.name, msg)
+
+    def schedule_once(self, msg):
+        self.s.registerCancellable(False, self.name, msg)
+
+    def cancel(self, msg):
+        self.s.cancelTimer(self.name, msg)
+
+
+def hash6(a, b, c, d, e, f):
+    """demi_hash6 (include/demi_limits.h): only used to compare schedules with the C oracle's per-interleaving hashes."""
+    M = (1 << 64) - 1
+    acc = (a * 0x9E3779B1 + b * 0x85EBCA77 + c * 0xC2B2AE3D + d * 0x27D4EB2F + e * 0x165667B1 + f * 0xD3A2646D + 0x6A09E667BB67AE85) & M
+    acc ^= acc >> 32
+    acc = (acc * 0x9E3779B97F4A7C15) & M
+    acc ^= acc >> 29
+    return acc
+
+
 # ---------------------------------------------------------------- DDMin (minification/DeltaDebugging.scala, Util.scala)
 def split_list(l, split_ways):                   # minification/Util.scala:9-37
     if split_ways < 1:

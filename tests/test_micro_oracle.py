@@ -225,3 +225,58 @@ def test_sts_replay_of_external_subsequences_matches_the_c_oracle(oracle):
         _, c = _replay_case(oracle, N.MODEL_PINGPONG3, D.pingpong3_program(20), seed, -1, 3, 1 | (4 << 8), 30, rng)
         n_checked += c
     assert n_viol >= 4 and n_checked >= 1200
+
+
+def _dpor_case(oracle, model, prog, flags, max_messages, budget, stop_if_found, looking_for=0):
+    ext = D.pack_externals(prog)
+    rc, r, viol, hashes = oracle.dpor_search(model, ext, max_messages, budget, looking_for=looking_for,
+                                             stop_if_found=1 if stop_if_found else 0, model_flags=flags)
+    assert rc == 0 and int(r["status"]) == 0
+    if model == N.MODEL_RAFT5:
+        make = lambda: {str(i): M.RaftActor(i, flags) for i in range(5)}
+        inv = M.raft_invariant
+    else:
+        make = lambda: {str(i): M.PingPongActor(i) for i in range(3)}
+        inv = M.pingpong_invariant(flags)
+    s = M.DPORSearch(make, to_prog(prog), inv, max_messages, stop_if_found=stop_if_found, looking_for=looking_for or None)
+    exhausted = s.search(budget)
+
+    def sched_hash(trace):
+        h = 0
+        for i, u in enumerate(trace):
+            if i == 0:
+                continue
+            snd, rcv, (t, p0, p1) = s.event[u]
+            h = (h + M.hash6(name_idx(snd) | (int(rcv) << 8) | (t << 16), p0, p1, i, 0, 0)) & ((1 << 64) - 1)
+        return h
+    assert len(s.traces) == int(r["interleavings"]), (len(s.traces), int(r["interleavings"]))
+    assert [sched_hash(t) for t in s.traces] == [int(h) for h in hashes]                      # the same schedules, in the same order
+    assert sum(len(t) - 1 for t in s.traces) == int(r["deliveries"])
+    assert s.races == int(r["races"]) and s.next_id == int(r["n_nodes"]) and len(s.explored) == int(r["n_explored"])
+    assert [(k, v) for k, v in s.violations] == [(int(x["interleaving"]), int(x["code"])) for x in viol]
+    assert bool(exhausted) == bool(r["exhausted"])
+    return len(s.traces), len(s.violations)
+
+
+def test_dpor_search_matches_the_c_oracle(oracle):
+    """DPORwHeuristics restated in Python straight from the Scala (graph of Uniques with child reuse, nextTrace matching,
+    the race scan with getCommonPrefix, ExploredTacker, getNext) against the C oracle: the same schedules in the same
+    order, the same counters, on exhaustive and budgeted raft5 / pingpong3 searches, with and without a seeded bug."""
+    rng = np.random.default_rng(11)
+    total = viols = 0
+    for trial in range(14):
+        starts = [int(a) for a in rng.permutation(5)]
+        boots = [int(a) for a in rng.permutation(5)[:int(rng.integers(2, 6))]]
+        prog = [D.Start(a) for a in starts] + [D.Send(a, 1, 0x1F) for a in boots]
+        if trial % 3 == 0:
+            prog.append(D.Send(int(rng.integers(0, 5)), 2, int(rng.integers(1, 50))))
+        flags = [0, 1, 3][trial % 3]
+        maxm = int(rng.integers(14, 30))
+        n, v = _dpor_case(oracle, N.MODEL_RAFT5, prog, flags, maxm, 400, stop_if_found=(trial % 2 == 0))
+        total += n; viols += v
+    n, v = _dpor_case(oracle, N.MODEL_RAFT5, [D.Start(a) for a in range(5)] + [D.Send(a, 1, 0x1F) for a in range(5)], 1, 60, 150, False)
+    total += n; viols += v
+    pprog = [D.Start(0), D.Start(1), D.Start(2), D.Send(2, 1, 0), D.Send(2, 1, 1), D.Send(0, 1, 2)]
+    n, v = _dpor_case(oracle, N.MODEL_PINGPONG3, pprog, 1 | (2 << 8), 40, 500, False, looking_for=7)
+    total += n; viols += v
+    assert total > 300 and viols > 0
