@@ -712,6 +712,70 @@ class STSReplay(Execution):
         return self.violationMatches(self.invariant(self.actors))
 
 
+# ---------------------------------------------------------------- internal-event minimization
+class LeftToRightOneAtATime(object):
+    """OneAtATimeStrategy + LeftToRightOneAtATime (internal_minimization/OneAtATimeRemoval.scala:17-137)."""
+
+    def __init__(self, verified_events, is_external):
+        from collections import Counter
+        self.triedIgnoring = Counter()
+        for e in verified_events:                                    # init(): external deliveries are unignorable
+            if e[0] == "MsgEvent" and is_external(e[3]):
+                self.triedIgnoring[(e[1], e[2], e[3])] += 1
+        self.unignorable = sum(self.triedIgnoring.values())
+
+    def getNextTrace(self, trace, alreadyRemoved, violationTriggered):
+        from collections import Counter
+        keysThisIteration = Counter(alreadyRemoved)
+        found = [False]
+
+        def checkDelivery(snd, rcv, msg):
+            key = (snd, rcv, msg)
+            keysThisIteration[key] += 1
+            if found[0]:
+                return True
+            if keysThisIteration[key] > self.triedIgnoring[key]:     # choiceFilter is `true`
+                found[0] = True
+                self.triedIgnoring[key] += 1
+                return False
+            return True
+        modified = [e for e in trace if e[0] != "MsgEvent" or checkDelivery(e[1], e[2], e[3])]
+        return modified if found[0] else None
+
+
+class STSSchedMinimizer(object):
+    """STSSchedMinimizer.minimize (internal_minimization/ScheduleCheckers.scala:19-107)."""
+
+    def __init__(self, mcs, verified_events, violation, strategy, test):
+        self.mcs, self.verified, self.violation, self.strategy, self.test = mcs, verified_events, violation, strategy, test
+        self.total_replays = 0
+        self.internal_sizes = []
+
+    def minimize(self):
+        from collections import Counter
+        count = lambda tr: sum(1 for e in tr if e[0] == "MsgEvent")
+        deliveries = lambda tr: Counter((e[1], e[2], e[3]) for e in tr if e[0] == "MsgEvent")
+        last = self.verified
+        lastSize = count(last)
+        prunedOverall = Counter()
+        triggered = False
+        nxt = self.strategy.getNextTrace(last, prunedOverall, triggered)
+        while nxt is not None:
+            self.total_replays += 1                                  # STSScheduler.test: stats.increment_replays
+            got = self.test(nxt)                                     # RunnerUtils.testWithStsSched -> Option[EventTrace]
+            if got is not None:
+                triggered = True
+                prunedOverall += deliveries(last) - deliveries(got)  # MultiSet.setDifference
+                last = got
+                lastSize = count(got)
+                self.internal_sizes.append(lastSize)
+            else:
+                triggered = False
+                self.internal_sizes.append(lastSize)
+            nxt = self.strategy.getNextTrace(last, prunedOverall, triggered)
+        return last
+
+
 # ---------------------------------------------------------------- DPORwHeuristics (schedulers/DPORwHeuristics.scala)
 class DPORSearch(object):
     """DPORwHeuristics.test for external programs of Start / Send events: DefaultBacktrackOrdering, trackHistory on,

@@ -280,3 +280,59 @@ def test_dpor_search_matches_the_c_oracle(oracle):
     n, v = _dpor_case(oracle, N.MODEL_PINGPONG3, pprog, 1 | (2 << 8), 40, 500, False, looking_for=7)
     total += n; viols += v
     assert total > 300 and viols > 0
+
+
+KIND_NAME = {1: "MsgSend", 2: "MsgEvent", 3: "Spawn", 4: "Kill", 5: "Partition", 6: "UnPartition", 7: "BeginWaitQuiescence", 8: "Quiescence"}
+
+
+def unflat(ev):
+    """C event records -> the tuples the micro-oracle works on."""
+    nm = lambda x: "Timer" if x == 0xFE else M.DEADLETTERS if x == 0xFF else str(x)
+    out = []
+    for e in ev:
+        k = KIND_NAME[int(e["kind"])]
+        if k in ("MsgSend", "MsgEvent"):
+            out.append((k, nm(int(e["src"])), str(int(e["dst"])), (int(e["type"]), int(e["p0"]), int(e["p1"])), int(e["uniq"]), 0))
+        elif k in ("Spawn", "Kill"):
+            out.append((k, str(int(e["dst"]))))
+        elif k in ("Partition", "UnPartition"):
+            out.append((k, str(int(e["src"])), str(int(e["dst"]))))
+        else:
+            out.append((k,))
+    return out
+
+
+def test_internal_minimization_matches_the_c_oracle(oracle):
+    """STSSchedMinimizer + LeftToRightOneAtATime restated in Python (on top of the Python STSScheduler) against
+    oracle_internal_minimize: the minimized schedule, the number of replays, the size series, the unignorable count."""
+    cases = 0
+    prog = D.raft5_program(client_cmds=2)
+    ext = D.pack_externals(prog)
+    res = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 400, 40, 5, model_flags=1)
+    for i in np.nonzero(res["violation"])[0][:4]:
+        seed = 1 + int(i)
+        ev, par, r = oracle.fuzz_trace(N.MODEL_RAFT5, ext, seed, 40, 5, model_flags=1)
+        code = int(r["violation"])
+        full = np.asarray(oracle.full_mask(ext), dtype=np.uint64).reshape(-1)
+        rr, vtrace = oracle.replay_trace(N.MODEL_RAFT5, ev, ext, full, looking_for=code, model_flags=1)
+        if int(rr["violation"]) != code:
+            continue
+        mcs_idx = [k for k in range(len(ext)) if (int(full[k >> 6]) >> (k & 63)) & 1]
+        mcs_prog = [prog[k] for k in mcs_idx]
+        mcs_ext = D.pack_externals(mcs_prog)
+        rc, ctrace, total, sizes, unig = oracle.internal_minimize(N.MODEL_RAFT5, vtrace, mcs_ext, code, model_flags=1)
+        assert rc == 0
+        mcs_events = to_prog(mcs_prog)
+        is_ext = lambda m: m[0] in (1, 2)
+
+        def test(candidate):
+            actors = {str(k): M.RaftActor(k, 1) for k in range(5)}
+            sts = M.STSReplay(actors, candidate, mcs_events, M.raft_invariant, is_ext, looking_for=code)
+            return sts.events if sts.test(list(range(len(mcs_events)))) == code else None
+        verified = unflat(vtrace)
+        sm = M.STSSchedMinimizer(mcs_events, verified, code, M.LeftToRightOneAtATime(verified, is_ext), test)
+        final = sm.minimize()
+        assert (sm.total_replays, sm.internal_sizes, sm.strategy.unignorable) == (total, [int(x) for x in sizes], unig), seed
+        assert [row[:7] for row in flat(final)] == [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in ctrace], seed
+        cases += 1
+    assert cases >= 2
