@@ -743,6 +743,72 @@ class LeftToRightOneAtATime(object):
         return modified if found[0] else None
 
 
+class SrcDstFIFORemoval(LeftToRightOneAtATime):
+    """SrcDstFIFORemoval (OneAtATimeRemoval.scala:139-251): only the last delivery of each (src, dst) FIFO is tried, plus
+    timers; the per-pair bookkeeping and its recomputation after a successful removal as written."""
+
+    def __init__(self, verified_events, is_external):
+        LeftToRightOneAtATime.__init__(self, verified_events, is_external)
+        self.verified = verified_events
+        self.srcDstToMessages = {}
+        for e in verified_events:
+            if e[0] == "MsgEvent" and e[1] != DEADLETTERS:
+                self.srcDstToMessages.setdefault((e[1], e[2]), []).append(e[3])
+        self.previouslyChosenSrcDst = None
+        self.srcDstToCurrentIdx = {}
+        self.reset_idx()
+
+    def reset_idx(self):
+        for k in self.srcDstToMessages:
+            self.srcDstToCurrentIdx[k] = -1
+
+    def choiceFilter(self, snd, rcv, msg):
+        key = (snd, rcv)
+        if key in self.srcDstToMessages:
+            self.srcDstToCurrentIdx[key] += 1
+            idx = self.srcDstToCurrentIdx[key]
+            lst = self.srcDstToMessages[key]
+            if idx == len(lst) - 1:
+                self.srcDstToMessages[key] = lst[:-1]
+                if not self.srcDstToMessages[key]:
+                    del self.srcDstToMessages[key]
+                self.previouslyChosenSrcDst = key
+                return True
+        self.previouslyChosenSrcDst = None
+        return snd == DEADLETTERS                                    # a timer
+
+    def getNextTrace(self, trace, alreadyRemoved, violationTriggered):
+        from collections import Counter
+        if not violationTriggered and self.previouslyChosenSrcDst is not None:
+            self.srcDstToMessages.pop(self.previouslyChosenSrcDst, None)
+        if violationTriggered:
+            self.srcDstToMessages = {}
+            left = Counter(alreadyRemoved)
+            for e in reversed(self.verified):
+                if e[0] == "MsgEvent" and e[1] != DEADLETTERS:
+                    t = (e[1], e[2], e[3])
+                    if left[t] > 0:
+                        left[t] -= 1
+                    else:
+                        self.srcDstToMessages[(e[1], e[2])] = [e[3]] + self.srcDstToMessages.get((e[1], e[2]), [])
+        self.reset_idx()
+        keysThisIteration = Counter(alreadyRemoved)
+        found = [False]
+
+        def checkDelivery(snd, rcv, msg):
+            key = (snd, rcv, msg)
+            keysThisIteration[key] += 1
+            if found[0]:
+                return True
+            if keysThisIteration[key] > self.triedIgnoring[key] and self.choiceFilter(snd, rcv, msg):
+                found[0] = True
+                self.triedIgnoring[key] += 1
+                return False
+            return True
+        modified = [e for e in trace if e[0] != "MsgEvent" or checkDelivery(e[1], e[2], e[3])]
+        return modified if found[0] else None
+
+
 class STSSchedMinimizer(object):
     """STSSchedMinimizer.minimize (internal_minimization/ScheduleCheckers.scala:19-107)."""
 

@@ -334,5 +334,12 @@ def test_internal_minimization_matches_the_c_oracle(oracle):
         final = sm.minimize()
         assert (sm.total_replays, sm.internal_sizes, sm.strategy.unignorable) == (total, [int(x) for x in sizes], unig), seed
         assert [row[:7] for row in flat(final)] == [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in ctrace], seed
+        # SrcDstFIFORemoval (OneAtATimeRemoval.scala:139-251)
+        rc, ftrace, ftotal, fsizes, funig = oracle.internal_minimize(N.MODEL_RAFT5, vtrace, mcs_ext, code, model_flags=1, flags=N.IM_SRC_DST_FIFO)
+        assert rc == 0
+        sf = M.STSSchedMinimizer(mcs_events, verified, code, M.SrcDstFIFORemoval(verified, is_ext), test)
+        ffinal = sf.minimize()
+        assert (sf.total_replays, sf.internal_sizes, sf.strategy.unignorable) == (ftotal, [int(x) for x in fsizes], funig), seed
+        assert [row[:7] for row in flat(ffinal)] == [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in ftrace], seed
         cases += 1
     assert cases >= 2
