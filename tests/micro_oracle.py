@@ -1057,6 +1057,120 @@ class DPORSearch(object):
         return exhausted
 
 
+class ResumableDPORInstance(DPORSearch):
+    """One DPORwHeuristics instance as RunnerUtils.editDistanceDporDDMin configures it (RunnerUtils.scala:822-835) and
+    ResumableDPOR drives it (IncrementalDeltaDebugging.scala:90-122): setInitialDepGraph / setInitialTrace,
+    prioritizePendingUponDivergence, ArvindDistanceOrdering (BacktrackOrdering.scala:99-173), setMaxDistance, and test()
+    called repeatedly (:1193-1242)."""
+
+    def __init__(self, make_actors, externals, invariant, max_messages, init_nodes=None, init_trace=None, arvind=False,
+                 prioritize_pending=False, stop_if_found=True, looking_for=None):
+        DPORSearch.__init__(self, make_actors, externals, invariant, max_messages, stop_if_found, looking_for)
+        self.arvind, self.prioritize = arvind, prioritize_pending
+        self.init_trace = list(init_trace) if init_trace is not None else None
+        self.originalIndices = {}
+        if init_nodes is not None:                                   # depGraph ++= initialGraph
+            for i, (snd, rcv, msg, par) in enumerate(init_nodes):
+                if i == 0:
+                    continue
+                self.event[i] = (snd, rcv, msg)
+                self.parent_of[i] = par
+                self.kids.setdefault(par, []).append(i)
+                self.kids.setdefault(i, [])
+            self.next_id = len(init_nodes)
+        if self.init_trace is not None:
+            for i, e in enumerate(self.init_trace):                  # ArvindDistanceOrdering.init: later occurrences overwrite
+                self.originalIndices[e] = i
+        self.started = False
+        self.currentTrace = []
+        self.max_distance = None
+
+    def get_matching_message(self):              # getNextMatchingMessage :542-555 when prioritizePendingUponDivergence
+        res = DPORSearch.get_matching_message(self)
+        while res is None and self.prioritize and self.nextTrace:
+            res = DPORSearch.get_matching_message(self)
+        return res
+
+    def distance(self, key):                     # arvindDistance :119-146 (DefaultBacktrackOrdering: 0)
+        if not self.arvind:
+            return 0
+        _, _, (e1, e2), replayThis = key
+        path = self.path_from_root(e1) + list(replayThis) + [e1, e2]
+        d = 0
+        for i, e in enumerate(path):
+            if e not in self.originalIndices:
+                d += 1
+            else:
+                for pred in path[:i]:
+                    if pred in self.originalIndices and self.originalIndices[pred] > self.originalIndices[e]:
+                        d += 1
+        return d
+
+    def dpor(self, trace):
+        self.interleavingCounter += 1
+        n = len(trace)
+        for laterI in range(n):
+            later = trace[laterI]
+            for earlierI in range(laterI):
+                earlier = trace[earlierI]
+                if self.event[earlier][1] != self.event[later][1] or self.has_path_to(later, earlier):
+                    continue
+                lp, ep = self.path_from_root(later), self.path_from_root(earlier)
+                common = [x for x in lp if x in ep]
+                branchI = trace.index(common[-1])
+                needToReplay = [x for x in trace[branchI + 1:laterI + 1] if x != earlier]
+                self.explored.add((earlier, later))
+                self.races += 1
+                key = (branchI, self.seq, (later, earlier), needToReplay)
+                # a key's distance never changes (the graph only grows below its events): computed once, like the
+                # ordering's `distances` cache (:107, :148-154)
+                self.backTrack.append(key + (self.distance(key),))
+                self.seq += 1
+        while True:                                                  # getNext :1142-1162
+            if not self.backTrack:
+                return None
+            rank = lambda i: (self.backTrack[i][4], self.backTrack[i][0], -self.backTrack[i][1])
+            best = max(range(len(self.backTrack)), key=rank)          # the larger distance is served first, as written
+            if self.max_distance is not None and self.backTrack[best][4] >= self.max_distance:
+                return None
+            if self.stopIfViolationFound and self.shortestTraceSoFar is not None:
+                return None
+            maxIndex, _, (e1, e2), replayThis, _ = self.backTrack.pop(best)
+            if (e1, e2) in self.explored:
+                continue
+            self.explored.add((e1, e2))
+            return trace[:maxIndex + 1] + replayThis
+
+    def test(self, max_distance, max_interleavings):
+        """One DPORwHeuristics.test after ResumableDPOR's setMaxDistance.  Returns (traces run in this call, found)."""
+        if self.stopIfViolationFound and self.shortestTraceSoFar is not None:
+            return [], True                                          # "Already have shortestTrace!"
+        self.max_distance = None if max_distance < 0 else max_distance
+        nxt = None
+        if self.started and self.backTrack:
+            nxt = self.dpor(self.currentTrace)                       # startFromBackTrackPoints :1219-1220
+        elif self.init_trace is not None:
+            nxt = list(self.init_trace)
+        self.nextTrace = list(nxt) if nxt is not None else []
+        self.started = True
+        ran, found = [], False
+        while len(self.traces) < max_interleavings:
+            v = self.run_interleaving()
+            k = len(self.traces)
+            self.traces.append(list(self.currentTrace)); ran.append(list(self.currentTrace))
+            if v is not None:
+                self.violations.append((k, v)); found = True
+                if self.stopIfViolationFound:
+                    break
+            if len(self.traces) >= max_interleavings:
+                break
+            nxt = self.dpor(self.currentTrace)
+            if nxt is None:
+                break
+            self.nextTrace = nxt
+        return ran, found
+
+
 class _DporContext(object):
     def __init__(self, s, name):
         self.s, self.name = s, name

@@ -343,3 +343,43 @@ def test_internal_minimization_matches_the_c_oracle(oracle):
         assert [row[:7] for row in flat(ffinal)] == [tuple(int(e[f]) for f in ("kind", "src", "dst", "type", "p0", "p1", "uniq")) for e in ftrace], seed
         cases += 1
     assert cases >= 2
+
+
+def test_resumable_edit_distance_dpor_matches_the_c_oracle(oracle):
+    """The configuration IncrementalDDMin drives (seeded dependency graph + initial trace, prioritizePendingUponDivergence,
+    ArvindDistanceOrdering, setMaxDistance, repeated test() calls on one instance), restated in Python, against
+    oracle_dpor_open / oracle_dpor_test: per call the same schedules, the same verdict, the same graph and history sizes."""
+    nm = lambda x: M.DEADLETTERS if x == 0xFF else str(x)
+    ext_all = D.pack_externals(D.raft5_program())
+    dprog = [e for e in D.raft5_program() if type(e).__name__ in ("Start", "Send")]
+    dext = D.pack_externals(dprog)
+    checked = 0
+    for seed_index, caps, arv in ((100, [0, 2, 4, 8, -1], 1), (1, [0, 2, -1], 1), (7, [0, 0, 2, 4, 16], 1), (100, [-1], 0), (33, [0, 4, -1, -1], 1)):
+        ev, par, r = oracle.fuzz_trace(N.MODEL_RAFT5, ext_all, 1 + seed_index, 40, 5, model_flags=1)
+        m = int(r["steps"])
+        nodes, trace = oracle.dpor_seed(ev, par)
+        inst = oracle.DporInstance(N.MODEL_RAFT5, dext, m, 300, seed=(nodes, trace), arvind=arv, prioritize_pending=1, model_flags=1,
+                                   looking_for=1)
+        init_nodes = [(nm(int(w[0]) & 0xFF), str((int(w[0]) >> 8) & 0xFF), ((int(w[0]) >> 16) & 0xFF, int(w[1]), int(w[2])), int(w[3])) for w in nodes]
+        py = M.ResumableDPORInstance(lambda: {str(i): M.RaftActor(i, 1) for i in range(5)}, to_prog(dprog), M.raft_invariant, m,
+                                     init_nodes=init_nodes, init_trace=[int(x) for x in trace], arvind=bool(arv), prioritize_pending=True,
+                                     stop_if_found=True, looking_for=1)
+
+        def sched_hash(tr):
+            h = 0
+            for i, u in enumerate(tr):
+                if i:
+                    snd, rcv, (t, p0, p1) = py.event[u]
+                    h = (h + M.hash6(name_idx(snd) | (int(rcv) << 8) | (t << 16), p0, p1, i, 0, 0)) & ((1 << 64) - 1)
+            return h
+        for cap in caps:
+            races_before = py.races
+            rc, hashes = inst.test(cap)
+            ran, found = py.test(cap, 300)
+            assert int(rc["status"]) == 0
+            assert (len(ran), bool(found)) == (int(rc["interleavings"]), int(rc["violations"]) > 0), (seed_index, cap)
+            assert [sched_hash(t) for t in ran] == [int(h) for h in hashes], (seed_index, cap)
+            assert (py.races - races_before, py.next_id, len(py.explored)) == (int(rc["races"]), int(rc["n_nodes"]), int(rc["n_explored"])), (seed_index, cap)
+            checked += 1
+        inst.close()
+    assert checked >= 15
