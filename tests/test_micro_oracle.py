@@ -383,3 +383,50 @@ def test_resumable_edit_distance_dpor_matches_the_c_oracle(oracle):
             checked += 1
         inst.close()
     assert checked >= 15
+
+
+def test_incremental_ddmin_over_resumable_dpor_matches_the_c_oracle(oracle):
+    """IncrementalDDMin (IncrementalDeltaDebugging.scala:20-88) over ResumableDPOR (:90-122): the Python DDMin drives one
+    Python DPOR instance per external subsequence with growing distance caps; MCS, total replays, rounds and the number
+    of instances equal oracle_incremental_ddmin's."""
+    nm = lambda x: M.DEADLETTERS if x == 0xFF else str(x)
+    ext_all = D.pack_externals(D.raft5_program())
+    dprog = [e for e in D.raft5_program() if type(e).__name__ in ("Start", "Send")]
+    dext = D.pack_externals(dprog)
+    devents = to_prog(dprog)
+    done = 0
+    for seed_index in (1, 7):
+        ev, par, r = oracle.fuzz_trace(N.MODEL_RAFT5, ext_all, 1 + seed_index, 40, 5, model_flags=1)
+        if int(r["violation"]) != 1:
+            continue
+        m = int(r["steps"])
+        nodes, trace = oracle.dpor_seed(ev, par)
+        rc, cmcs, info = oracle.incremental_ddmin(N.MODEL_RAFT5, dext, m, 60, (nodes, trace), max_max_distance=8, stop_at_size=1,
+                                                  looking_for=1, model_flags=1)
+        assert rc == 0
+        init_nodes = [(nm(int(w[0]) & 0xFF), str((int(w[0]) >> 8) & 0xFF), ((int(w[0]) >> 16) & 0xFF, int(w[1]), int(w[2])), int(w[3])) for w in nodes]
+        instances = {}
+        state = {"dist": 0}
+
+        def test(sub):                                               # ResumableDPOR.test
+            key = tuple(id(e) for e in sub)
+            if key not in instances:
+                instances[key] = M.ResumableDPORInstance(lambda: {str(i): M.RaftActor(i, 1) for i in range(5)}, list(sub), M.raft_invariant, m,
+                                                         init_nodes=init_nodes, init_trace=[int(x) for x in trace], arvind=True,
+                                                         prioritize_pending=True, stop_if_found=True, looking_for=1)
+            return instances[key].test(state["dist"], 60)[1]
+        current = list(enumerate(devents))
+        total = rounds = 0
+        sizes = []
+        while state["dist"] < 8 and len(current) > 1:
+            dd = M.DDMin(test)
+            current = dd.ddmin2(current, [])
+            total += dd.total_replays
+            rounds += 1
+            sizes.append(len(current))
+            state["dist"] = 2 if state["dist"] == 0 else state["dist"] << 1
+        mask = sum(1 << i for i, _ in current)
+        assert (mask, total, rounds, len(instances)) == (int(cmcs[0]), info["total_replays"], info["rounds"], info["instances"]), seed_index
+        assert sizes == [int(x) for x in info["mcs_sizes"]]
+        done += 1
+    assert done >= 1
