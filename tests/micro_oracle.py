@@ -712,6 +712,54 @@ class STSReplay(Execution):
         return self.violationMatches(self.invariant(self.actors))
 
 
+# ---------------------------------------------------------------- ProvenanceTracker (schedulers/Util.scala:267-376)
+class ProvenanceTracker(object):
+    """trace: [(unique id, receiver name)] = DepTracker.initialTrace (the root first); parent_of: the DepTracker tree.
+    happensBefore = first-order pairs (same receiver, earlier or the event itself; a receive and the messages sent as
+    its result) closed transitively — by plain reachability here, the relation is what matters."""
+
+    def __init__(self, trace, parent_of):
+        self.trace = trace
+        kids = {}
+        for c, p in parent_of.items():
+            if p is not None:
+                kids.setdefault(p, []).append(c)
+        first = set()
+        prior = {}
+        for u, rcv in trace:
+            prior.setdefault(rcv, []).append(u)
+            for p in prior[rcv]:
+                first.add((p, u))
+            for c in kids.get(u, []):
+                first.add((u, c))
+        succ = {}
+        for a, b in first:
+            if a != b:
+                succ.setdefault(a, set()).add(b)
+        verts = set(x for pr in first if pr[0] != pr[1] for x in pr)
+        self.hb = set(first)
+        for v in verts:                                              # v's transitive closure includes v itself
+            seen, stack = {v}, [v]
+            while stack:
+                x = stack.pop()
+                for y in succ.get(x, ()):
+                    if y not in seen:
+                        seen.add(y); stack.append(y)
+            for y in seen:
+                self.hb.add((v, y))
+
+    def pruneConcurrentEvents(self, affected_nodes):
+        last = []
+        for node in affected_nodes:                                  # findLastEventForNode
+            for u, rcv in reversed(self.trace):
+                if rcv == node:
+                    last.append(u)
+                    break
+        def concurrent_or_after_all(u):
+            return all((not ((o, u) in self.hb or (u, o) in self.hb)) or (o, u) in self.hb for o in last)
+        return [i for i, (u, _) in enumerate(self.trace) if not concurrent_or_after_all(u)]
+
+
 # ---------------------------------------------------------------- internal-event minimization
 class LeftToRightOneAtATime(object):
     """OneAtATimeStrategy + LeftToRightOneAtATime (internal_minimization/OneAtATimeRemoval.scala:17-137)."""

@@ -430,3 +430,27 @@ def test_incremental_ddmin_over_resumable_dpor_matches_the_c_oracle(oracle):
         assert sizes == [int(x) for x in info["mcs_sizes"]]
         done += 1
     assert done >= 1
+
+
+def test_provenance_pruning_matches_the_c_oracle(oracle):
+    """ProvenanceTracker.pruneConcurrentEvents restated in Python (closure by plain reachability) against the C oracle's
+    literal restatement (topological sweep): the same deliveries are kept."""
+    ext = D.pack_externals(D.raft5_program())
+    res = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, 2000, 50, 5, model_flags=1)
+    viol = np.nonzero(res["violation"])[0][:25]
+    assert len(viol) >= 10
+    kept_any = 0
+    for i in viol:
+        seed = 1 + int(i)
+        ev, par, r = oracle.fuzz_trace(N.MODEL_RAFT5, ext, seed, 50, 5, model_flags=1)
+        keep, out = oracle.fuzz_provenance(N.MODEL_RAFT5, ext, seed, 50, 5, 1, model_flags=1)
+        assert int(out["status"]) == 0
+        affected = [str(a) for a in range(5) if (int(out["affected_mask"]) >> a) & 1]
+        trace = [(0, "null")] + [(int(e["node"]), str(int(e["dst"]))) for e in ev if int(e["kind"]) == 2]
+        parent_of = {k: (int(par[k]) if k else None) for k in range(len(par))}
+        pt = M.ProvenanceTracker(trace, parent_of)
+        kept = pt.pruneConcurrentEvents(affected)
+        assert kept == [t for t in range(len(trace)) if (int(keep[t >> 6]) >> (t & 63)) & 1], seed
+        assert len(kept) == int(out["n_kept"]) and len(trace) == int(out["n_trace"])
+        kept_any += bool(kept)
+    assert kept_any >= 10
