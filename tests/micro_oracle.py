@@ -272,7 +272,24 @@ class Execution(object):
             if self.violationFound is not None:
                 return None
         self.send_external_messages()
-        if self.pendingEvents.isEmpty():                             # find_non_blocked_message (Util.scala:470-489)
+        e = self.pick_non_blocked()
+        if e is None:
+            return None
+        uniq, unique, snd, rcv, msg = e
+        self.messagesScheduledSoFar += 1
+        self.events.append(("MsgEvent", snd, rcv, msg, uniq, unique.id))
+        self.depTracker.reportNewlyDelivered(unique)
+        if (rcv, msg) in self.timerToCancellable:                    # updateRepeatingTimer :405-421
+            self.justScheduledTimers.add((rcv, msg))
+        else:
+            for r, t in self.timersToResend:
+                self.handle_timer(r, t)
+            self.timersToResend = []
+            self.justScheduledTimers.clear()
+        return e
+
+    def pick_non_blocked(self):                  # find_non_blocked_message (Util.scala:470-489) over the strategy
+        if self.pendingEvents.isEmpty():
             return None
         blocked = []
         e = self.strategy_removeRandomElement()
@@ -285,17 +302,6 @@ class Execution(object):
             e = self.strategy_removeRandomElement()
         for b in blocked:
             self.pendingEvents.insert(b)
-        uniq, unique, snd, rcv, msg = e
-        self.messagesScheduledSoFar += 1
-        self.events.append(("MsgEvent", snd, rcv, msg, uniq, unique.id))
-        self.depTracker.reportNewlyDelivered(unique)
-        if (rcv, msg) in self.timerToCancellable:                    # updateRepeatingTimer :405-421
-            self.justScheduledTimers.add((rcv, msg))
-        else:
-            for r, t in self.timersToResend:
-                self.handle_timer(r, t)
-            self.timersToResend = []
-            self.justScheduledTimers.clear()
         return e
 
     def strategy_removeRandomElement(self):      # FullyRandom.removeRandomElement (:666-684), as written
@@ -331,6 +337,79 @@ class Execution(object):
         if self.violationFound is None and self.messagesScheduledSoFar <= self.maxMessages:   # explore :256 + checkIfBugFound
             self.violationFound = self.violationMatches(self.invariant(self.actors))
         return self.violationFound
+
+
+class SrcDstFifoExecution(Execution):
+    """RandomScheduler over the SrcDstFIFO strategy (RandomScheduler.scala:702-870): one FIFO per (src, dst) pair, timers
+    and externals in a FullyRandom of their own.  The reference seeds both generators from the clock; here both are
+    java.util.Random(seed), the convention DESIGN.md states for the `seed parameter added` to the strategy."""
+
+    def __init__(self, *a, **kw):
+        Execution.__init__(self, *a, **kw)
+        seed = a[2]
+        self.timersAndExternals = self.pendingEvents              # the FullyRandom(seed) Execution made
+        self.rand = JavaRandom(seed)
+        self.srcDsts = []
+        self.srcDstToMessages = {}
+        outer = self
+
+        class View(object):                                          # what Execution touches of `pendingEvents`
+            def insert(_, t):                                        # SrcDstFIFO.+= (:786-805)
+                if t[2] == DEADLETTERS:
+                    outer.timersAndExternals.insert(t)
+                    return
+                key = (t[2], t[3])
+                if key not in outer.srcDstToMessages:
+                    outer.srcDsts.append(key)
+                    outer.srcDstToMessages[key] = []
+                outer.srcDstToMessages[key].append(t)
+
+            def remove(_, t):                                        # only timers are ever removed (cancel)
+                outer.timersAndExternals.remove(t)
+
+            @property
+            def arr(_):
+                return outer.timersAndExternals.arr + [(t, 0) for q in outer.srcDstToMessages.values() for t in q]
+
+            def isEmpty(_):
+                return not outer.timersAndExternals.arr and not outer.srcDstToMessages
+        self.pendingEvents = View()
+
+    def _timer_non_blocked(self):                # find_non_blocked_message over timersAndExternals
+        te = self.timersAndExternals
+        if te.isEmpty():
+            return None
+        blocked = []
+        e = te.removeRandomElement()
+        while e[3] in self.blockedActors:
+            blocked.append(e)
+            if te.isEmpty():
+                for b in blocked:
+                    te.insert(b)
+                return None
+            e = te.removeRandomElement()
+        for b in blocked:
+            te.insert(b)
+        return e
+
+    def pick_non_blocked(self):                  # getNonBlockedMessage (:716-756) + dequeue (:758-768)
+        if not any(k[1] not in self.blockedActors for k in self.srcDstToMessages):
+            return self._timer_non_blocked()                         # "Only timers left"
+        n_all = len(self.timersAndExternals.arr) + sum(len(q) for q in self.srcDstToMessages.values())
+        if self.rand.nextInt(n_all) < len(self.timersAndExternals.arr):
+            t = self._timer_non_blocked()
+            if t is not None:
+                return t
+        idx = self.rand.nextInt(len(self.srcDsts))
+        while self.srcDsts[idx][1] in self.blockedActors:
+            idx = self.rand.nextInt(len(self.srcDsts))
+        key = self.srcDsts[idx]
+        q = self.srcDstToMessages[key]
+        ret = q.pop(0)
+        if not q:
+            del self.srcDstToMessages[key]
+            del self.srcDsts[idx]
+        return ret
 
 
 class Context(object):

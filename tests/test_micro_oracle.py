@@ -52,7 +52,7 @@ def flat(events):
     return rows
 
 
-def run_micro(model, prog, seed, maxm, interval, flags, rules=()):
+def run_micro(model, prog, seed, maxm, interval, flags, rules=(), strategy=0):
     if model == N.MODEL_RAFT5:
         fresh = lambda name: M.RaftActor(int(name), flags)
         actors = {str(i): fresh(str(i)) for i in range(5)}
@@ -69,8 +69,9 @@ def run_micro(model, prog, seed, maxm, interval, flags, rules=()):
             if src_ok and (dst_mask >> int(rcv)) & 1 and (type_mask >> msg[0]) & 1:
                 return False
         return True
-    ex = M.Execution(actors, to_prog(prog), seed, maxm, interval, inv, lambda m: m[0] in ext_types,
-                     user_filter=user_filter if rules else None, fresh_actor=fresh)
+    cls = M.SrcDstFifoExecution if strategy == 1 else M.Execution
+    ex = cls(actors, to_prog(prog), seed, maxm, interval, inv, lambda m: m[0] in ext_types,
+             user_filter=user_filter if rules else None, fresh_actor=fresh)
     v = ex.run()
     return ex, (v or 0)
 
@@ -454,3 +455,20 @@ def test_provenance_pruning_matches_the_c_oracle(oracle):
         assert len(kept) == int(out["n_kept"]) and len(trace) == int(out["n_trace"])
         kept_any += bool(kept)
     assert kept_any >= 10
+
+
+def test_src_dst_fifo_strategy_matches_the_c_oracle(oracle):
+    """RandomScheduler over SrcDstFIFO (RandomScheduler.scala:702-870): verdicts, counters and the whole EventTrace."""
+    for prog, maxm, interval, flags, n in ((D.raft5_program(), 50, 5, 1, 300), (D.raft5_program(client_cmds=3), 120, 7, 3, 150)):
+        ext = D.pack_externals(prog)
+        res = oracle.fuzz_batch(N.MODEL_RAFT5, ext, 1, n, maxm, interval, model_flags=flags, strategy=1)
+        for k in range(n):
+            seed = 1 + k
+            ex, v = run_micro(N.MODEL_RAFT5, prog, seed, maxm, interval, flags, strategy=1)
+            r = res[k]
+            assert (int(r["violation"]), int(r["steps"]), int(r["n_nodes"]), int(r["n_events"]), int(r["max_pending"]), int(r["status"])) == \
+                   (v, ex.messagesScheduledSoFar, ex.depTracker.next_id, len(ex.events), ex.max_pending, 0), seed
+            if k % 10 == 0:
+                ev, par, _ = oracle.fuzz_trace(N.MODEL_RAFT5, ext, seed, maxm, interval, model_flags=flags, strategy=1)
+                got = [(int(e["kind"]), int(e["src"]), int(e["dst"]), int(e["type"]), int(e["p0"]), int(e["p1"]), int(e["uniq"]), int(e["node"])) for e in ev]
+                assert got == flat(ex.events), seed
